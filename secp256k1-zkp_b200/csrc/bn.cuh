@@ -1,0 +1,215 @@
+// bn.cuh -- 256-bit big-number primitives for sm_100a.
+//
+// Representation: 8 x uint32 little-endian limbs == the reference's packed
+// `secp256k1_fe_storage` / `secp256k1_scalar` 4x64 form (field_5x52.h:45-47,
+// scalar_4x64.h:13-15) viewed as 32-bit words.  The B200 integer datapath is
+// 32-bit: one 64x64->128 product of the reference's 5x52 schedule costs four
+// IMAD.WIDE.U32, so a 5x52 fe_mul is 124 MACs while the saturated
+// 8x32 schedule below is 64 + 8 MACs.  Loads/stores and results are the
+// reference's 4x64 forms; only the in-register limb schedule differs.
+//
+// Device path: inline PTX mad.lo.cc/madc.hi.cc chains which ptxas fuses into
+// IMAD.WIDE.U32(.X) (checked with cuobjdump: 64 products -> 64 IMAD.WIDE).
+// The "even/odd column" split keeps every chain free of 32-bit-misaligned
+// carries.  A portable C path (uint64_t accumulators) is used when compiled
+// for the host (tests/hostemu) or with -DB200_PORTABLE_BN (on-device A/B check).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define HD __host__ __device__ __forceinline__
+#define HDNI __host__ __device__ __noinline__
+#else
+#define HD inline
+#define HDNI
+#endif
+
+#ifndef B200_NS
+#define B200_NS b200
+#endif
+
+#if defined(__CUDA_ARCH__) && !defined(B200_PORTABLE_BN)
+#define BN_PTX 1
+#else
+#define BN_PTX 0
+#endif
+
+namespace B200_NS {
+
+#if BN_PTX
+// acc[0..8] += (a0 + a1*2^64 + a2*2^128 + a3*2^192) * b   (a_i, b 32-bit; four aligned 64-bit products)
+__device__ __forceinline__ void bn_cmad4(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+    asm("mad.lo.cc.u32  %0, %9,  %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9,  %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32       %8, %8, 0;\n\t"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+#endif
+
+// r[0..15] = a[0..7] * b[0..7]
+HD void bn_mul_wide(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#if BN_PTX
+    uint32_t e[17], o[17];
+#pragma unroll
+    for (int i = 0; i < 17; i++) { e[i] = 0; o[i] = 0; }
+    // e[k] holds weight 2^(32k) for products whose column is even, o[k] weight 2^(32(k+1)) for odd columns
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        bn_cmad4(e + i, a[0], a[2], a[4], a[6], b[i]);          // columns i+0,2,4,6   (even)
+        bn_cmad4(o + i, a[1], a[3], a[5], a[7], b[i]);          // columns i+1,3,5,7   (odd)
+        bn_cmad4(o + i, a[0], a[2], a[4], a[6], b[i + 1]);      // columns i+1+0,2,..  (odd)
+        bn_cmad4(e + i + 2, a[1], a[3], a[5], a[7], b[i + 1]);  // columns i+2,4,..    (even)
+    }
+    r[0] = e[0];
+    uint32_t cmid, cdummy;
+    asm("add.cc.u32  %0, %9,  %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32    %8, 0, 0;\n\t"
+        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(cmid)
+        : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(e[8]),
+          "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]));
+    // the carry is handed over in a register (cmid) and re-materialised with add.cc cmid + 0xffffffff,
+    // so no statement depends on the CC flag surviving between two asm blocks.
+    asm("add.cc.u32  %7, %22, 0xffffffff;\n\t"
+        "addc.cc.u32 %0, %8,  %15;\n\t"
+        "addc.cc.u32 %1, %9,  %16;\n\t"
+        "addc.cc.u32 %2, %10, %17;\n\t"
+        "addc.cc.u32 %3, %11, %18;\n\t"
+        "addc.cc.u32 %4, %12, %19;\n\t"
+        "addc.cc.u32 %5, %13, %20;\n\t"
+        "addc.u32    %6, %14, %21;\n\t"
+        : "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(cdummy)
+        : "r"(e[9]), "r"(e[10]), "r"(e[11]), "r"(e[12]), "r"(e[13]), "r"(e[14]), "r"(e[15]),
+          "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(cmid));
+    (void)cdummy;
+#else
+    // column sums of low/high halves kept apart so nothing overflows 64 bits
+    uint32_t out[16];
+    uint64_t carry = 0;
+    for (int k = 0; k < 15; k++) {
+        uint64_t lo = carry & 0xffffffffu, hi = carry >> 32;
+        for (int i = 0; i < 8; i++) {
+            int j = k - i;
+            if (j < 0 || j > 7) continue;
+            uint64_t p = (uint64_t)a[i] * b[j];
+            lo += p & 0xffffffffu;
+            hi += p >> 32;
+        }
+        out[k] = (uint32_t)lo;
+        carry = hi + (lo >> 32);
+    }
+    out[15] = (uint32_t)carry;
+    for (int i = 0; i < 16; i++) r[i] = out[i];
+#endif
+}
+
+// r[0..15] = a[0..7]^2
+HD void bn_sqr_wide(uint32_t* r, const uint32_t* a) {
+    bn_mul_wide(r, a, a);
+}
+
+// r = a + b, returns carry (0/1)
+HD uint32_t bn_add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#if BN_PTX
+    uint32_t c;
+    asm("add.cc.u32  %0, %9,  %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32    %8, 0, 0;\n\t"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return c;
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)a[i] + b[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    return (uint32_t)c;
+#endif
+}
+
+// r = a - b, returns borrow (0/1)
+HD uint32_t bn_sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#if BN_PTX
+    uint32_t c;
+    asm("sub.cc.u32  %0, %9,  %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32    %8, 0, 0;\n\t"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return c & 1u;   // subc.u32 0-0-borrow = 0xffffffff when borrow
+#else
+    int64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        c += (int64_t)a[i] - (int64_t)b[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;  // arithmetic shift: 0 or -1
+    }
+    return (uint32_t)(c & 1);
+#endif
+}
+
+// compare a >= b (both 8 limbs)
+HD int bn_gte8(const uint32_t* a, const uint32_t* b) {
+    uint32_t t[8];
+    return bn_sub8(t, a, b) == 0;
+}
+
+HD int bn_is_zero8(const uint32_t* a) {
+    uint32_t x = a[0] | a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7];
+    return x == 0;
+}
+
+HD int bn_eq8(const uint32_t* a, const uint32_t* b) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x |= a[i] ^ b[i];
+    return x == 0;
+}
+
+// 32 big-endian bytes -> 8 LE limbs
+HD void bn_from_be32(uint32_t* r, const uint8_t* b) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint8_t* p = b + 4 * (7 - i);
+        r[i] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+    }
+}
+HD void bn_to_be32(uint8_t* b, const uint32_t* a) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint8_t* p = b + 4 * (7 - i);
+        p[0] = (uint8_t)(a[i] >> 24); p[1] = (uint8_t)(a[i] >> 16); p[2] = (uint8_t)(a[i] >> 8); p[3] = (uint8_t)a[i];
+    }
+}
+
+}  // namespace B200_NS

@@ -1,0 +1,77 @@
+// tests/hostemu/hostemu.cpp -- TEST-ONLY host build of the device headers (HD functions compile
+// as plain C++ when __CUDACC__ is undefined, using the portable big-number path).
+// Lets the CPU-only test tier check the group law / ecmult / verify LOGIC against the oracle
+// without a GPU.  Never linked into, nor loaded by, the product library.
+#include "../../secp256k1-zkp_b200/csrc/fe.cuh"
+using namespace b200;
+extern "C" {
+void emu_fe_mul(uint8_t* r, const uint8_t* a, const uint8_t* b) { fe x, y, z; fe_set_b32(x, a); fe_set_b32(y, b); fe_mul(z, x, y); fe_get_b32(r, z); }
+void emu_fe_sqr(uint8_t* r, const uint8_t* a) { fe x, z; fe_set_b32(x, a); fe_sqr(z, x); fe_get_b32(r, z); }
+void emu_fe_add(uint8_t* r, const uint8_t* a, const uint8_t* b) { fe x, y, z; fe_set_b32(x, a); fe_set_b32(y, b); fe_add(z, x, y); fe_get_b32(r, z); }
+void emu_fe_sub(uint8_t* r, const uint8_t* a, const uint8_t* b) { fe x, y, z; fe_set_b32(x, a); fe_set_b32(y, b); fe_sub(z, x, y); fe_get_b32(r, z); }
+void emu_fe_neg(uint8_t* r, const uint8_t* a) { fe x, z; fe_set_b32(x, a); fe_neg(z, x); fe_get_b32(r, z); }
+void emu_fe_half(uint8_t* r, const uint8_t* a) { fe x, z; fe_set_b32(x, a); fe_half(z, x); fe_get_b32(r, z); }
+void emu_fe_mul_small(uint8_t* r, const uint8_t* a, uint32_t k) { fe x, z; fe_set_b32(x, a); fe_mul_small(z, x, k); fe_get_b32(r, z); }
+void emu_fe_inv(uint8_t* r, const uint8_t* a) { fe x, z; fe_set_b32(x, a); fe_inv(z, x); fe_get_b32(r, z); }
+int emu_fe_sqrt(uint8_t* r, const uint8_t* a) { fe x, z; fe_set_b32(x, a); int ok = fe_sqrt(z, x); fe_get_b32(r, z); return ok; }
+int emu_fe_is_zero(const uint8_t* a) { fe x; fe_set_b32(x, a); return fe_is_zero(x); }
+}
+
+// ---- scalar / group / ecmult / verify logic -------------------------------
+#include "../../secp256k1-zkp_b200/csrc/gtable.cuh"
+#include "../../secp256k1-zkp_b200/csrc/verify.cuh"
+#include <vector>
+#include <string.h>
+static std::vector<uint32_t> g_tab;
+static ecmult_gtable g_gt = {nullptr, 0, 0};
+static bip340_midstate g_mid;
+static void ge_from_xy64(ge& p, const uint8_t* xy) {
+    int z = 1; for (int i = 0; i < 64; i++) z &= (xy[i] == 0);
+    if (z) { ge_set_infinity(p); return; }
+    fe_set_b32(p.x, xy); fe_set_b32(p.y, xy + 32); p.inf = 0;
+}
+static int gej_to_xy64(uint8_t* xy, const gej& a) {
+    if (a.inf) { memset(xy, 0, 64); return 0; }
+    ge p; ge_set_gej(p, a);
+    fe_get_b32(xy, p.x); fe_get_b32(xy + 32, p.y);
+    return 1;
+}
+extern "C" {
+void emu_init(int gw) {
+    int windows = (256 + gw - 1) / gw;
+    g_tab.assign(ecmult_gtable_words(gw), 0);
+    std::vector<uint32_t> bases(16 * windows);
+    gtable_compute_bases(bases.data(), gw, windows);
+    for (int j = 0; j < windows; j++)
+        for (uint32_t d = 1; d < (1u << gw); d++)
+            gtable_compute_entry(g_tab.data() + (((size_t)j << gw) + d) * 16, bases.data() + 16 * j, d, gw);
+    g_gt.data = g_tab.data(); g_gt.gw = gw; g_gt.windows = windows;
+    sha256 h; sha256_init_tagged(h, (const uint8_t*)"BIP0340/challenge", 17);
+    for (int i = 0; i < 8; i++) g_mid.s[i] = h.s[i];
+}
+void emu_sc_mul(uint8_t* r, const uint8_t* a, const uint8_t* b) { sc x, y, z; sc_set_b32(x, a); sc_set_b32(y, b); sc_mul(z, x, y); sc_get_b32(r, z); }
+void emu_sc_add(uint8_t* r, const uint8_t* a, const uint8_t* b) { sc x, y, z; sc_set_b32(x, a); sc_set_b32(y, b); sc_add(z, x, y); sc_get_b32(r, z); }
+void emu_sc_negate(uint8_t* r, const uint8_t* a) { sc x, z; sc_set_b32(x, a); sc_negate(z, x); sc_get_b32(r, z); }
+void emu_sc_inverse(uint8_t* r, const uint8_t* a) { sc x, z; sc_set_b32(x, a); sc_inverse(z, x); sc_get_b32(r, z); }
+int emu_sc_set_b32(uint8_t* r, const uint8_t* a) { sc x; int ov = sc_set_b32(x, a); sc_get_b32(r, x); return ov; }
+int emu_sc_is_high(const uint8_t* a) { sc x; sc_set_b32(x, a); return sc_is_high(x); }
+void emu_sc_split_lambda(uint8_t* r1, uint8_t* r2, const uint8_t* k) { sc x, a, b; sc_set_b32(x, k); sc_split_lambda(a, b, x); sc_get_b32(r1, a); sc_get_b32(r2, b); }
+void emu_sha256(uint8_t* out, const uint8_t* data, size_t len) { sha256 h; sha256_init(h); sha256_write(h, data, len); sha256_finalize(h, out); }
+int emu_ge_double(uint8_t* r, const uint8_t* a) { ge p; ge_from_xy64(p, a); gej j, t; gej_set_ge(j, p); gej_double(t, j); return gej_to_xy64(r, t); }
+int emu_ge_add(uint8_t* r, const uint8_t* a, const uint8_t* b) { ge p, q; ge_from_xy64(p, a); ge_from_xy64(q, b); gej j, k, t; gej_set_ge(j, p); gej_set_ge(k, q); gej_add(t, j, k); return gej_to_xy64(r, t); }
+int emu_ge_add_mixed(uint8_t* r, const uint8_t* a, const uint8_t* b) { ge p, q; ge_from_xy64(p, a); ge_from_xy64(q, b); gej j, t; gej_set_ge(j, p);
+    gej d; gej_double(d, j); gej nd; /* make z != 1: (2a) + (-a) = a, then + b */ ge np; ge_neg(np, p); gej_add_ge(nd, d, np); gej_add_ge(t, nd, q); return gej_to_xy64(r, t); }
+int emu_ecmult(uint8_t* r, const uint8_t* a, const uint8_t* na, const uint8_t* ng) {
+    ge p; ge_from_xy64(p, a); gej pj, R; gej_set_ge(pj, p);
+    sc x, y; sc_set_b32(x, na); if (ng) sc_set_b32(y, ng); else sc_set_zero(y);
+    tab_local tab;
+    ecmult(R, pj, x, y, g_gt, tab);
+    return gej_to_xy64(r, R);
+}
+int emu_schnorr_verify(const uint8_t* sig, const uint8_t* msg, uint32_t msglen, const uint8_t* pk, int pkfmt) {
+    tab_local tab; return schnorr_verify_item(sig, msg, msglen, pk, pkfmt, g_mid, g_gt, tab);
+}
+int emu_ecdsa_verify(const uint8_t* sig, int sigfmt, const uint8_t* msg32, const uint8_t* pk, int pkfmt) {
+    tab_local tab; return ecdsa_verify_item(sig, sigfmt, msg32, pk, pkfmt, g_gt, tab);
+}
+}
