@@ -1,0 +1,117 @@
+/* secp256k1_b200.h -- C ABI of the B200-native batch engine (libsecp256k1_b200.so).
+ *
+ * Plain pointers and sizes only.  Two families of entry points:
+ *   *_batch      host buffers in / host buffers out (H2D + kernels + D2H inside the call)
+ *   *_batch_dev  device pointers, asynchronous on the given CUDA stream (cudaStream_t passed as void*)
+ * Every function returns 1 on success and 0 on an engine/CUDA failure (secp256k1_b200_last_error()
+ * gives the reason); per-item accept/reject results go to the `ok` byte array (1 = valid).
+ * There is NO CPU fallback: without a usable B200 every call fails.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference tree):
+ *   secp256k1_b200_fe_op_batch          batched secp256k1_fe_mul/_sqr/... (src/field_5x52_int128_impl.h:18,:154;
+ *                                       src/field_5x52_impl.h; src/field_impl.h:37) -- roofline probe + self test
+ *   secp256k1_b200_ecmult_batch         static secp256k1_ecmult (src/ecmult.h:47, src/ecmult_impl.h:365), one call per item
+ *   secp256k1_b200_schnorrsig_verify_batch   secp256k1_schnorrsig_verify (include/secp256k1_schnorrsig.h:178,
+ *                                       src/modules/schnorrsig/main_impl.h:215) [+ secp256k1_xonly_pubkey_parse,
+ *                                       include/secp256k1_extrakeys.h:47 when pkfmt = XONLY32]
+ *   secp256k1_b200_ecdsa_verify_batch   secp256k1_ecdsa_verify (include/secp256k1.h:622, src/secp256k1.c:498)
+ *                                       [+ secp256k1_ec_pubkey_parse / secp256k1_ecdsa_signature_parse_compact]
+ *   secp256k1_b200_pedersen_commit_batch     secp256k1_pedersen_commit (include/secp256k1_generator.h:114,
+ *                                       src/modules/generator/main_impl.h:309) + _commitment_serialize (:281)
+ *   secp256k1_b200_rangeproof_verify_batch   secp256k1_rangeproof_verify (include/secp256k1_rangeproof.h:70,
+ *                                       src/modules/rangeproof/main_impl.h:54)
+ *   secp256k1_b200_ecmult_multi         static secp256k1_ecmult_multi_var (src/ecmult.h:62, src/ecmult_impl.h:823)
+ *   secp256k1_b200_bppp_norm_verify_batch    static secp256k1_bppp_rangeproof_norm_product_verify
+ *                                       (src/modules/bppp/bppp_norm_product_impl.h:425)
+ */
+#ifndef SECP256K1_B200_H
+#define SECP256K1_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SECP256K1_B200_API __attribute__((visibility("default")))
+#else
+#define SECP256K1_B200_API
+#endif
+
+typedef struct secp256k1_b200_engine secp256k1_b200_engine;
+
+/* public-key encodings accepted by the batch verifiers */
+#define SECP256K1_B200_PK_OPAQUE64     0 /* secp256k1_pubkey / secp256k1_xonly_pubkey 64-byte opaque (include/secp256k1.h:62) */
+#define SECP256K1_B200_PK_XONLY32      1 /* BIP-340 x-only 32 bytes; parsing (lift_x) is done on the GPU */
+#define SECP256K1_B200_PK_COMPRESSED33 2 /* SEC1 compressed 33 bytes; decompression on the GPU */
+/* signature encodings for ECDSA */
+#define SECP256K1_B200_SIG_OPAQUE64    0 /* secp256k1_ecdsa_signature 64-byte opaque (src/secp256k1.c:393-415) */
+#define SECP256K1_B200_SIG_COMPACT64   1 /* r||s big-endian, as secp256k1_ecdsa_signature_parse_compact takes */
+
+/* field-op selector for secp256k1_b200_fe_op_batch */
+#define SECP256K1_B200_FE_MUL  0
+#define SECP256K1_B200_FE_SQR  1
+#define SECP256K1_B200_FE_ADD  2
+#define SECP256K1_B200_FE_SUB  3
+#define SECP256K1_B200_FE_HALF 4
+#define SECP256K1_B200_FE_INV  5
+#define SECP256K1_B200_FE_SQRT 6
+#define SECP256K1_B200_FE_NEG  7
+#define SECP256K1_B200_FE_MUL_PORTABLE 16 /* same op through the portable (non-PTX) limb code: on-device A/B self test */
+#define SECP256K1_B200_FE_SQR_PORTABLE 17
+
+/* ---- engine ------------------------------------------------------------------------------ */
+/* Creates an engine on CUDA device `device` (-1 = current).  gen_window_bits = 0 picks the default
+ * comb window for the generator table (16 -> 64 MiB).  If build_tables is 0 the table memory is
+ * allocated but left for the caller to fill (e.g. by an NCCL broadcast from rank 0) -- see
+ * secp256k1_b200_engine_table_ptr. */
+SECP256K1_B200_API int secp256k1_b200_engine_create(secp256k1_b200_engine **out, int device, int gen_window_bits, int build_tables);
+SECP256K1_B200_API void secp256k1_b200_engine_destroy(secp256k1_b200_engine *e);
+SECP256K1_B200_API const char *secp256k1_b200_last_error(void);
+/* device pointer / size of the generator comb table (for the init-time NCCL broadcast) */
+SECP256K1_B200_API void *secp256k1_b200_engine_table_ptr(secp256k1_b200_engine *e);
+SECP256K1_B200_API size_t secp256k1_b200_engine_table_bytes(const secp256k1_b200_engine *e);
+SECP256K1_B200_API int secp256k1_b200_engine_table_build(secp256k1_b200_engine *e);
+/* number of kernel launches issued by this engine so far */
+SECP256K1_B200_API uint64_t secp256k1_b200_engine_launch_count(const secp256k1_b200_engine *e);
+SECP256K1_B200_API int secp256k1_b200_engine_device(const secp256k1_b200_engine *e);
+
+/* ---- field micro-kernel (roofline probe / self test) ---------------------------------------- */
+/* out[i] = op(a[i], b[i]) applied `iters` times (iters >= 1: r = op(r, b) repeated, for timing);
+ * elements are 32-byte big-endian, any 256-bit value accepted (reduced mod p), outputs canonical. */
+SECP256K1_B200_API int secp256k1_b200_fe_op_batch(secp256k1_b200_engine *e, int op, unsigned char *out32,
+        const unsigned char *a32, const unsigned char *b32, size_t n, int iters);
+SECP256K1_B200_API int secp256k1_b200_fe_op_batch_dev(secp256k1_b200_engine *e, int op, unsigned char *d_out32,
+        const unsigned char *d_a32, const unsigned char *d_b32, size_t n, int iters, void *stream);
+
+/* Integer-pipe peak probe: blocks*threads threads each issue 16*iters register-resident IMAD.WIDE.U32
+ * (32x32+64 MAC).  d_out: blocks*threads*8 bytes.  The measured MAC/s is the roofline denominator. */
+SECP256K1_B200_API int secp256k1_b200_imad_probe_dev(secp256k1_b200_engine *e, void *d_out, int blocks, int threads, int iters, void *stream);
+
+/* ---- ecmult: out = na*A + ng*G ---------------------------------------------------------------- */
+/* a64: affine x||y big-endian (all-zero = infinity); na32/ng32: big-endian scalars (reduced mod n);
+ * ng32 may be NULL (= 0).  out64: affine x||y big-endian, all-zero for infinity. */
+SECP256K1_B200_API int secp256k1_b200_ecmult_batch(secp256k1_b200_engine *e, unsigned char *out64,
+        const unsigned char *a64, const unsigned char *na32, const unsigned char *ng32, size_t n);
+SECP256K1_B200_API int secp256k1_b200_ecmult_batch_dev(secp256k1_b200_engine *e, unsigned char *d_out64,
+        const unsigned char *d_a64, const unsigned char *d_na32, const unsigned char *d_ng32, size_t n, void *stream);
+
+/* ---- BIP-340 Schnorr ---------------------------------------------------------------------------- */
+/* sig64[n][64], msg[n][msglen] (same length for the whole batch), pk[n][32|33|64] per pkfmt. */
+SECP256K1_B200_API int secp256k1_b200_schnorrsig_verify_batch(secp256k1_b200_engine *e, unsigned char *ok,
+        const unsigned char *sig64, const unsigned char *msg, size_t msglen, const unsigned char *pk, int pkfmt, size_t n);
+SECP256K1_B200_API int secp256k1_b200_schnorrsig_verify_batch_dev(secp256k1_b200_engine *e, unsigned char *d_ok,
+        const unsigned char *d_sig64, const unsigned char *d_msg, size_t msglen, const unsigned char *d_pk, int pkfmt, size_t n, void *stream);
+
+/* ---- ECDSA ------------------------------------------------------------------------------------ */
+SECP256K1_B200_API int secp256k1_b200_ecdsa_verify_batch(secp256k1_b200_engine *e, unsigned char *ok,
+        const unsigned char *sig64, int sigfmt, const unsigned char *msghash32, const unsigned char *pk, int pkfmt, size_t n);
+SECP256K1_B200_API int secp256k1_b200_ecdsa_verify_batch_dev(secp256k1_b200_engine *e, unsigned char *d_ok,
+        const unsigned char *d_sig64, int sigfmt, const unsigned char *d_msghash32, const unsigned char *d_pk, int pkfmt, size_t n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SECP256K1_B200_H */

@@ -19,10 +19,10 @@
 
 #if defined(__CUDACC__)
 #define HD __host__ __device__ __forceinline__
-#define HDNI __host__ __device__ __noinline__
+#define HDNI static __host__ __device__ __noinline__
 #else
 #define HD inline
-#define HDNI
+#define HDNI static
 #endif
 
 #ifndef B200_NS

@@ -1,0 +1,287 @@
+// engine.cu -- host side of libsecp256k1_b200.so: engine object, device memory, the C ABI declared
+// in include/secp256k1_b200.h.  No CPU compute path exists here: every entry point launches kernels
+// on the B200 or fails.
+#include "../../include/secp256k1_b200.h"
+#include "launch.h"
+#include "sha256.cuh"
+
+#include <mutex>
+#include <string>
+#include <vector>
+#include <stdio.h>
+#include <string.h>
+
+using namespace b200;
+
+static thread_local std::string g_last_error;
+static void set_error(const char* what, cudaError_t err) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(err);
+}
+static void set_error(const char* what) { g_last_error = what; }
+
+#define CK(call)                                   \
+    do {                                           \
+        cudaError_t _e = (call);                   \
+        if (_e != cudaSuccess) {                   \
+            set_error(#call, _e);                  \
+            return 0;                              \
+        }                                          \
+    } while (0)
+
+struct secp256k1_b200_engine {
+    int device;
+    int gw, windows;
+    uint32_t* d_gtab;
+    uint32_t* d_bases;
+    size_t gtab_bytes;
+    bip340_midstate_h mid;
+    cudaStream_t stream;       // engine-owned stream for host-buffer calls
+    uint8_t* d_scratch;        // grow-only device scratch for host-buffer calls
+    size_t scratch_bytes;
+    uint64_t launches;
+    std::mutex mu;             // the reference context is usable from many threads (secp256k1.h:42-49): serialize here
+
+    gtable_dev gt() const { gtable_dev g; g.data = d_gtab; g.gw = gw; g.windows = windows; return g; }
+};
+
+namespace {
+struct device_guard {
+    int prev;
+    bool ok;
+    explicit device_guard(int dev) : prev(-1), ok(true) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+        changed = (prev != dev);
+    }
+    ~device_guard() { if (ok && changed) cudaSetDevice(prev); }
+    bool changed = false;
+};
+
+// carve `count` sub-buffers (each 256-byte aligned) out of the engine scratch
+struct carver {
+    secp256k1_b200_engine* e;
+    size_t off = 0;
+    std::vector<std::pair<size_t, size_t>> parts;
+    explicit carver(secp256k1_b200_engine* e_) : e(e_) {}
+    size_t add(size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+    }
+    int commit() {
+        if (off > e->scratch_bytes) {
+            if (e->d_scratch) cudaFree(e->d_scratch);
+            e->d_scratch = nullptr; e->scratch_bytes = 0;
+            size_t want = off + (off >> 2);
+            cudaError_t err = cudaMalloc((void**)&e->d_scratch, want);
+            if (err != cudaSuccess) { set_error("cudaMalloc(scratch)", err); return 0; }
+            e->scratch_bytes = want;
+        }
+        return 1;
+    }
+    uint8_t* at(size_t o) const { return e->d_scratch + o; }
+};
+}  // namespace
+
+extern "C" {
+
+const char* secp256k1_b200_last_error(void) { return g_last_error.c_str(); }
+
+int secp256k1_b200_engine_create(secp256k1_b200_engine** out, int device, int gen_window_bits, int build_tables) {
+    if (!out) { set_error("engine_create: out is NULL"); return 0; }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0) {
+        set_error("engine_create: no CUDA device (this library has no CPU fallback)", err == cudaSuccess ? cudaErrorNoDevice : err);
+        return 0;
+    }
+    if (device < 0) CK(cudaGetDevice(&device));
+    if (device >= count) { set_error("engine_create: device index out of range"); return 0; }
+    device_guard guard(device);
+    if (!guard.ok) { set_error("engine_create: cudaSetDevice failed"); return 0; }
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("engine_create: this build contains sm_100a code only (B200 required)");
+        return 0;
+    }
+    int gw = gen_window_bits ? gen_window_bits : 16;
+    if (gw < 2 || gw > 18) { set_error("engine_create: gen_window_bits must be in [2,18]"); return 0; }
+    secp256k1_b200_engine* e = new secp256k1_b200_engine();
+    e->device = device;
+    e->gw = gw;
+    e->windows = (256 + gw - 1) / gw;
+    e->gtab_bytes = (size_t)e->windows * ((size_t)1 << gw) * 64;
+    e->d_gtab = nullptr; e->d_bases = nullptr; e->d_scratch = nullptr; e->scratch_bytes = 0; e->launches = 0;
+    e->stream = nullptr;
+    {
+        sha256 h;
+        sha256_init_tagged(h, (const uint8_t*)"BIP0340/challenge", 17);
+        for (int i = 0; i < 8; i++) e->mid.s[i] = h.s[i];
+    }
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc((void**)&e->d_gtab, e->gtab_bytes) != cudaSuccess ||
+        cudaMalloc((void**)&e->d_bases, (size_t)e->windows * 64) != cudaSuccess) {
+        set_error("engine_create: device allocation failed", cudaGetLastError());
+        secp256k1_b200_engine_destroy(e);
+        return 0;
+    }
+    if (build_tables && !secp256k1_b200_engine_table_build(e)) {
+        secp256k1_b200_engine_destroy(e);
+        return 0;
+    }
+    *out = e;
+    return 1;
+}
+
+void secp256k1_b200_engine_destroy(secp256k1_b200_engine* e) {
+    if (!e) return;
+    device_guard guard(e->device);
+    if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+    if (e->d_gtab) cudaFree(e->d_gtab);
+    if (e->d_bases) cudaFree(e->d_bases);
+    if (e->d_scratch) cudaFree(e->d_scratch);
+    delete e;
+}
+
+void* secp256k1_b200_engine_table_ptr(secp256k1_b200_engine* e) { return e ? (void*)e->d_gtab : nullptr; }
+size_t secp256k1_b200_engine_table_bytes(const secp256k1_b200_engine* e) { return e ? e->gtab_bytes : 0; }
+uint64_t secp256k1_b200_engine_launch_count(const secp256k1_b200_engine* e) { return e ? e->launches : 0; }
+int secp256k1_b200_engine_device(const secp256k1_b200_engine* e) { return e ? e->device : -1; }
+
+int secp256k1_b200_engine_table_build(secp256k1_b200_engine* e) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    std::lock_guard<std::mutex> lock(e->mu);
+    device_guard guard(e->device);
+    CK(launch_gtable_build(e->d_gtab, e->d_bases, e->gw, e->windows, e->stream, &e->launches));
+    CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
+/* ---- field micro-kernel ------------------------------------------------------------------------- */
+int secp256k1_b200_fe_op_batch_dev(secp256k1_b200_engine* e, int op, unsigned char* d_out32, const unsigned char* d_a32,
+                                   const unsigned char* d_b32, size_t n, int iters, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (iters < 1) iters = 1;
+    device_guard guard(e->device);
+    if (op >= 16) CK(launch_fe_op_portable(op - 16, d_out32, d_a32, d_b32, n, iters, (cudaStream_t)stream, &e->launches));
+    else CK(launch_fe_op(op, d_out32, d_a32, d_b32, n, iters, (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_fe_op_batch(secp256k1_b200_engine* e, int op, unsigned char* out32, const unsigned char* a32,
+                               const unsigned char* b32, size_t n, int iters) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (n == 0) return 1;
+    std::lock_guard<std::mutex> lock(e->mu);
+    device_guard guard(e->device);
+    carver c(e);
+    size_t oa = c.add(32 * n), ob = c.add(32 * n), oo = c.add(32 * n);
+    if (!c.commit()) return 0;
+    CK(cudaMemcpyAsync(c.at(oa), a32, 32 * n, cudaMemcpyHostToDevice, e->stream));
+    if (b32) CK(cudaMemcpyAsync(c.at(ob), b32, 32 * n, cudaMemcpyHostToDevice, e->stream));
+    else CK(cudaMemsetAsync(c.at(ob), 0, 32 * n, e->stream));
+    if (!secp256k1_b200_fe_op_batch_dev(e, op, c.at(oo), c.at(oa), c.at(ob), n, iters, e->stream)) return 0;
+    CK(cudaMemcpyAsync(out32, c.at(oo), 32 * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
+/* IMAD.WIDE peak probe: blocks*threads threads, each 16*iters MACs; d_out needs blocks*threads*8 bytes */
+int secp256k1_b200_imad_probe_dev(secp256k1_b200_engine* e, void* d_out, int blocks, int threads, int iters, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (threads < 32 || threads > 256 || blocks < 1) { set_error("imad_probe: bad launch shape"); return 0; }
+    device_guard guard(e->device);
+    CK(launch_imad_probe((uint64_t*)d_out, blocks, threads, iters, (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+
+/* ---- ecmult ---------------------------------------------------------------------------------------- */
+int secp256k1_b200_ecmult_batch_dev(secp256k1_b200_engine* e, unsigned char* d_out64, const unsigned char* d_a64,
+                                    const unsigned char* d_na32, const unsigned char* d_ng32, size_t n, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    device_guard guard(e->device);
+    CK(launch_ecmult(d_out64, d_a64, d_na32, d_ng32, n, e->gt(), (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_ecmult_batch(secp256k1_b200_engine* e, unsigned char* out64, const unsigned char* a64,
+                                const unsigned char* na32, const unsigned char* ng32, size_t n) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (n == 0) return 1;
+    std::lock_guard<std::mutex> lock(e->mu);
+    device_guard guard(e->device);
+    carver c(e);
+    size_t oa = c.add(64 * n), ona = c.add(32 * n), ong = c.add(32 * n), oo = c.add(64 * n);
+    if (!c.commit()) return 0;
+    CK(cudaMemcpyAsync(c.at(oa), a64, 64 * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(ona), na32, 32 * n, cudaMemcpyHostToDevice, e->stream));
+    if (ng32) CK(cudaMemcpyAsync(c.at(ong), ng32, 32 * n, cudaMemcpyHostToDevice, e->stream));
+    if (!secp256k1_b200_ecmult_batch_dev(e, c.at(oo), c.at(oa), c.at(ona), ng32 ? c.at(ong) : nullptr, n, e->stream)) return 0;
+    CK(cudaMemcpyAsync(out64, c.at(oo), 64 * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
+/* ---- Schnorr --------------------------------------------------------------------------------------- */
+static size_t pk_len(int pkfmt) {
+    return pkfmt == SECP256K1_B200_PK_OPAQUE64 ? 64 : (pkfmt == SECP256K1_B200_PK_XONLY32 ? 32 : 33);
+}
+int secp256k1_b200_schnorrsig_verify_batch_dev(secp256k1_b200_engine* e, unsigned char* d_ok, const unsigned char* d_sig64,
+                                               const unsigned char* d_msg, size_t msglen, const unsigned char* d_pk, int pkfmt,
+                                               size_t n, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (pkfmt < 0 || pkfmt > 2) { set_error("bad pkfmt"); return 0; }
+    device_guard guard(e->device);
+    CK(launch_schnorr_verify(d_ok, d_sig64, d_msg, (uint32_t)msglen, d_pk, pkfmt, n, e->mid, e->gt(), (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_schnorrsig_verify_batch(secp256k1_b200_engine* e, unsigned char* ok, const unsigned char* sig64,
+                                           const unsigned char* msg, size_t msglen, const unsigned char* pk, int pkfmt, size_t n) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (pkfmt < 0 || pkfmt > 2) { set_error("bad pkfmt"); return 0; }
+    if (n == 0) return 1;
+    std::lock_guard<std::mutex> lock(e->mu);
+    device_guard guard(e->device);
+    carver c(e);
+    size_t pl = pk_len(pkfmt);
+    size_t os = c.add(64 * n), om = c.add(msglen * n + 16), op = c.add(pl * n), oo = c.add(n);
+    if (!c.commit()) return 0;
+    CK(cudaMemcpyAsync(c.at(os), sig64, 64 * n, cudaMemcpyHostToDevice, e->stream));
+    if (msglen) CK(cudaMemcpyAsync(c.at(om), msg, msglen * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(op), pk, pl * n, cudaMemcpyHostToDevice, e->stream));
+    if (!secp256k1_b200_schnorrsig_verify_batch_dev(e, c.at(oo), c.at(os), c.at(om), msglen, c.at(op), pkfmt, n, e->stream)) return 0;
+    CK(cudaMemcpyAsync(ok, c.at(oo), n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
+/* ---- ECDSA ------------------------------------------------------------------------------------------ */
+int secp256k1_b200_ecdsa_verify_batch_dev(secp256k1_b200_engine* e, unsigned char* d_ok, const unsigned char* d_sig64, int sigfmt,
+                                          const unsigned char* d_msghash32, const unsigned char* d_pk, int pkfmt, size_t n, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (pkfmt < 0 || pkfmt > 2 || sigfmt < 0 || sigfmt > 1) { set_error("bad format selector"); return 0; }
+    device_guard guard(e->device);
+    CK(launch_ecdsa_verify(d_ok, d_sig64, sigfmt, d_msghash32, d_pk, pkfmt, n, e->gt(), (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_ecdsa_verify_batch(secp256k1_b200_engine* e, unsigned char* ok, const unsigned char* sig64, int sigfmt,
+                                      const unsigned char* msghash32, const unsigned char* pk, int pkfmt, size_t n) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (pkfmt < 0 || pkfmt > 2 || sigfmt < 0 || sigfmt > 1) { set_error("bad format selector"); return 0; }
+    if (n == 0) return 1;
+    std::lock_guard<std::mutex> lock(e->mu);
+    device_guard guard(e->device);
+    carver c(e);
+    size_t pl = pk_len(pkfmt);
+    size_t os = c.add(64 * n), om = c.add(32 * n), op = c.add(pl * n), oo = c.add(n);
+    if (!c.commit()) return 0;
+    CK(cudaMemcpyAsync(c.at(os), sig64, 64 * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(om), msghash32, 32 * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(op), pk, pl * n, cudaMemcpyHostToDevice, e->stream));
+    if (!secp256k1_b200_ecdsa_verify_batch_dev(e, c.at(oo), c.at(os), sigfmt, c.at(om), c.at(op), pkfmt, n, e->stream)) return 0;
+    CK(cudaMemcpyAsync(ok, c.at(oo), n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+// k_verify.cu -- one-thread-per-item kernels: ecmult batch, BIP-340 verify batch, ECDSA verify batch.
+// Block = 128 threads; dynamic shared memory = 128 * 512 B = 64 KiB for the per-thread tables of odd
+// multiples (3 blocks resident per SM = 192 KiB of the 227 KiB).
+#include "verify.cuh"
+#include "launch.h"
+
+namespace b200 {
+
+#define VERIFY_BLOCK 128
+#define VERIFY_SMEM (VERIFY_BLOCK * 8 * 16 * 4)
+
+__device__ __forceinline__ void load_bytes_global(uint8_t* dst, const uint8_t* src, int nbytes) {
+    // 16-byte vector path when aligned (contiguous per-item records), byte path otherwise
+    if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)nbytes) & 15) == 0) {
+        const uint4* q = reinterpret_cast<const uint4*>(src);
+        uint4* d = reinterpret_cast<uint4*>(dst);
+        for (int i = 0; i < nbytes / 16; i++) d[i] = __ldg(q + i);
+    } else {
+        for (int i = 0; i < nbytes; i++) dst[i] = __ldg(src + i);
+    }
+}
+
+__global__ void __launch_bounds__(VERIFY_BLOCK) k_ecmult(uint8_t* __restrict__ out64, const uint8_t* __restrict__ a64,
+        const uint8_t* __restrict__ na32, const uint8_t* __restrict__ ng32, size_t n, ecmult_gtable gt) {
+    extern __shared__ uint32_t smem[];
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    tab_shared tab = {smem + threadIdx.x, (int)blockDim.x};
+    __align__(16) uint8_t in[128];
+    load_bytes_global(in, a64 + 64 * i, 64);
+    load_bytes_global(in + 64, na32 + 32 * i, 32);
+    if (ng32) load_bytes_global(in + 96, ng32 + 32 * i, 32);
+    ge a;
+    int z = 1;
+    for (int k = 0; k < 64; k++) z &= (in[k] == 0);
+    if (z) ge_set_infinity(a);
+    else { fe_set_b32(a.x, in); fe_set_b32(a.y, in + 32); a.inf = 0; }
+    sc na, ng;
+    sc_set_b32(na, in + 64);
+    if (ng32) sc_set_b32(ng, in + 96); else sc_set_zero(ng);
+    gej aj, R;
+    gej_set_ge(aj, a);
+    ecmult(R, aj, na, ng, gt, tab);
+    __align__(16) uint8_t o[64];
+    if (R.inf) {
+        for (int k = 0; k < 64; k++) o[k] = 0;
+    } else {
+        ge Ra; ge_set_gej(Ra, R);
+        fe_get_b32(o, Ra.x); fe_get_b32(o + 32, Ra.y);
+    }
+    uint4* q = reinterpret_cast<uint4*>(out64 + 64 * i);
+    const uint4* s4 = reinterpret_cast<const uint4*>(o);
+    if ((reinterpret_cast<uintptr_t>(out64) & 15) == 0) { q[0] = s4[0]; q[1] = s4[1]; q[2] = s4[2]; q[3] = s4[3]; }
+    else for (int k = 0; k < 64; k++) out64[64 * i + k] = o[k];
+}
+
+__global__ void __launch_bounds__(VERIFY_BLOCK) k_schnorr_verify(uint8_t* __restrict__ ok, const uint8_t* __restrict__ sig64,
+        const uint8_t* __restrict__ msg, uint32_t msglen, const uint8_t* __restrict__ pk, int pkfmt, size_t n,
+        bip340_midstate mid, ecmult_gtable gt) {
+    extern __shared__ uint32_t smem[];
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    tab_shared tab = {smem + threadIdx.x, (int)blockDim.x};
+    __align__(16) uint8_t in[64 + 64];
+    load_bytes_global(in, sig64 + 64 * i, 64);
+    int pklen = pkfmt == PK_OPAQUE64 ? 64 : (pkfmt == PK_XONLY32 ? 32 : 33);
+    load_bytes_global(in + 64, pk + (size_t)pklen * i, pklen);
+    // messages of arbitrary (batch-uniform) length are hashed straight from global memory
+    ok[i] = (uint8_t)schnorr_verify_item(in, msg + (size_t)msglen * i, msglen, in + 64, pkfmt, mid, gt, tab);
+}
+
+__global__ void __launch_bounds__(VERIFY_BLOCK) k_ecdsa_verify(uint8_t* __restrict__ ok, const uint8_t* __restrict__ sig64, int sigfmt,
+        const uint8_t* __restrict__ msg32, const uint8_t* __restrict__ pk, int pkfmt, size_t n, ecmult_gtable gt) {
+    extern __shared__ uint32_t smem[];
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    tab_shared tab = {smem + threadIdx.x, (int)blockDim.x};
+    __align__(16) uint8_t in[64 + 32 + 64];
+    load_bytes_global(in, sig64 + 64 * i, 64);
+    load_bytes_global(in + 64, msg32 + 32 * i, 32);
+    int pklen = pkfmt == PK_OPAQUE64 ? 64 : (pkfmt == PK_XONLY32 ? 32 : 33);
+    load_bytes_global(in + 96, pk + (size_t)pklen * i, pklen);
+    ok[i] = (uint8_t)ecdsa_verify_item(in, sigfmt, in + 64, in + 96, pkfmt, gt, tab);
+}
+
+template <class K>
+static cudaError_t set_smem(K kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VERIFY_SMEM);
+}
+static inline ecmult_gtable to_gt(const gtable_dev& g) { ecmult_gtable t; t.data = g.data; t.gw = g.gw; t.windows = g.windows; return t; }
+
+cudaError_t launch_ecmult(uint8_t* out64, const uint8_t* a64, const uint8_t* na32, const uint8_t* ng32, size_t n,
+                          const gtable_dev& gt, cudaStream_t s, uint64_t* launches) {
+    if (n == 0) return cudaSuccess;
+    cudaError_t err = set_smem(k_ecmult);
+    if (err != cudaSuccess) return err;
+    k_ecmult<<<(unsigned)((n + VERIFY_BLOCK - 1) / VERIFY_BLOCK), VERIFY_BLOCK, VERIFY_SMEM, s>>>(out64, a64, na32, ng32, n, to_gt(gt));
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+cudaError_t launch_schnorr_verify(uint8_t* ok, const uint8_t* sig64, const uint8_t* msg, uint32_t msglen, const uint8_t* pk, int pkfmt,
+                                  size_t n, const bip340_midstate_h& mid, const gtable_dev& gt, cudaStream_t s, uint64_t* launches) {
+    if (n == 0) return cudaSuccess;
+    cudaError_t err = set_smem(k_schnorr_verify);
+    if (err != cudaSuccess) return err;
+    bip340_midstate m;
+    for (int i = 0; i < 8; i++) m.s[i] = mid.s[i];
+    k_schnorr_verify<<<(unsigned)((n + VERIFY_BLOCK - 1) / VERIFY_BLOCK), VERIFY_BLOCK, VERIFY_SMEM, s>>>(ok, sig64, msg, msglen, pk, pkfmt, n, m, to_gt(gt));
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+cudaError_t launch_ecdsa_verify(uint8_t* ok, const uint8_t* sig64, int sigfmt, const uint8_t* msg32, const uint8_t* pk, int pkfmt,
+                                size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches) {
+    if (n == 0) return cudaSuccess;
+    cudaError_t err = set_smem(k_ecdsa_verify);
+    if (err != cudaSuccess) return err;
+    k_ecdsa_verify<<<(unsigned)((n + VERIFY_BLOCK - 1) / VERIFY_BLOCK), VERIFY_BLOCK, VERIFY_SMEM, s>>>(ok, sig64, sigfmt, msg32, pk, pkfmt, n, to_gt(gt));
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace b200

@@ -1,0 +1,29 @@
+// launch.h -- internal host-side declarations of the kernel launchers (one per .cu file).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b200 {
+
+struct bip340_midstate_h { uint32_t s[8]; };
+
+struct gtable_dev {
+    const uint32_t* data;
+    int gw;
+    int windows;
+};
+
+// every launcher returns the number of kernel launches it issued through *launches (added)
+cudaError_t launch_fe_op(int op, uint8_t* out, const uint8_t* a, const uint8_t* b, size_t n, int iters, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_imad_probe(uint64_t* out, int blocks, int threads, int iters, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_fe_op_portable(int op, uint8_t* out, const uint8_t* a, const uint8_t* b, size_t n, int iters, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_gtable_build(uint32_t* d_tab, uint32_t* d_bases, int gw, int windows, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_ecmult(uint8_t* out64, const uint8_t* a64, const uint8_t* na32, const uint8_t* ng32, size_t n,
+                          const gtable_dev& gt, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_schnorr_verify(uint8_t* ok, const uint8_t* sig64, const uint8_t* msg, uint32_t msglen, const uint8_t* pk, int pkfmt,
+                                  size_t n, const bip340_midstate_h& mid, const gtable_dev& gt, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_ecdsa_verify(uint8_t* ok, const uint8_t* sig64, int sigfmt, const uint8_t* msg32, const uint8_t* pk, int pkfmt,
+                                size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches);
+
+}  // namespace b200

@@ -1,0 +1,180 @@
+"""ctypes mirror of include/secp256k1_b200.h.
+
+Argument meaning and error behaviour follow the reference's C API for the hot path
+(include/secp256k1.h, include/secp256k1_schnorrsig.h, ...): every verify returns 1 = valid,
+0 = invalid per item; API misuse raises.  Engine/CUDA failures raise B200Error carrying
+secp256k1_b200_last_error().
+"""
+import ctypes
+import os
+
+import numpy as np
+
+PK_OPAQUE64, PK_XONLY32, PK_COMPRESSED33 = 0, 1, 2
+SIG_OPAQUE64, SIG_COMPACT64 = 0, 1
+FE_MUL, FE_SQR, FE_ADD, FE_SUB, FE_HALF, FE_INV, FE_SQRT, FE_NEG = range(8)
+FE_MUL_PORTABLE, FE_SQR_PORTABLE = 16, 17
+
+_PKLEN = {PK_OPAQUE64: 64, PK_XONLY32: 32, PK_COMPRESSED33: 33}
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libsecp256k1_b200.so")
+
+
+_LIB = None
+
+
+def load_library():
+    """Loads libsecp256k1_b200.so (built in-tree by build.py).  Fails loudly if it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise B200Error("libsecp256k1_b200.so is not built (%s); run `python __graft_entry__.py build`. "
+                        "There is no CPU fallback." % path)
+    lib = ctypes.CDLL(path)
+    vp, sz, ci, u8p = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p
+    lib.secp256k1_b200_last_error.restype = ctypes.c_char_p
+    lib.secp256k1_b200_engine_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci]
+    lib.secp256k1_b200_engine_destroy.argtypes = [vp]
+    lib.secp256k1_b200_engine_destroy.restype = None
+    lib.secp256k1_b200_engine_table_ptr.argtypes = [vp]
+    lib.secp256k1_b200_engine_table_ptr.restype = vp
+    lib.secp256k1_b200_engine_table_bytes.argtypes = [vp]
+    lib.secp256k1_b200_engine_table_bytes.restype = sz
+    lib.secp256k1_b200_engine_table_build.argtypes = [vp]
+    lib.secp256k1_b200_engine_launch_count.argtypes = [vp]
+    lib.secp256k1_b200_engine_launch_count.restype = ctypes.c_uint64
+    lib.secp256k1_b200_engine_device.argtypes = [vp]
+    lib.secp256k1_b200_fe_op_batch.argtypes = [vp, ci, u8p, u8p, u8p, sz, ci]
+    lib.secp256k1_b200_fe_op_batch_dev.argtypes = [vp, ci, u8p, u8p, u8p, sz, ci, vp]
+    lib.secp256k1_b200_imad_probe_dev.argtypes = [vp, vp, ci, ci, ci, vp]
+    lib.secp256k1_b200_ecmult_batch.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
+    lib.secp256k1_b200_ecmult_batch_dev.argtypes = [vp, u8p, u8p, u8p, u8p, sz, vp]
+    lib.secp256k1_b200_schnorrsig_verify_batch.argtypes = [vp, u8p, u8p, u8p, sz, u8p, ci, sz]
+    lib.secp256k1_b200_schnorrsig_verify_batch_dev.argtypes = [vp, u8p, u8p, u8p, sz, u8p, ci, sz, vp]
+    lib.secp256k1_b200_ecdsa_verify_batch.argtypes = [vp, u8p, u8p, ci, u8p, u8p, ci, sz]
+    lib.secp256k1_b200_ecdsa_verify_batch_dev.argtypes = [vp, u8p, u8p, ci, u8p, u8p, ci, sz, vp]
+    _LIB = lib
+    return lib
+
+
+def _u8(buf, nbytes, name):
+    """bytes / bytearray / uint8 ndarray -> contiguous uint8 ndarray of exactly nbytes."""
+    a = np.frombuffer(buf, dtype=np.uint8) if isinstance(buf, (bytes, bytearray, memoryview)) else np.ascontiguousarray(buf, dtype=np.uint8).reshape(-1)
+    if a.size != nbytes:
+        raise ValueError("%s: expected %d bytes, got %d" % (name, nbytes, a.size))
+    return a
+
+
+def _p(a):
+    return a.ctypes.data if a is not None else None
+
+
+class Engine:
+    """One engine per process per GPU (the reference context is stateless for verification; device
+    state -- the generator comb table, streams, scratch -- lives here, outside any secp256k1_context)."""
+
+    def __init__(self, device=-1, gen_window_bits=0, build_tables=True):
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        if not self._lib.secp256k1_b200_engine_create(ctypes.byref(h), device, gen_window_bits, 1 if build_tables else 0):
+            raise B200Error(self._err())
+        self._h = h
+
+    def _err(self):
+        return self._lib.secp256k1_b200_last_error().decode()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.secp256k1_b200_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- table plumbing (NCCL broadcast at init is done by the caller on this buffer) --
+    @property
+    def table_ptr(self):
+        return self._lib.secp256k1_b200_engine_table_ptr(self._h)
+
+    @property
+    def table_bytes(self):
+        return self._lib.secp256k1_b200_engine_table_bytes(self._h)
+
+    def build_tables(self):
+        if not self._lib.secp256k1_b200_engine_table_build(self._h):
+            raise B200Error(self._err())
+
+    @property
+    def launch_count(self):
+        return int(self._lib.secp256k1_b200_engine_launch_count(self._h))
+
+    @property
+    def device(self):
+        return self._lib.secp256k1_b200_engine_device(self._h)
+
+    def _ck(self, ok):
+        if not ok:
+            raise B200Error(self._err())
+
+    # -- host-buffer entry points ---------------------------------------------------------------
+    def fe_op(self, op, a32, b32=None, iters=1):
+        a = _u8(a32, len(a32) if not hasattr(a32, "size") else a32.size, "a32")
+        n = a.size // 32
+        b = _u8(b32, 32 * n, "b32") if b32 is not None else None
+        out = np.empty(32 * n, dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_fe_op_batch(self._h, op, _p(out), _p(a), _p(b), n, iters))
+        return out.reshape(n, 32)
+
+    def ecmult(self, a64, na32, ng32=None):
+        na = _u8(na32, len(na32) if not hasattr(na32, "size") else na32.size, "na32")
+        n = na.size // 32
+        a = _u8(a64, 64 * n, "a64")
+        ng = _u8(ng32, 32 * n, "ng32") if ng32 is not None else None
+        out = np.empty(64 * n, dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_ecmult_batch(self._h, _p(out), _p(a), _p(na), _p(ng), n))
+        return out.reshape(n, 64)
+
+    def schnorrsig_verify(self, sig64, msg, pk, pkfmt=PK_XONLY32, msglen=32):
+        sig = _u8(sig64, len(sig64) if not hasattr(sig64, "size") else sig64.size, "sig64")
+        n = sig.size // 64
+        m = _u8(msg, msglen * n, "msg") if msglen else np.zeros(1, dtype=np.uint8)
+        p = _u8(pk, _PKLEN[pkfmt] * n, "pk")
+        ok = np.empty(n, dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_schnorrsig_verify_batch(self._h, _p(ok), _p(sig), _p(m), msglen, _p(p), pkfmt, n))
+        return ok
+
+    def ecdsa_verify(self, sig64, msghash32, pk, sigfmt=SIG_COMPACT64, pkfmt=PK_COMPRESSED33):
+        sig = _u8(sig64, len(sig64) if not hasattr(sig64, "size") else sig64.size, "sig64")
+        n = sig.size // 64
+        m = _u8(msghash32, 32 * n, "msghash32")
+        p = _u8(pk, _PKLEN[pkfmt] * n, "pk")
+        ok = np.empty(n, dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_ecdsa_verify_batch(self._h, _p(ok), _p(sig), sigfmt, _p(m), _p(p), pkfmt, n))
+        return ok
+
+    # -- device-pointer entry points (ints: tensor.data_ptr(); stream: torch stream .cuda_stream) ---
+    def fe_op_dev(self, op, d_out, d_a, d_b, n, iters=1, stream=0):
+        self._ck(self._lib.secp256k1_b200_fe_op_batch_dev(self._h, op, d_out, d_a, d_b, n, iters, stream))
+
+    def imad_probe_dev(self, d_out, blocks, threads, iters, stream=0):
+        self._ck(self._lib.secp256k1_b200_imad_probe_dev(self._h, d_out, blocks, threads, iters, stream))
+
+    def ecmult_dev(self, d_out64, d_a64, d_na32, d_ng32, n, stream=0):
+        self._ck(self._lib.secp256k1_b200_ecmult_batch_dev(self._h, d_out64, d_a64, d_na32, d_ng32, n, stream))
+
+    def schnorrsig_verify_dev(self, d_ok, d_sig64, d_msg, msglen, d_pk, pkfmt, n, stream=0):
+        self._ck(self._lib.secp256k1_b200_schnorrsig_verify_batch_dev(self._h, d_ok, d_sig64, d_msg, msglen, d_pk, pkfmt, n, stream))
+
+    def ecdsa_verify_dev(self, d_ok, d_sig64, sigfmt, d_msg32, d_pk, pkfmt, n, stream=0):
+        self._ck(self._lib.secp256k1_b200_ecdsa_verify_batch_dev(self._h, d_ok, d_sig64, sigfmt, d_msg32, d_pk, pkfmt, n, stream))
