@@ -1,0 +1,354 @@
+"""bench.py -- headline benchmark: batch 2^20 independent BIP-340 schnorrsig_verify per GPU
+(BASELINE.json configs[1]; one verify = one a*P + b*G ecmult + x-only pubkey parse, exactly what the
+reference's `bench schnorrsig_verify` times, src/modules/schnorrsig/bench_impl.h:39-48).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (torchrun launches N ranks for N > 1)
+  python bench.py --impl reference --gpus N ...            the reference's CPU implementation (oracle/_ref)
+
+A step = one pass of the hot path over the rank's batch.  `value` = whole-job verifies/s with inputs
+resident in HBM (CUDA events, max over ranks); `e2e` = the same through the host-buffer C-ABI call
+(pinned host inputs, H2D and D2H inside the timed region).  Weak scaling: every rank verifies its own
+2^20 batch; the only collectives are the init-time NCCL broadcast of the generator table and the
+per-step all-gather of the packed accept bitmaps.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MAC_PER_ECMULT = 1.81e5      # reference-algorithm 32x32->64 MACs per a*P + b*G
+BYTES_PER_VERIFY = 64 + 32 + 32 + 1
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2n", type=int, default=20, help="verifies per GPU per step = 2^log2n")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.15)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(self.rows[0][2]), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference (CPU) legs: oracle/_ref = the unmodified reference compiled from its own sources
+def _make_cpu_workload(ref, n):
+    import hashlib
+    import numpy as np
+    sk = b"".join(hashlib.sha256(b"bench-sk" + i.to_bytes(4, "little")).digest() for i in range(n))
+    msg = b"".join(hashlib.sha256(b"bench-msg" + i.to_bytes(4, "little")).digest() for i in range(n))
+    sig, pk = ref.schnorr_make(sk, msg)
+    for i in range(7, n, 16):
+        bit = i % 512
+        sig[64 * i + bit // 8] ^= 1 << (bit % 8)
+    return sig, np.frombuffer(msg, dtype=np.uint8).copy(), pk
+
+
+def _cpu_verify_threads(ref, sig, msg, pk, n, threads):
+    """verifies items [0, n) split over `threads` host threads (ctypes releases the GIL); returns seconds"""
+    import numpy as np
+    per = (n + threads - 1) // threads
+    outs = [None] * threads
+
+    def work(t):
+        lo, hi = t * per, min(n, (t + 1) * per)
+        if lo < hi:
+            outs[t] = ref.schnorr_verify(sig[64 * lo:64 * hi], msg[32 * lo:32 * hi], pk[32 * lo:32 * hi])
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    ok = np.concatenate([o for o in outs if o is not None])
+    return dt, ok
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tests.refshim import RefLib
+    ref = RefLib()
+    cores = cpu_cores()
+    unique = 4096                                  # distinct signed items, tiled to the sample size
+    sig, msg, pk = _make_cpu_workload(ref, unique)
+    per_thread = 1024
+    sample = per_thread * cores
+    import numpy as np
+    reps = (sample + unique - 1) // unique
+    sigs, msgs, pks = np.tile(sig, reps)[:64 * sample], np.tile(msg, reps)[:32 * sample], np.tile(pk, reps)[:32 * sample]
+    for _ in range(args.warmup):
+        _cpu_verify_threads(ref, sigs, msgs, pks, sample, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        dt, ok = _cpu_verify_threads(ref, sigs, msgs, pks, sample, cores)
+        t += dt
+    ms = t / args.steps * 1e3
+    value = sample / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "schnorrsig_verify/s (= ecmult/s)", "value": value, "unit": "verify/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 (5x52 limbs, x86-64 int128)", "data": "synthetic",
+        "config": {"workload": "batch 2^%d independent BIP-340 schnorrsig_verify incl. xonly_pubkey_parse (random keys/msgs, 1/16 corrupted)" % args.log2n,
+                   "step": "bounded sample: %d verifies over %d host threads" % (sample, cores)},
+        "cpu_baseline": {"value": value, "unit": "verify/s", "cores": cores, "kind": "reference",
+                         "sample": "%d verifies per step (%d per thread), reference secp256k1_schnorrsig_verify + xonly_pubkey_parse from oracle/_ref" % (sample, per_thread)},
+        "e2e": {"value": value, "unit": "verify/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "accepted_fraction": float(ok.mean()),
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import secp256k1_zkp_b200 as b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun with %d ranks" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- engine + generator table: rank 0 builds, ONE NCCL broadcast replicates it ---------------
+    eng = b200.Engine(device=local_rank, build_tables=(rank == 0))
+    if world > 1:
+        tab = torch.empty(eng.table_bytes, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            eng.table_export_dev(tab.data_ptr(), stream)
+        dist.broadcast(tab, src=0)
+        if rank != 0:
+            eng.table_import_dev(tab.data_ptr(), stream)
+        torch.cuda.synchronize()
+        del tab
+
+    # ---- synthetic workload, generated on the GPU -----------------------------------------------------
+    n = 1 << args.log2n
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(20260923 + rank)
+    sk = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=gen)
+    sk[:, 0] &= 0x7F
+    sk[:, 31] |= 1
+    msg = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=gen)
+    sig = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+    pk = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    eng.testdata_schnorrsig_sign_dev(sig.data_ptr(), pk.data_ptr(), sk.data_ptr(), msg.data_ptr(), 32, n, stream)
+    bad = torch.arange(7, n, 16, device=dev)
+    bit = bad % 512
+    sig[bad, bit // 8] ^= (1 << (bit % 8)).to(torch.uint8)
+    expected = torch.ones(n, dtype=torch.uint8, device=dev)
+    expected[bad] = 0
+    ok = torch.zeros(n, dtype=torch.uint8, device=dev)
+    weights = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.uint8, device=dev)
+    gathered = torch.empty(world * n // 8, dtype=torch.uint8, device=dev) if world > 1 else None
+    torch.cuda.synchronize()
+
+    kernel_ms = []
+
+    def step(record=False):
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        eng.schnorrsig_verify_dev(ok.data_ptr(), sig.data_ptr(), msg.data_ptr(), 32, pk.data_ptr(), b200.PK_XONLY32, n, stream)
+        if record:
+            e1.record()
+            kernel_ms.append((e0, e1))
+        if world > 1:
+            packed = (ok.view(-1, 8) * weights).sum(dim=1, dtype=torch.uint8)
+            dist.all_gather_into_tensor(gathered, packed)
+
+    # ---- integer-pipe peak, measured live (register-resident IMAD.WIDE.U32 saturation) ------------------
+    pblocks, pthreads, piters = 148 * 8, 256, 4096
+    pout = torch.empty(pblocks * pthreads, dtype=torch.int64, device=dev)
+    for _ in range(2):
+        eng.imad_probe_dev(pout.data_ptr(), pblocks, pthreads, piters, stream)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    eng.imad_probe_dev(pout.data_ptr(), pblocks, pthreads, piters, stream)
+    pe1.record()
+    torch.cuda.synchronize()
+    imad_peak_tmacs = pblocks * pthreads * piters * 16 / pe0.elapsed_time(pe1) / 1e9
+
+    # ---- timed region: `value` (inputs resident in HBM) ---------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launch_count
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        step(record=True)
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop()
+    ms = t0.elapsed_time(t1) / args.steps
+    kms = sum(a.elapsed_time(b) for a, b in kernel_ms) / len(kernel_ms)
+    tms = torch.tensor([ms, kms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms, kms = float(tms[0]), float(tms[1])
+    full_ok = bool(torch.equal(ok, expected))
+
+    # ---- e2e: the host-buffer C-ABI call, pinned host inputs, H2D + D2H inside the timed region -------------
+    h_sig, h_msg, h_pk = sig.cpu().pin_memory(), msg.cpu().pin_memory(), pk.cpu().pin_memory()
+    h_ok = None
+
+    def e2e_step():
+        return eng.schnorrsig_verify(h_sig.numpy(), h_msg.numpy(), h_pk.numpy(), b200.PK_XONLY32)
+    for _ in range(2):
+        h_ok = e2e_step()
+    if world > 1:
+        dist.barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    tw = time.perf_counter()
+    for _ in range(e2e_steps):
+        h_ok = e2e_step()
+    e2e_ms = (time.perf_counter() - tw) / e2e_steps * 1e3
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te[0])
+    e2e_ok = bool(np.array_equal(h_ok, expected.cpu().numpy()))
+
+    # ---- parity sample against the oracle + CPU baseline (rank 0) -------------------------------------------
+    parity = {"full_batch_matches_construction": full_ok and e2e_ok}
+    cpu_baseline = None
+    if rank == 0:
+        try:
+            from tests.refshim import RefLib
+            ref = RefLib()
+            m = 4096
+            idx = slice(0, m)
+            exp = ref.schnorr_verify(h_sig.numpy()[idx].reshape(-1), h_msg.numpy()[idx].reshape(-1), h_pk.numpy()[idx].reshape(-1))
+            parity.update({"oracle": "oracle/_ref (reference)", "oracle_checked": m, "oracle_mismatches": int((exp != h_ok[:m]).sum())})
+            if world == 1 and not args.no_cpu_baseline:
+                cores = cpu_cores()
+                per_thread = 8192 if cores <= 16 else 4096
+                sample = min(n, per_thread * cores)
+                dt, okc = _cpu_verify_threads(ref, h_sig.numpy().reshape(-1), h_msg.numpy().reshape(-1), h_pk.numpy().reshape(-1), sample, cores)
+                cpu_baseline = {"value": sample / dt, "unit": "verify/s", "cores": cores, "kind": "reference",
+                                "sample": "first %d items of the same batch, %d host threads, reference xonly_pubkey_parse + schnorrsig_verify (oracle/_ref), %.1f s wall" % (sample, cores, dt),
+                                "mismatches_vs_gpu": int((okc != h_ok[:sample]).sum())}
+        except OSError as e:
+            parity.update({"oracle": "unavailable: %s" % e})
+
+    if rank == 0:
+        total = world * n
+        value = total / (ms / 1e3)
+        achieved = n * MAC_PER_ECMULT / (kms / 1e3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        line = {
+            "metric": "schnorrsig_verify/s (= ecmult/s)", "value": value, "unit": "verify/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 (8x32-bit limbs, IMAD.WIDE.U32)", "data": "synthetic",
+            "config": {"workload": "batch 2^%d independent BIP-340 schnorrsig_verify per GPU incl. x-only pubkey parse (random keys/msgs, 1/16 corrupted), %d GPU(s)" % (args.log2n, world),
+                       "per_gpu_batch": n, "global_batch": total, "l2": "inputs %.0f MiB per pass > 126 MB L2" % (n * 128 / 2**20),
+                       "parallelism": "independent shards, table broadcast at init, bitmap all-gather per step"},
+            "clocks": clocks,
+            "e2e": {"value": total / (e2e_ms / 1e3), "unit": "verify/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 128 * n, "d2h_bytes_per_step": n,
+                    "api": "secp256k1_b200_schnorrsig_verify_batch (host buffers, pinned)"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "int32 multiply pipe (IMAD.WIDE.U32); not hbm, not tensor", "achieved": achieved, "peak": imad_peak_tmacs, "unit": "TMAC/s",
+                         "frac": achieved / imad_peak_tmacs, "traffic": None,
+                         "how": "algorithmic 1.81e5 MAC per verify (SURVEY 8d, reference algorithm) x %d verifies / %.3f ms kernel (CUDA events); peak = live IMAD.WIDE.U32 register-saturation probe" % (n, kms),
+                         "kernel": "k_schnorr_verify", "kernel_ms": kms,
+                         "hbm": {"achieved_gbs": n * BYTES_PER_VERIFY / (kms / 1e3) / 1e9, "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback",
+                                 "frac": n * BYTES_PER_VERIFY / (kms / 1e3) / 1e9 / hbm_peak}},
+            "parity": parity,
+        }
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -74,6 +74,10 @@ SECP256K1_B200_API const char *secp256k1_b200_last_error(void);
 SECP256K1_B200_API void *secp256k1_b200_engine_table_ptr(secp256k1_b200_engine *e);
 SECP256K1_B200_API size_t secp256k1_b200_engine_table_bytes(const secp256k1_b200_engine *e);
 SECP256K1_B200_API int secp256k1_b200_engine_table_build(secp256k1_b200_engine *e);
+/* copy the table out of / into the engine (device pointers, table_bytes long): rank 0 builds + exports, the
+ * harness broadcasts the buffer with NCCL, the other ranks import. */
+SECP256K1_B200_API int secp256k1_b200_engine_table_export_dev(secp256k1_b200_engine *e, void *d_dst, void *stream);
+SECP256K1_B200_API int secp256k1_b200_engine_table_import_dev(secp256k1_b200_engine *e, const void *d_src, void *stream);
 /* number of kernel launches issued by this engine so far */
 SECP256K1_B200_API uint64_t secp256k1_b200_engine_launch_count(const secp256k1_b200_engine *e);
 SECP256K1_B200_API int secp256k1_b200_engine_device(const secp256k1_b200_engine *e);
@@ -110,6 +114,14 @@ SECP256K1_B200_API int secp256k1_b200_ecdsa_verify_batch(secp256k1_b200_engine *
         const unsigned char *sig64, int sigfmt, const unsigned char *msghash32, const unsigned char *pk, int pkfmt, size_t n);
 SECP256K1_B200_API int secp256k1_b200_ecdsa_verify_batch_dev(secp256k1_b200_engine *e, unsigned char *d_ok,
         const unsigned char *d_sig64, int sigfmt, const unsigned char *d_msghash32, const unsigned char *d_pk, int pkfmt, size_t n, void *stream);
+
+/* ---- synthetic inputs for tests and benchmarks (NOT constant time; never use with real secrets) ---- */
+/* BIP-340 signatures exactly as secp256k1_schnorrsig_sign_custom(ctx, sig, msg, msglen, keypair, NULL) emits them
+ * (src/modules/schnorrsig/main_impl.h:125-190), plus the x-only public keys; sk must be in [1, n-1]. */
+SECP256K1_B200_API int secp256k1_b200_testdata_schnorrsig_sign_batch(secp256k1_b200_engine *e, unsigned char *sig64, unsigned char *pk32,
+        const unsigned char *sk32, const unsigned char *msg, size_t msglen, size_t n);
+SECP256K1_B200_API int secp256k1_b200_testdata_schnorrsig_sign_batch_dev(secp256k1_b200_engine *e, unsigned char *d_sig64, unsigned char *d_pk32,
+        const unsigned char *d_sk32, const unsigned char *d_msg, size_t msglen, size_t n, void *stream);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,7 @@ struct secp256k1_b200_engine {
     uint32_t* d_bases;
     size_t gtab_bytes;
     bip340_midstate_h mid;
+    sign_consts_h sign;
     cudaStream_t stream;       // engine-owned stream for host-buffer calls
     uint8_t* d_scratch;        // grow-only device scratch for host-buffer calls
     size_t scratch_bytes;
@@ -118,7 +119,13 @@ int secp256k1_b200_engine_create(secp256k1_b200_engine** out, int device, int ge
     {
         sha256 h;
         sha256_init_tagged(h, (const uint8_t*)"BIP0340/challenge", 17);
-        for (int i = 0; i < 8; i++) e->mid.s[i] = h.s[i];
+        for (int i = 0; i < 8; i++) { e->mid.s[i] = h.s[i]; e->sign.mid_challenge[i] = h.s[i]; }
+        sha256_init_tagged(h, (const uint8_t*)"BIP0340/nonce", 13);
+        for (int i = 0; i < 8; i++) e->sign.mid_nonce[i] = h.s[i];
+        const uint8_t zeros[32] = {0};
+        sha256_init_tagged(h, (const uint8_t*)"BIP0340/aux", 11);
+        sha256_write(h, zeros, 32);
+        sha256_finalize(h, e->sign.zero_mask);
     }
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc((void**)&e->d_gtab, e->gtab_bytes) != cudaSuccess ||
@@ -252,6 +259,46 @@ int secp256k1_b200_schnorrsig_verify_batch(secp256k1_b200_engine* e, unsigned ch
     if (!secp256k1_b200_schnorrsig_verify_batch_dev(e, c.at(oo), c.at(os), c.at(om), msglen, c.at(op), pkfmt, n, e->stream)) return 0;
     CK(cudaMemcpyAsync(ok, c.at(oo), n, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
+/* ---- synthetic inputs (tests / benchmarks only) ---------------------------------------------------- */
+int secp256k1_b200_testdata_schnorrsig_sign_batch_dev(secp256k1_b200_engine* e, unsigned char* d_sig64, unsigned char* d_pk32,
+                                                      const unsigned char* d_sk32, const unsigned char* d_msg, size_t msglen, size_t n, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    device_guard guard(e->device);
+    CK(launch_schnorr_sign(d_sig64, d_pk32, nullptr, d_sk32, d_msg, (uint32_t)msglen, n, e->sign, e->gt(), (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_testdata_schnorrsig_sign_batch(secp256k1_b200_engine* e, unsigned char* sig64, unsigned char* pk32,
+                                                  const unsigned char* sk32, const unsigned char* msg, size_t msglen, size_t n) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (n == 0) return 1;
+    std::lock_guard<std::mutex> lock(e->mu);
+    device_guard guard(e->device);
+    carver c(e);
+    size_t os = c.add(64 * n), op = c.add(32 * n), ok = c.add(32 * n), om = c.add(msglen * n + 16);
+    if (!c.commit()) return 0;
+    CK(cudaMemcpyAsync(c.at(ok), sk32, 32 * n, cudaMemcpyHostToDevice, e->stream));
+    if (msglen) CK(cudaMemcpyAsync(c.at(om), msg, msglen * n, cudaMemcpyHostToDevice, e->stream));
+    if (!secp256k1_b200_testdata_schnorrsig_sign_batch_dev(e, c.at(os), c.at(op), c.at(ok), c.at(om), msglen, n, e->stream)) return 0;
+    CK(cudaMemcpyAsync(sig64, c.at(os), 64 * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(pk32, c.at(op), 32 * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
+/* generator-table exchange for the init-time broadcast: copy the table out of / into the engine (device pointers) */
+int secp256k1_b200_engine_table_export_dev(secp256k1_b200_engine* e, void* d_dst, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    device_guard guard(e->device);
+    CK(cudaMemcpyAsync(d_dst, e->d_gtab, e->gtab_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 1;
+}
+int secp256k1_b200_engine_table_import_dev(secp256k1_b200_engine* e, const void* d_src, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    device_guard guard(e->device);
+    CK(cudaMemcpyAsync(e->d_gtab, d_src, e->gtab_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 1;
 }
 

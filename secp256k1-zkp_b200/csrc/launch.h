@@ -8,6 +8,8 @@ namespace b200 {
 
 struct bip340_midstate_h { uint32_t s[8]; };
 
+struct sign_consts_h { uint32_t mid_challenge[8]; uint32_t mid_nonce[8]; uint8_t zero_mask[32]; };
+
 struct gtable_dev {
     const uint32_t* data;
     int gw;
@@ -25,5 +27,8 @@ cudaError_t launch_schnorr_verify(uint8_t* ok, const uint8_t* sig64, const uint8
                                   size_t n, const bip340_midstate_h& mid, const gtable_dev& gt, cudaStream_t s, uint64_t* launches);
 cudaError_t launch_ecdsa_verify(uint8_t* ok, const uint8_t* sig64, int sigfmt, const uint8_t* msg32, const uint8_t* pk, int pkfmt,
                                 size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches);
+
+cudaError_t launch_schnorr_sign(uint8_t* sig64, uint8_t* pk32, uint8_t* ok, const uint8_t* sk32, const uint8_t* msg, uint32_t msglen, size_t n,
+                                const sign_consts_h& c, const gtable_dev& gt, cudaStream_t s, uint64_t* launches);
 
 }  // namespace b200

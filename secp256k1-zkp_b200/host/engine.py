@@ -54,6 +54,10 @@ def load_library():
     lib.secp256k1_b200_engine_device.argtypes = [vp]
     lib.secp256k1_b200_fe_op_batch.argtypes = [vp, ci, u8p, u8p, u8p, sz, ci]
     lib.secp256k1_b200_fe_op_batch_dev.argtypes = [vp, ci, u8p, u8p, u8p, sz, ci, vp]
+    lib.secp256k1_b200_engine_table_export_dev.argtypes = [vp, vp, vp]
+    lib.secp256k1_b200_engine_table_import_dev.argtypes = [vp, vp, vp]
+    lib.secp256k1_b200_testdata_schnorrsig_sign_batch.argtypes = [vp, u8p, u8p, u8p, u8p, sz, sz]
+    lib.secp256k1_b200_testdata_schnorrsig_sign_batch_dev.argtypes = [vp, u8p, u8p, u8p, u8p, sz, sz, vp]
     lib.secp256k1_b200_imad_probe_dev.argtypes = [vp, vp, ci, ci, ci, vp]
     lib.secp256k1_b200_ecmult_batch.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
     lib.secp256k1_b200_ecmult_batch_dev.argtypes = [vp, u8p, u8p, u8p, u8p, sz, vp]
@@ -162,6 +166,24 @@ class Engine:
         ok = np.empty(n, dtype=np.uint8)
         self._ck(self._lib.secp256k1_b200_ecdsa_verify_batch(self._h, _p(ok), _p(sig), sigfmt, _p(m), _p(p), pkfmt, n))
         return ok
+
+    def testdata_schnorrsig_sign(self, sk32, msg, msglen=32):
+        sk = _u8(sk32, len(sk32) if not hasattr(sk32, "size") else sk32.size, "sk32")
+        n = sk.size // 32
+        m = _u8(msg, msglen * n, "msg") if msglen else np.zeros(1, dtype=np.uint8)
+        sig = np.empty(64 * n, dtype=np.uint8)
+        pk = np.empty(32 * n, dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_testdata_schnorrsig_sign_batch(self._h, _p(sig), _p(pk), _p(sk), _p(m), msglen, n))
+        return sig, pk
+
+    def testdata_schnorrsig_sign_dev(self, d_sig64, d_pk32, d_sk32, d_msg, msglen, n, stream=0):
+        self._ck(self._lib.secp256k1_b200_testdata_schnorrsig_sign_batch_dev(self._h, d_sig64, d_pk32, d_sk32, d_msg, msglen, n, stream))
+
+    def table_export_dev(self, d_dst, stream=0):
+        self._ck(self._lib.secp256k1_b200_engine_table_export_dev(self._h, d_dst, stream))
+
+    def table_import_dev(self, d_src, stream=0):
+        self._ck(self._lib.secp256k1_b200_engine_table_import_dev(self._h, d_src, stream))
 
     # -- device-pointer entry points (ints: tensor.data_ptr(); stream: torch stream .cuda_stream) ---
     def fe_op_dev(self, op, d_out, d_a, d_b, n, iters=1, stream=0):

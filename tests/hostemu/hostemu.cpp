@@ -20,6 +20,7 @@ int emu_fe_is_zero(const uint8_t* a) { fe x; fe_set_b32(x, a); return fe_is_zero
 // ---- scalar / group / ecmult / verify logic -------------------------------
 #include "../../secp256k1-zkp_b200/csrc/gtable.cuh"
 #include "../../secp256k1-zkp_b200/csrc/verify.cuh"
+#include "../../secp256k1-zkp_b200/csrc/testdata.cuh"
 #include <vector>
 #include <string.h>
 static std::vector<uint32_t> g_tab;
@@ -70,6 +71,14 @@ int emu_ecmult(uint8_t* r, const uint8_t* a, const uint8_t* na, const uint8_t* n
 }
 int emu_schnorr_verify(const uint8_t* sig, const uint8_t* msg, uint32_t msglen, const uint8_t* pk, int pkfmt) {
     tab_local tab; return schnorr_verify_item(sig, msg, msglen, pk, pkfmt, g_mid, g_gt, tab);
+}
+int emu_schnorr_sign(uint8_t* sig64, uint8_t* pk32, const uint8_t* sk32, const uint8_t* msg, uint32_t msglen) {
+    bip340_sign_consts c; sha256 h;
+    sha256_init_tagged(h, (const uint8_t*)"BIP0340/challenge", 17); for (int i = 0; i < 8; i++) c.mid_challenge[i] = h.s[i];
+    sha256_init_tagged(h, (const uint8_t*)"BIP0340/nonce", 13); for (int i = 0; i < 8; i++) c.mid_nonce[i] = h.s[i];
+    const uint8_t zeros[32] = {0};
+    sha256_init_tagged(h, (const uint8_t*)"BIP0340/aux", 11); sha256_write(h, zeros, 32); sha256_finalize(h, c.zero_mask);
+    return schnorr_sign_item(sig64, pk32, sk32, msg, msglen, c, g_gt);
 }
 int emu_ecdsa_verify(const uint8_t* sig, int sigfmt, const uint8_t* msg32, const uint8_t* pk, int pkfmt) {
     tab_local tab; return ecdsa_verify_item(sig, sigfmt, msg32, pk, pkfmt, g_gt, tab);

@@ -143,3 +143,129 @@ def test_ecdsa_verify_batch_vs_reference(engine, ref):
     got = engine.ecdsa_verify(sig, msg, pk, b200.SIG_COMPACT64, b200.PK_COMPRESSED33)
     assert np.array_equal(got, exp)
     assert 0.2 < exp.mean() < 0.7
+
+
+# ---- the reference's own golden vectors through the C ABI ------------------------------------------
+import json
+import os
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_bip340_vectors_gpu(engine):
+    import secp256k1_zkp_b200 as b200
+    vecs = json.load(open(os.path.join(GOLD, "bip340.json")))["vectors"]
+    for v in vecs:
+        pk = bytes.fromhex(v["pk"])
+        if v["pk_parse_fails"]:
+            assert int(engine.schnorrsig_verify(bytes(64), bytes(32), pk, b200.PK_XONLY32)[0]) == 0
+            continue
+        msg = bytes.fromhex(v["msg"])
+        got = int(engine.schnorrsig_verify(bytes.fromhex(v["sig"]), msg, pk, b200.PK_XONLY32, msglen=len(msg))[0])
+        assert got == v["expected"], v["index"]
+
+
+def test_wycheproof_ecdsa_vectors_gpu(engine):
+    import secp256k1_zkp_b200 as b200
+    vecs = [v for v in json.load(open(os.path.join(GOLD, "wycheproof_ecdsa.json")))["vectors"] if v["der_ok"]]
+    sig = b"".join(bytes.fromhex(v["compact"]) for v in vecs)
+    msg = b"".join(bytes.fromhex(v["msghash"]) for v in vecs)
+    pk65 = [bytes.fromhex(v["pk65"]) for v in vecs]
+    opaque = b"".join(p[1:33][::-1] + p[33:65][::-1] for p in pk65)
+    comp = b"".join(bytes([2 + (p[64] & 1)]) + p[1:33] for p in pk65)
+    exp = np.array([v["expected"] for v in vecs], dtype=np.uint8)
+    assert np.array_equal(engine.ecdsa_verify(sig, msg, opaque, b200.SIG_COMPACT64, b200.PK_OPAQUE64), exp)
+    assert np.array_equal(engine.ecdsa_verify(sig, msg, comp, b200.SIG_COMPACT64, b200.PK_COMPRESSED33), exp)
+
+
+def _digest(points):
+    acc = hashlib.sha256()
+    for xy in points:
+        xy = bytes(xy)
+        acc.update(b"\0" if xy == bytes(64) else b"\x04" + xy)
+    return acc.hexdigest()
+
+
+def test_ecmult_constants_digests_gpu(engine):
+    """run_ecmult_constants (src/tests.c:5800-5960), all three scalar families, each computed two ways
+    (comb table for G; GLV/fixed-window path with A = G)."""
+    g = json.load(open(os.path.join(GOLD, "ecmult.json")))["constants"]
+    fam = {}
+    for key in ("sha_6bit20", "sha_8bit8"):
+        c = g[key]
+        fam[key] = ([0, 1, N - 1] + [int.from_bytes(hashlib.sha256(c["prefix"].to_bytes(4, "little") + i.to_bytes(2, "little")).digest(), "big") % N
+                                      for i in range(c["iter"])], c["digest"])
+    two = []
+    for i in range(37):
+        two += [i, (N - i) % N]
+    for i in range(256):
+        for j in range(1, 256, 2):
+            two.append((j << i) % N)
+    fam["2bit"] = (two, g["2bit"])
+    for key, (scalars, digest) in fam.items():
+        S = b"".join(b32(x) for x in scalars)
+        n = len(scalars)
+        via_g = engine.ecmult(bytes(64 * n), bytes(32 * n), S)
+        via_a = engine.ecmult(G64 * n, S, bytes(32 * n))
+        assert _digest(via_g) == digest, key
+        assert _digest(via_a) == digest, key
+
+
+def test_ecmult_chain_endpoint_gpu(engine):
+    c = json.load(open(os.path.join(GOLD, "ecmult.json")))["chain"]
+    xn, gn, xf, gf = int(c["xn"], 16), int(c["gn"], 16), int(c["xf"], 16), int(c["gf"], 16)
+    ae, ge = 1, 0
+    for _ in range(c["iterations"]):
+        ae = ae * xn % N
+        ge = (ge * xn + gn) % N
+        xn = xn * xf % N
+        gn = gn * gf % N
+    out = engine.ecmult(bytes.fromhex(c["a_xy"]), b32(ae), b32(ge))
+    assert bytes(out[0]).hex() == c["expected_xy"].lower()
+    # and 64 real chain steps, one dependent launch each, against the reference
+    x = bytes.fromhex(c["a_xy"])
+    xn, gn = int(c["xn"], 16), int(c["gn"], 16)
+    for _ in range(64):
+        x = bytes(engine.ecmult(x, b32(xn), b32(gn))[0])
+        xn = xn * xf % N
+        gn = gn * gf % N
+    ae, ge = 1, 0
+    xn, gn = int(c["xn"], 16), int(c["gn"], 16)
+    for _ in range(64):
+        ae = ae * xn % N
+        ge = (ge * xn + gn) % N
+        xn = xn * xf % N
+        gn = gn * gf % N
+    assert x == bytes(engine.ecmult(bytes.fromhex(c["a_xy"]), b32(ae), b32(ge))[0])
+
+
+def test_testdata_signer_matches_reference(engine, ref):
+    n = 3000
+    sk = b"".join(hashlib.sha256(b"tsk%d" % i).digest() for i in range(n))
+    msg = b"".join(hashlib.sha256(b"tmsg%d" % i).digest() for i in range(n))
+    sig, pk = engine.testdata_schnorrsig_sign(sk, msg)
+    rsig, rpk = ref.schnorr_make(sk, msg)
+    assert np.array_equal(sig, rsig) and np.array_equal(pk, rpk)
+
+
+def test_full_size_batch_properties(engine):
+    """2^20-item batch (BASELINE size): signer -> verify round trip, then every 16th item corrupted
+    must be exactly the rejected set (size-independent property, no oracle needed)."""
+    import secp256k1_zkp_b200 as b200
+    n = 1 << 20
+    rnd = np.random.default_rng(5)
+    sk = rnd.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    sk[:, 0] &= 0x7F
+    sk[:, 31] |= 1
+    msg = rnd.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    sig, pk = engine.testdata_schnorrsig_sign(sk, msg)
+    ok = engine.schnorrsig_verify(sig, msg, pk, b200.PK_XONLY32)
+    assert ok.all()
+    sig = sig.reshape(n, 64).copy()
+    bad = np.arange(7, n, 16)
+    bit = bad % 512
+    sig[bad, bit // 8] ^= (1 << (bit % 8)).astype(np.uint8)
+    ok = engine.schnorrsig_verify(sig, msg, pk, b200.PK_XONLY32)
+    exp = np.ones(n, dtype=np.uint8)
+    exp[bad] = 0
+    assert np.array_equal(ok, exp)

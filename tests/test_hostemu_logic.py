@@ -1,0 +1,199 @@
+"""CPU tier: the device headers compiled for the host (portable limb code) against the reference in
+oracle/_ref and against the reference's own golden vectors.  This checks the LOGIC the kernels run
+(field folding, scalar reduction, GLV split, signed-window recoding, group law corner cases, verify
+epilogues); the PTX limb code itself is checked on the GPU tier (test_gpu_parity.py)."""
+import ctypes
+import hashlib
+import json
+import os
+import random
+
+import pytest
+
+from tests.hostemu_lib import load
+
+P = 2**256 - 2**32 - 977
+N = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+G64 = bytes.fromhex("79BE667EF9DCBBAC55A06295CE870B07029BFCDB2DCE28D959F2815B16F81798"
+                    "483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def b32(x):
+    return int(x).to_bytes(32, "big")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return load()
+
+
+def test_field_ops(emu):
+    rnd = random.Random(1)
+    edge = [0, 1, 2, P - 1, P, P + 1, 2**256 - 1, 2**256 - 2, 2**32 + 977, 2**32 + 976, 2**255, P - 2, 2**128, 2**224 - 1]
+    vals = edge + [rnd.getrandbits(256) for _ in range(200)] + [rnd.getrandbits(256) | (2**256 - 2**200) for _ in range(40)]
+    r = ctypes.create_string_buffer(32)
+    inv2 = pow(2, -1, P)
+    for x in vals:
+        for y in rnd.sample(vals, 12) + edge:
+            emu.emu_fe_mul(r, b32(x), b32(y)); assert int.from_bytes(r.raw, "big") == x * y % P
+            emu.emu_fe_add(r, b32(x), b32(y)); assert int.from_bytes(r.raw, "big") == (x + y) % P
+            emu.emu_fe_sub(r, b32(x), b32(y)); assert int.from_bytes(r.raw, "big") == (x - y) % P
+        emu.emu_fe_sqr(r, b32(x)); assert int.from_bytes(r.raw, "big") == x * x % P
+        emu.emu_fe_neg(r, b32(x)); assert int.from_bytes(r.raw, "big") == (-x) % P
+        emu.emu_fe_half(r, b32(x)); assert int.from_bytes(r.raw, "big") == x * inv2 % P
+        for k in (2, 3, 4, 8, 21, 977, 2**20 - 1):
+            emu.emu_fe_mul_small(r, b32(x), k); assert int.from_bytes(r.raw, "big") == x * k % P
+        assert emu.emu_fe_is_zero(b32(x)) == (x % P == 0)
+    for x in vals[:60]:
+        emu.emu_fe_inv(r, b32(x)); assert int.from_bytes(r.raw, "big") == pow(x, P - 2, P)
+        ok = emu.emu_fe_sqrt(r, b32(x))
+        assert ok == (pow(x % P, (P - 1) // 2, P) in (0, 1))
+        assert int.from_bytes(r.raw, "big") == pow(x, (P + 1) // 4, P)
+
+
+def test_scalar_ops_and_sha(emu, ref):
+    rnd = random.Random(2)
+    edge = [0, 1, 2, N - 1, N, N + 1, 2**256 - 1, N // 2, N // 2 + 1, N // 2 + 2, 2**128, 2**128 - 1]
+    vals = edge + [rnd.getrandbits(256) for _ in range(150)]
+    r, r2, q, q2 = (ctypes.create_string_buffer(32) for _ in range(4))
+    for x in vals:
+        for y in rnd.sample(vals, 8) + edge:
+            emu.emu_sc_mul(r, b32(x), b32(y)); assert int.from_bytes(r.raw, "big") == (x % N) * (y % N) % N
+            emu.emu_sc_add(r, b32(x), b32(y)); assert int.from_bytes(r.raw, "big") == ((x % N) + (y % N)) % N
+        emu.emu_sc_negate(r, b32(x)); assert int.from_bytes(r.raw, "big") == (-x) % N
+        ov = emu.emu_sc_set_b32(r, b32(x)); assert ov == (x >= N) and int.from_bytes(r.raw, "big") == x % N
+        assert emu.emu_sc_is_high(b32(x)) == ((x % N) > N // 2)
+        emu.emu_sc_split_lambda(r, r2, b32(x)); ref.lib.ref_scalar_split_lambda(q, q2, b32(x % N))
+        assert r.raw == q.raw and r2.raw == q2.raw
+    for x in vals[:30]:
+        emu.emu_sc_inverse(r, b32(x)); assert int.from_bytes(r.raw, "big") == pow(x % N, N - 2, N)
+    for ln in [0, 1, 55, 56, 63, 64, 65, 119, 120, 128, 1000]:
+        d = bytes(rnd.getrandbits(8) for _ in range(ln))
+        emu.emu_sha256(r, d, ctypes.c_size_t(ln)); assert r.raw == hashlib.sha256(d).digest()
+
+
+def _refmul(ref, k):
+    o = ctypes.create_string_buffer(64)
+    ref.lib.ref_ecmult(o, G64, b32(0), b32(k))
+    return o.raw
+
+
+def test_group_law_and_ecmult(emu, ref):
+    rnd = random.Random(3)
+    L = ref.lib
+    o, o2 = ctypes.create_string_buffer(64), ctypes.create_string_buffer(64)
+    pts = [_refmul(ref, k) for k in [1, 2, 3, 5, N - 1, N - 2, rnd.getrandbits(200)]] + [bytes(64)]
+    for a in pts:
+        emu.emu_ge_double(o, a); L.ref_ge_double(o2, a); assert o.raw == o2.raw
+        for c in pts:
+            emu.emu_ge_add(o, a, c); L.ref_ge_add(o2, a, c); assert o.raw == o2.raw
+            if a != bytes(64):
+                emu.emu_ge_add_mixed(o, a, c); assert o.raw == o2.raw
+    lam = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
+    scal = [0, 1, 2, 3, N - 1, N - 2, 2**128, 2**128 - 1, 2**127, N // 2, N // 2 + 1, lam, N - lam] + \
+           [rnd.getrandbits(256) % N for _ in range(60)] + [rnd.getrandbits(k) for k in (8, 64, 120, 129, 130)]
+    for i, na in enumerate(scal):
+        for ng in rnd.sample(scal, 4) + [0, 1]:
+            a = pts[i % len(pts)]
+            e1 = emu.emu_ecmult(o, a, b32(na), b32(ng)); e2 = L.ref_ecmult(o2, a, b32(na), b32(ng))
+            assert o.raw == o2.raw and e1 == e2
+
+
+def test_bip340_vectors(emu):
+    vecs = json.load(open(os.path.join(GOLD, "bip340.json")))["vectors"]
+    for v in vecs:
+        pk = bytes.fromhex(v["pk"])
+        if v["pk_parse_fails"]:
+            # parsing is fused into the verify: any signature must be rejected
+            assert emu.emu_schnorr_verify(bytes(64), bytes(32), 32, pk, 1) == 0
+            continue
+        msg = bytes.fromhex(v["msg"])
+        got = emu.emu_schnorr_verify(bytes.fromhex(v["sig"]), msg if msg else b"\0", len(msg), pk, 1)
+        assert got == v["expected"], v["index"]
+
+
+def test_wycheproof_ecdsa_vectors(emu):
+    vecs = json.load(open(os.path.join(GOLD, "wycheproof_ecdsa.json")))["vectors"]
+    assert len(vecs) == 463
+    for v in vecs:
+        if not v["der_ok"]:
+            assert v["expected"] == 0
+            continue
+        pk65 = bytes.fromhex(v["pk65"])
+        opaque = pk65[1:33][::-1] + pk65[33:65][::-1]     # 64-byte opaque pubkey = x,y little-endian
+        got = emu.emu_ecdsa_verify(bytes.fromhex(v["compact"]), 1, bytes.fromhex(v["msghash"]), opaque, 0)
+        assert got == v["expected"], v["tcId"]
+        comp = bytes([2 + (pk65[64] & 1)]) + pk65[1:33]
+        assert emu.emu_ecdsa_verify(bytes.fromhex(v["compact"]), 1, bytes.fromhex(v["msghash"]), comp, 2) == v["expected"]
+
+
+def _constants_sha_digest(mul, prefix, iters):
+    acc = hashlib.sha256()
+    scalars = [0, 1, N - 1] + [int.from_bytes(hashlib.sha256(prefix.to_bytes(4, "little") + i.to_bytes(2, "little")).digest(), "big") % N
+                               for i in range(iters)]
+    for x in scalars:
+        xy = mul(x)
+        acc.update(b"\0" if xy == bytes(64) else b"\x04" + xy)
+    return acc.hexdigest()
+
+
+def test_ecmult_constants_digests(emu):
+    """run_ecmult_constants (src/tests.c:5800-5960): digests computed by an independent implementation."""
+    g = json.load(open(os.path.join(GOLD, "ecmult.json")))["constants"]
+    o = ctypes.create_string_buffer(64)
+
+    def mul_g(x):       # ng*G through the comb table
+        emu.emu_ecmult(o, bytes(64), b32(0), b32(x)); return o.raw
+
+    def mul_a(x):       # na*A with A = G through the GLV / fixed-window path
+        emu.emu_ecmult(o, G64, b32(x), b32(0)); return o.raw
+    c = g["sha_6bit20"]
+    assert _constants_sha_digest(mul_g, c["prefix"], c["iter"]) == c["digest"]
+    assert _constants_sha_digest(mul_a, c["prefix"], c["iter"]) == c["digest"]
+    c = g["sha_8bit8"]
+    assert _constants_sha_digest(mul_a, c["prefix"], c["iter"]) == c["digest"]
+
+
+def test_ecmult_chain_endpoint_closed_form(emu):
+    """run_ecmult_chain (src/tests.c:4617-4674): X_{i+1} = xn_i*X_i + gn_i*G; after 20000 steps the
+    reference hard-codes the endpoint.  ae/ge are accumulated with Python integers, then ONE ecmult
+    ae*A + ge*G must hit the expected point."""
+    c = json.load(open(os.path.join(GOLD, "ecmult.json")))["chain"]
+    xn, gn = int(c["xn"], 16), int(c["gn"], 16)
+    xf, gf = int(c["xf"], 16), int(c["gf"], 16)
+    ae, ge = 1, 0
+    for _ in range(c["iterations"]):
+        ae = ae * xn % N
+        ge = (ge * xn + gn) % N
+        xn = xn * xf % N
+        gn = gn * gf % N
+    o = ctypes.create_string_buffer(64)
+    emu.emu_ecmult(o, bytes.fromhex(c["a_xy"]), b32(ae), b32(ge))
+    assert o.raw.hex() == c["expected_xy"].lower()
+
+
+def test_schnorr_and_ecdsa_random_vs_reference(emu, ref):
+    n = 200
+    sk = b"".join(hashlib.sha256(b"sk%d" % i).digest() for i in range(n))
+    msg = b"".join(hashlib.sha256(b"m%d" % i).digest() for i in range(n))
+    sig, pk = ref.schnorr_make(sk, msg)
+    sig, pk, m = bytearray(sig.tobytes()), bytearray(pk.tobytes()), bytearray(msg)
+    for i in range(n):
+        if i % 3 == 1: sig[64 * i + (i * 7) % 64] ^= 1 << (i % 8)
+        if i % 7 == 2: m[32 * i + i % 32] ^= 0x10
+        if i % 11 == 3: pk[32 * i + i % 32] ^= 0x01
+    exp = ref.schnorr_verify(bytes(sig), bytes(m), bytes(pk))
+    for i in range(n):
+        assert emu.emu_schnorr_verify(bytes(sig[64 * i:64 * i + 64]), bytes(m[32 * i:32 * i + 32]), 32, bytes(pk[32 * i:32 * i + 32]), 1) == exp[i]
+    sig, pk = ref.ecdsa_make(sk, msg)
+    sig, pk, m = bytearray(sig.tobytes()), bytearray(pk.tobytes()), bytearray(msg)
+    for i in range(n):
+        if i % 3 == 1: sig[64 * i + (i * 7) % 64] ^= 1 << (i % 8)
+        if i % 7 == 2: m[32 * i + i % 32] ^= 0x10
+        if i % 11 == 3: pk[33 * i + 1 + i % 32] ^= 0x01
+        if i % 13 == 4:
+            s = int.from_bytes(sig[64 * i + 32:64 * i + 64], "big"); sig[64 * i + 32:64 * i + 64] = b32((N - s) % N)
+    exp = ref.ecdsa_verify(bytes(sig), bytes(m), bytes(pk))
+    for i in range(n):
+        assert emu.emu_ecdsa_verify(bytes(sig[64 * i:64 * i + 64]), 1, bytes(m[32 * i:32 * i + 32]), bytes(pk[33 * i:33 * i + 33]), 2) == exp[i]
