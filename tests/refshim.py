@@ -81,6 +81,52 @@ class RefLib:
         m = bytes(msg)
         return 1, self.lib.secp256k1_schnorrsig_verify(self.ctx, bytes(sig64), m if len(m) else None, ctypes.c_size_t(len(m)), pk)
 
+    # ---- pedersen / rangeproof (generator = 64-byte opaque secp256k1_generator = x||y big-endian) ----
+    def generator_h(self):
+        p = ctypes.c_void_p.in_dll(self.lib, "secp256k1_generator_h")
+        return ctypes.string_at(p.value, 64)
+
+    def pedersen_commit(self, blind32, values, gen64):
+        blind32 = _buf(blind32)
+        n = len(blind32) // 32
+        vals = (ctypes.c_uint64 * n)(*[int(v) for v in values])
+        ok = ctypes.create_string_buffer(n)
+        out = ctypes.create_string_buffer(33 * n)
+        self.lib.ref_pedersen_commit_batch.restype = None
+        self.lib.ref_pedersen_commit_batch(self.ctx, ok, out, blind32, vals, bytes(gen64), ctypes.c_size_t(n))
+        return np.frombuffer(ok.raw, dtype=np.uint8).copy(), np.frombuffer(out.raw, dtype=np.uint8).reshape(n, 33).copy()
+
+    def rangeproof_make(self, blind32, values, gen64, min_value=0, exp=0, min_bits=64, stride=5134):
+        blind32 = _buf(blind32)
+        n = len(blind32) // 32
+        vals = (ctypes.c_uint64 * n)(*[int(v) for v in values])
+        proofs = ctypes.create_string_buffer(stride * n)
+        plen = (ctypes.c_size_t * n)()
+        commit = ctypes.create_string_buffer(33 * n)
+        ok = self.lib.ref_rangeproof_make_batch(self.ctx, proofs, ctypes.c_size_t(stride), plen, commit, blind32, vals,
+                                                ctypes.c_uint64(min_value), exp, min_bits, bytes(gen64), ctypes.c_size_t(n))
+        assert ok == 1
+        return (np.frombuffer(proofs.raw, dtype=np.uint8).reshape(n, stride).copy(), np.array(list(plen), dtype=np.uint64),
+                np.frombuffer(commit.raw, dtype=np.uint8).reshape(n, 33).copy())
+
+    def rangeproof_verify(self, commit33, proofs, plen, gen64, extra=b""):
+        proofs = np.ascontiguousarray(proofs, dtype=np.uint8)
+        n, stride = proofs.shape
+        ok = ctypes.create_string_buffer(n)
+        mn = (ctypes.c_uint64 * n)()
+        mx = (ctypes.c_uint64 * n)()
+        pl = (ctypes.c_size_t * n)(*[int(x) for x in plen])
+        self.lib.ref_rangeproof_verify_batch.restype = None
+        self.lib.ref_rangeproof_verify_batch(self.ctx, ok, mn, mx, _buf(commit33), proofs.tobytes(), ctypes.c_size_t(stride), pl,
+                                             bytes(extra) if extra else None, ctypes.c_size_t(len(extra)), bytes(gen64), ctypes.c_size_t(n))
+        return (np.frombuffer(ok.raw, dtype=np.uint8).copy(), np.array(list(mn), dtype=np.uint64), np.array(list(mx), dtype=np.uint64))
+
+    def rangeproof_verify_one(self, commit33, proof, gen64=None, extra=b""):
+        gen64 = gen64 or self.generator_h()
+        proof = np.frombuffer(bytes(proof), dtype=np.uint8).reshape(1, -1)
+        ok, mn, mx = self.rangeproof_verify(bytes(commit33), proof, [proof.shape[1]], gen64, extra)
+        return int(ok[0]), int(mn[0]), int(mx[0])
+
     def ecdsa_make(self, sk32, msg32):
         sk32 = _buf(sk32)
         n = len(sk32) // 32
@@ -95,3 +141,36 @@ class RefLib:
         ok = ctypes.create_string_buffer(n)
         self.lib.ref_ecdsa_verify_batch(self.ctx, ok, sig64, _buf(msg32), _buf(pk33), ctypes.c_size_t(n))
         return np.frombuffer(ok.raw, dtype=np.uint8).copy()
+
+
+PORT_SO = os.path.join(ROOT, "oracle", "libsecp_oracle.so")
+
+
+class PortLib:
+    """oracle/libsecp_oracle.so -- our plain-C restatement (oracle/secp_oracle.c)."""
+
+    def __init__(self, path=PORT_SO):
+        self.lib = ctypes.CDLL(path)
+        self.lib.orc_ecmult_batch.restype = None
+        self.lib.orc_schnorrsig_verify_batch.restype = None
+
+    def ecmult_batch(self, a64, na32, ng32=None):
+        na32 = _buf(na32)
+        n = len(na32) // 32
+        out = ctypes.create_string_buffer(64 * n)
+        self.lib.orc_ecmult_batch(out, _buf(a64), na32, _buf(ng32), ctypes.c_size_t(n))
+        return np.frombuffer(out.raw, dtype=np.uint8).reshape(n, 64)
+
+    def schnorr_verify(self, sig64, msg32, pk32):
+        sig64 = _buf(sig64)
+        n = len(sig64) // 64
+        ok = ctypes.create_string_buffer(n)
+        self.lib.orc_schnorrsig_verify_batch(ok, sig64, _buf(msg32), _buf(pk32), ctypes.c_size_t(n))
+        return np.frombuffer(ok.raw, dtype=np.uint8).copy()
+
+    def rangeproof_verify(self, commit33, proof, gen64, extra=b""):
+        mn, mx = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        proof = bytes(proof)
+        ok = self.lib.orc_rangeproof_verify(ctypes.byref(mn), ctypes.byref(mx), bytes(commit33), proof, ctypes.c_size_t(len(proof)),
+                                            bytes(extra) if extra else None, ctypes.c_size_t(len(extra)), bytes(gen64))
+        return ok, mn.value, mx.value

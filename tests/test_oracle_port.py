@@ -1,0 +1,142 @@
+"""Pins the oracle port (oracle/secp_oracle.c, our plain-C restatement) against the reference's OWN
+golden vectors and, where oracle/_ref exists, against the unmodified reference on random inputs."""
+import ctypes
+import hashlib
+import json
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.refshim import PORT_SO, PortLib, ROOT
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+N = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+P = 2**256 - 2**32 - 977
+G64 = bytes.fromhex("79BE667EF9DCBBAC55A06295CE870B07029BFCDB2DCE28D959F2815B16F81798"
+                    "483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8")
+
+
+def b32(x):
+    return int(x).to_bytes(32, "big")
+
+
+@pytest.fixture(scope="module")
+def port():
+    src = os.path.join(ROOT, "oracle", "secp_oracle.c")
+    if not os.path.exists(PORT_SO) or os.path.getmtime(PORT_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
+    return PortLib()
+
+
+def test_port_field_scalar_sha(port):
+    rnd = random.Random(4)
+    r = ctypes.create_string_buffer(32)
+    for _ in range(300):
+        a, b = rnd.getrandbits(256), rnd.getrandbits(256)
+        port.lib.orc_fe_mul(r, b32(a), b32(b)); assert int.from_bytes(r.raw, "big") == a * b % P
+        port.lib.orc_scalar_mul(r, b32(a), b32(b)); assert int.from_bytes(r.raw, "big") == (a % N) * (b % N) % N
+    for a in [1, 2, P - 1, N - 1, rnd.getrandbits(255)]:
+        port.lib.orc_fe_inv(r, b32(a)); assert int.from_bytes(r.raw, "big") == pow(a, P - 2, P)
+        port.lib.orc_scalar_inverse(r, b32(a)); assert int.from_bytes(r.raw, "big") == pow(a % N, N - 2, N)
+        ok = port.lib.orc_fe_sqrt(r, b32(a)); assert ok == (pow(a % P, (P - 1) // 2, P) in (0, 1))
+    for ln in (0, 1, 55, 56, 64, 119, 1000):
+        d = bytes(rnd.getrandbits(8) for _ in range(ln))
+        port.lib.orc_sha256(r, d, ctypes.c_size_t(ln)); assert r.raw == hashlib.sha256(d).digest()
+
+
+def test_port_bip340_vectors(port):
+    for v in json.load(open(os.path.join(GOLD, "bip340.json")))["vectors"]:
+        pk = bytes.fromhex(v["pk"])
+        if v["pk_parse_fails"]:
+            xy = ctypes.create_string_buffer(64)
+            assert port.lib.orc_xonly_pubkey_parse(xy, pk) == 0
+            continue
+        msg = bytes.fromhex(v["msg"])
+        assert port.lib.orc_schnorrsig_verify(bytes.fromhex(v["sig"]), msg, ctypes.c_size_t(len(msg)), pk) == v["expected"], v["index"]
+
+
+def test_port_wycheproof_vectors(port):
+    for v in json.load(open(os.path.join(GOLD, "wycheproof_ecdsa.json")))["vectors"]:
+        if not v["der_ok"]:
+            continue
+        pk = bytes.fromhex(v["pk65"])
+        got = port.lib.orc_ecdsa_verify(bytes.fromhex(v["compact"]), bytes.fromhex(v["msghash"]), pk, ctypes.c_size_t(65))
+        assert got == v["expected"], v["tcId"]
+
+
+def test_port_ecmult_constants_and_chain(port):
+    g = json.load(open(os.path.join(GOLD, "ecmult.json")))
+    c = g["constants"]["sha_6bit20"]
+    scalars = [0, 1, N - 1] + [int.from_bytes(hashlib.sha256(c["prefix"].to_bytes(4, "little") + i.to_bytes(2, "little")).digest(), "big") % N
+                               for i in range(c["iter"])]
+    n = len(scalars)
+    S = b"".join(b32(x) for x in scalars)
+    for pts in (port.ecmult_batch(bytes(64 * n), bytes(32 * n), S), port.ecmult_batch(G64 * n, S, None)):
+        acc = hashlib.sha256()
+        for xy in pts:
+            xy = bytes(xy)
+            acc.update(b"\0" if xy == bytes(64) else b"\x04" + xy)
+        assert acc.hexdigest() == c["digest"]
+    ch = g["chain"]
+    out = ctypes.create_string_buffer(64)
+    # the real 20000-step chain of run_ecmult_chain (src/tests.c:4617-4674)
+    port.lib.orc_ecmult_chain(out, bytes.fromhex(ch["a_xy"]), bytes.fromhex(ch["xn"]), bytes.fromhex(ch["gn"]),
+                              b32(int(ch["xf"], 16)), b32(int(ch["gf"], 16)), ctypes.c_size_t(ch["iterations"]))
+    assert out.raw.hex() == ch["expected_xy"].lower()
+
+
+def test_port_rangeproof_vectors(port, ref):
+    gen = ref.generator_h()
+    assert gen.hex().startswith("50929b74c1a04954b78b4b6035e97a5e")
+    for v in json.load(open(os.path.join(GOLD, "rangeproof.json")))["vectors"]:
+        proof, commit = bytes.fromhex(v["proof"]), bytes.fromhex(v["commit"])
+        ok, mn, mx = port.rangeproof_verify(commit, proof, gen)
+        assert (ok, mn, mx) == (1, v["min_value"], v["max_value"]), v["name"]
+        # one flipped bit per 97 bytes must be rejected (rangeproof/tests_impl.h:306-310 flips every bit)
+        for pos in range(0, len(proof), 97):
+            bad = bytearray(proof); bad[pos] ^= 1 << (pos % 8)
+            assert port.rangeproof_verify(commit, bytes(bad), gen)[0] == 0
+        assert port.rangeproof_verify(commit, proof + b"\0", gen)[0] == 0   # trailing byte (:303-304)
+
+
+def test_port_vs_reference_random(port, ref):
+    rnd = random.Random(9)
+    n = 40
+    sk = b"".join(hashlib.sha256(b"psk%d" % i).digest() for i in range(n))
+    msg = b"".join(hashlib.sha256(b"pm%d" % i).digest() for i in range(n))
+    sig, pk = ref.schnorr_make(sk, msg)
+    for i in range(0, n, 3):
+        sig[64 * i + i] ^= 2
+    assert np.array_equal(port.schnorr_verify(sig, msg, pk), ref.schnorr_verify(sig, msg, pk))
+    pts = ref.ecmult_batch(G64 * n, bytes(32 * n), sk)
+    na = b"".join(b32(rnd.getrandbits(256) % N) for _ in range(n))
+    assert np.array_equal(port.ecmult_batch(pts, na, msg), ref.ecmult_batch(pts, na, msg))
+    # MSM: Strauss and Pippenger sizes of the reference vs the port's plain sum
+    for m in (1, 7, 100):
+        sc = b"".join(b32(rnd.getrandbits(256) % N) for _ in range(m))
+        pp = ref.ecmult_batch(G64 * m, bytes(32 * m), b"".join(b32(rnd.getrandbits(256) % N) for _ in range(m))).tobytes()
+        out = ctypes.create_string_buffer(64)
+        port.lib.orc_ecmult_multi(out, b32(5), sc, pp, ctypes.c_size_t(m))
+        ok, exp = ref.ecmult_multi(sc, pp, b32(5), scratch_bytes=1 << 20)
+        assert ok == 1 and out.raw == exp
+    # pedersen commitments
+    gen = ref.generator_h()
+    vals = [0, 1, 2**64 - 1] + [rnd.getrandbits(64) for _ in range(5)]
+    blinds = b"".join(b32(rnd.getrandbits(256) % N) for _ in vals)
+    okr, cr = ref.pedersen_commit(blinds, vals, gen)
+    for i, v in enumerate(vals):
+        out = ctypes.create_string_buffer(33)
+        assert port.lib.orc_pedersen_commit(out, blinds[32 * i:32 * i + 32], ctypes.c_uint64(v), gen) == okr[i] == 1
+        assert out.raw == bytes(cr[i])
+    # a fresh random range proof (8-bit, with min_value) and a corrupted copy
+    proofs, plen, commits = ref.rangeproof_make(blinds[:64], [77, 200], gen, min_value=13, exp=1, min_bits=8)
+    for i in range(2):
+        pr = bytes(proofs[i][:int(plen[i])])
+        exp_ok, exp_mn, exp_mx = ref.rangeproof_verify_one(bytes(commits[i]), pr, gen)
+        assert exp_ok == 1
+        assert port.rangeproof_verify(bytes(commits[i]), pr, gen) == (1, exp_mn, exp_mx)
+        bad = bytearray(pr); bad[len(bad) // 2] ^= 4
+        assert port.rangeproof_verify(bytes(commits[i]), bytes(bad), gen)[0] == ref.rangeproof_verify_one(bytes(commits[i]), bytes(bad), gen)[0] == 0
