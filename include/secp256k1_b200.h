@@ -115,6 +115,30 @@ SECP256K1_B200_API int secp256k1_b200_ecdsa_verify_batch(secp256k1_b200_engine *
 SECP256K1_B200_API int secp256k1_b200_ecdsa_verify_batch_dev(secp256k1_b200_engine *e, unsigned char *d_ok,
         const unsigned char *d_sig64, int sigfmt, const unsigned char *d_msghash32, const unsigned char *d_pk, int pkfmt, size_t n, void *stream);
 
+/* ---- Pedersen commitments -------------------------------------------------------------------------- */
+/* commit33[i] = serialize(blind[i]*G + value[i]*gen[i]) (tag 8/9 + x); ok[i] = 0 (and zeros) if blind >= n or the
+ * result is infinity.  gen64: 64-byte secp256k1_generator objects (x||y big-endian, include/secp256k1_generator.h:24);
+ * gen_stride = 0 uses one generator for the whole batch, otherwise gen64 + i*gen_stride.
+ * NOT constant time in the blinding factor: for public recomputation / benchmarking. */
+SECP256K1_B200_API int secp256k1_b200_pedersen_commit_batch(secp256k1_b200_engine *e, unsigned char *ok, unsigned char *commit33,
+        const unsigned char *blind32, const uint64_t *value, const unsigned char *gen64, size_t gen_stride, size_t n);
+SECP256K1_B200_API int secp256k1_b200_pedersen_commit_batch_dev(secp256k1_b200_engine *e, unsigned char *d_ok, unsigned char *d_commit33,
+        const unsigned char *d_blind32, const uint64_t *d_value, const unsigned char *d_gen64, size_t gen_stride, size_t n, void *stream);
+
+/* ---- range proofs ------------------------------------------------------------------------------------ */
+/* One proof per item: proofs + i*proof_stride, plen[i] bytes; commit33: serialized commitments (33 bytes, as
+ * secp256k1_pedersen_commitment_serialize emits / the first 33 bytes of the opaque object); generators as above;
+ * extra: optional extra_commit data (extra + i*extra_stride, extra_len[i] bytes; NULL = none).
+ * ok[i] = accept bit; min_value[i]/max_value[i] are written from the proof header exactly when the reference writes
+ * them (also for proofs that fail later), 0 if the header itself is rejected first. */
+SECP256K1_B200_API int secp256k1_b200_rangeproof_verify_batch(secp256k1_b200_engine *e, unsigned char *ok, uint64_t *min_value, uint64_t *max_value,
+        const unsigned char *commit33, const unsigned char *proofs, size_t proof_stride, const uint32_t *plen,
+        const unsigned char *gen64, size_t gen_stride, const unsigned char *extra, size_t extra_stride, const uint32_t *extra_len, size_t n);
+SECP256K1_B200_API int secp256k1_b200_rangeproof_verify_batch_dev(secp256k1_b200_engine *e, unsigned char *d_ok, uint64_t *d_min_value, uint64_t *d_max_value,
+        const unsigned char *d_commit33, const unsigned char *d_proofs, size_t proof_stride, const uint32_t *d_plen,
+        const unsigned char *d_gen64, size_t gen_stride, const unsigned char *d_extra, size_t extra_stride, const uint32_t *d_extra_len,
+        size_t n, void *stream);
+
 /* ---- synthetic inputs for tests and benchmarks (NOT constant time; never use with real secrets) ---- */
 /* BIP-340 signatures exactly as secp256k1_schnorrsig_sign_custom(ctx, sig, msg, msglen, keypair, NULL) emits them
  * (src/modules/schnorrsig/main_impl.h:125-190), plus the x-only public keys; sk must be in [1, n-1]. */

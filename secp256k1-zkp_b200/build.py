@@ -19,8 +19,8 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler",
 # translation unit -> extra flags
 UNITS = {
     "engine.cu": [],
-    "k_fe.cu": [],
-    "k_fe_portable.cu": ["-DB200_PORTABLE_BN", "-DB200_NS=b200_portable"],
+    "k_fe.cu": ["-DB200_INLINE_FE"],
+    "k_fe_portable.cu": ["-DB200_PORTABLE_BN", "-DB200_NS=b200_portable", "-DB200_INLINE_FE"],
     "k_gtable.cu": [],
     "k_verify.cu": [],
 }

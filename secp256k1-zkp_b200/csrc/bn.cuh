@@ -52,6 +52,33 @@ __device__ __forceinline__ void bn_cmad4(uint32_t* acc, uint32_t a0, uint32_t a1
         : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
 }
+__device__ __forceinline__ void bn_cmad3(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b) {
+    asm("mad.lo.cc.u32  %0, %7, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+        "addc.u32       %6, %6, 0;\n\t"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+}
+__device__ __forceinline__ void bn_cmad2(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t b) {
+    asm("mad.lo.cc.u32  %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32       %4, %4, 0;\n\t"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4])
+        : "r"(a0), "r"(a1), "r"(b));
+}
+__device__ __forceinline__ void bn_cmad1(uint32_t* acc, uint32_t a0, uint32_t b) {
+    asm("mad.lo.cc.u32  %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32       %2, %2, 0;\n\t"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2])
+        : "r"(a0), "r"(b));
+}
 #endif
 
 // r[0..15] = a[0..7] * b[0..7]
@@ -119,7 +146,84 @@ HD void bn_mul_wide(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 
 // r[0..15] = a[0..7]^2
 HD void bn_sqr_wide(uint32_t* r, const uint32_t* a) {
+#if BN_PTX
+    // off-diagonal products a_i*a_j (i<j), 28 instead of 56, in the same even/odd column split
+    uint32_t e[17], o[17];
+#pragma unroll
+    for (int i = 0; i < 17; i++) { e[i] = 0; o[i] = 0; }
+    bn_cmad3(e + 2, a[2], a[4], a[6], a[0]);   bn_cmad4(o + 0, a[1], a[3], a[5], a[7], a[0]);
+    bn_cmad3(e + 4, a[3], a[5], a[7], a[1]);   bn_cmad3(o + 2, a[2], a[4], a[6], a[1]);
+    bn_cmad2(e + 6, a[4], a[6], a[2]);         bn_cmad3(o + 4, a[3], a[5], a[7], a[2]);
+    bn_cmad2(e + 8, a[5], a[7], a[3]);         bn_cmad2(o + 6, a[4], a[6], a[3]);
+    bn_cmad1(e + 10, a[6], a[4]);              bn_cmad2(o + 8, a[5], a[7], a[4]);
+    bn_cmad1(e + 12, a[7], a[5]);              bn_cmad1(o + 10, a[6], a[5]);
+    bn_cmad1(o + 12, a[7], a[6]);
+    // s = e + (o << 32)   (s[0] = s[1]... e[0], e[1] are zero by construction)
+    uint32_t s[16], cmid, cdummy;
+    s[0] = 0;
+    asm("add.cc.u32  %0, %9,  %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32    %8, 0, 0;\n\t"
+        : "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(s[8]), "=r"(cmid)
+        : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(e[8]),
+          "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]));
+    asm("add.cc.u32  %7, %22, 0xffffffff;\n\t"
+        "addc.cc.u32 %0, %8,  %15;\n\t"
+        "addc.cc.u32 %1, %9,  %16;\n\t"
+        "addc.cc.u32 %2, %10, %17;\n\t"
+        "addc.cc.u32 %3, %11, %18;\n\t"
+        "addc.cc.u32 %4, %12, %19;\n\t"
+        "addc.cc.u32 %5, %13, %20;\n\t"
+        "addc.u32    %6, %14, %21;\n\t"
+        : "=r"(s[9]), "=r"(s[10]), "=r"(s[11]), "=r"(s[12]), "=r"(s[13]), "=r"(s[14]), "=r"(s[15]), "=r"(cdummy)
+        : "r"(e[9]), "r"(e[10]), "r"(e[11]), "r"(e[12]), "r"(e[13]), "r"(e[14]), "r"(e[15]),
+          "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(cmid));
+    // d = 2*s (funnel shifts, no carry chain)
+    uint32_t d[16];
+    d[0] = s[0] << 1;
+#pragma unroll
+    for (int k = 1; k < 16; k++) d[k] = __funnelshift_l(s[k - 1], s[k], 1);
+    // diagonal squares
+    uint32_t q[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        asm("mul.lo.u32 %0, %2, %2;\n\tmul.hi.u32 %1, %2, %2;\n\t" : "=r"(q[2 * i]), "=r"(q[2 * i + 1]) : "r"(a[i]));
+    }
+    // r = d + q
+    asm("add.cc.u32  %0, %9,  %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32    %8, 0, 0;\n\t"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(cmid)
+        : "r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3]), "r"(d[4]), "r"(d[5]), "r"(d[6]), "r"(d[7]),
+          "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]), "r"(q[4]), "r"(q[5]), "r"(q[6]), "r"(q[7]));
+    asm("add.cc.u32  %8, %25, 0xffffffff;\n\t"
+        "addc.cc.u32 %0, %9,  %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.u32    %7, %16, %24;\n\t"
+        : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(cdummy)
+        : "r"(d[8]), "r"(d[9]), "r"(d[10]), "r"(d[11]), "r"(d[12]), "r"(d[13]), "r"(d[14]), "r"(d[15]),
+          "r"(q[8]), "r"(q[9]), "r"(q[10]), "r"(q[11]), "r"(q[12]), "r"(q[13]), "r"(q[14]), "r"(q[15]), "r"(cmid));
+    (void)cdummy;
+#else
     bn_mul_wide(r, a, a);
+#endif
 }
 
 // r = a + b, returns carry (0/1)

@@ -331,4 +331,84 @@ int secp256k1_b200_ecdsa_verify_batch(secp256k1_b200_engine* e, unsigned char* o
     return 1;
 }
 
+/* ---- Pedersen commitments / range proofs --------------------------------------------------------------- */
+int secp256k1_b200_pedersen_commit_batch_dev(secp256k1_b200_engine* e, unsigned char* d_ok, unsigned char* d_commit33,
+                                             const unsigned char* d_blind32, const uint64_t* d_value, const unsigned char* d_gen64,
+                                             size_t gen_stride, size_t n, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (gen_stride != 0 && gen_stride < 64) { set_error("gen_stride must be 0 (shared generator) or >= 64"); return 0; }
+    device_guard guard(e->device);
+    CK(launch_pedersen_commit(d_ok, d_commit33, d_blind32, d_value, d_gen64, gen_stride, n, e->gt(), (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_pedersen_commit_batch(secp256k1_b200_engine* e, unsigned char* ok, unsigned char* commit33, const unsigned char* blind32,
+                                         const uint64_t* value, const unsigned char* gen64, size_t gen_stride, size_t n) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (gen_stride != 0 && gen_stride < 64) { set_error("gen_stride must be 0 (shared generator) or >= 64"); return 0; }
+    if (n == 0) return 1;
+    std::lock_guard<std::mutex> lock(e->mu);
+    device_guard guard(e->device);
+    carver c(e);
+    size_t gbytes = gen_stride ? gen_stride * n : 64;
+    size_t ob = c.add(32 * n), ov = c.add(8 * n), og = c.add(gbytes), ook = c.add(n), oc = c.add(33 * n);
+    if (!c.commit()) return 0;
+    CK(cudaMemcpyAsync(c.at(ob), blind32, 32 * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(ov), value, 8 * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(og), gen64, gbytes, cudaMemcpyHostToDevice, e->stream));
+    if (!secp256k1_b200_pedersen_commit_batch_dev(e, c.at(ook), c.at(oc), c.at(ob), (const uint64_t*)c.at(ov), c.at(og), gen_stride, n, e->stream)) return 0;
+    CK(cudaMemcpyAsync(ok, c.at(ook), n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(commit33, c.at(oc), 33 * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
+int secp256k1_b200_rangeproof_verify_batch_dev(secp256k1_b200_engine* e, unsigned char* d_ok, uint64_t* d_min_value, uint64_t* d_max_value,
+                                               const unsigned char* d_commit33, const unsigned char* d_proofs, size_t proof_stride,
+                                               const uint32_t* d_plen, const unsigned char* d_gen64, size_t gen_stride,
+                                               const unsigned char* d_extra, size_t extra_stride, const uint32_t* d_extra_len, size_t n, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (gen_stride != 0 && gen_stride < 64) { set_error("gen_stride must be 0 (shared generator) or >= 64"); return 0; }
+    device_guard guard(e->device);
+    CK(launch_rangeproof_verify(d_ok, d_min_value, d_max_value, d_commit33, d_proofs, proof_stride, d_plen, d_gen64, gen_stride,
+                                d_extra, extra_stride, d_extra_len, n, e->gt(), (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_rangeproof_verify_batch(secp256k1_b200_engine* e, unsigned char* ok, uint64_t* min_value, uint64_t* max_value,
+                                           const unsigned char* commit33, const unsigned char* proofs, size_t proof_stride, const uint32_t* plen,
+                                           const unsigned char* gen64, size_t gen_stride, const unsigned char* extra, size_t extra_stride,
+                                           const uint32_t* extra_len, size_t n) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (gen_stride != 0 && gen_stride < 64) { set_error("gen_stride must be 0 (shared generator) or >= 64"); return 0; }
+    if (n == 0) return 1;
+    for (size_t i = 0; i < n; i++) {
+        if (plen[i] > proof_stride) { set_error("rangeproof_verify_batch: plen[i] > proof_stride"); return 0; }
+        if (extra && extra_len && extra_len[i] > extra_stride) { set_error("rangeproof_verify_batch: extra_len[i] > extra_stride"); return 0; }
+    }
+    std::lock_guard<std::mutex> lock(e->mu);
+    device_guard guard(e->device);
+    carver c(e);
+    size_t gbytes = gen_stride ? gen_stride * n : 64;
+    bool has_extra = extra && extra_len && extra_stride;
+    size_t oc = c.add(33 * n), op = c.add(proof_stride * n), ol = c.add(4 * n), og = c.add(gbytes);
+    size_t oe = c.add(has_extra ? extra_stride * n : 16), oel = c.add(4 * n);
+    size_t ook = c.add(n), omn = c.add(8 * n), omx = c.add(8 * n);
+    if (!c.commit()) return 0;
+    CK(cudaMemcpyAsync(c.at(oc), commit33, 33 * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(op), proofs, proof_stride * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(ol), plen, 4 * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(og), gen64, gbytes, cudaMemcpyHostToDevice, e->stream));
+    if (has_extra) {
+        CK(cudaMemcpyAsync(c.at(oe), extra, extra_stride * n, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(c.at(oel), extra_len, 4 * n, cudaMemcpyHostToDevice, e->stream));
+    }
+    if (!secp256k1_b200_rangeproof_verify_batch_dev(e, c.at(ook), (uint64_t*)c.at(omn), (uint64_t*)c.at(omx), c.at(oc), c.at(op), proof_stride,
+                                                    (const uint32_t*)c.at(ol), c.at(og), gen_stride, has_extra ? c.at(oe) : nullptr, extra_stride,
+                                                    has_extra ? (const uint32_t*)c.at(oel) : nullptr, n, e->stream)) return 0;
+    CK(cudaMemcpyAsync(ok, c.at(ook), n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(min_value, c.at(omn), 8 * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(max_value, c.at(omx), 8 * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
 }  // extern "C"

@@ -107,15 +107,37 @@ HD void fe_reduce512(fe& r, const uint32_t* t) {
 #endif
 }
 
-HD void fe_mul(fe& r, const fe& a, const fe& b) {
+HD void fe_mul_inl(fe& r, const fe& a, const fe& b) {
     uint32_t t[16];
     bn_mul_wide(t, a.v, b.v);
     fe_reduce512(r, t);
 }
-HD void fe_sqr(fe& r, const fe& a) {
+HD void fe_sqr_inl(fe& r, const fe& a) {
     uint32_t t[16];
     bn_sqr_wide(t, a.v);
     fe_reduce512(r, t);
+}
+// In the large kernels fe_mul / fe_sqr are real (non-inlined) functions: operands travel BY VALUE in registers
+// (checked in SASS: CALL.REL.NOINC, no local-memory traffic).  Fully inlined, a verify kernel is several hundred KB
+// of code and ncu shows it instruction-fetch bound (stall_no_instruction dominant); with ~2 KB bodies shared by all
+// call sites the hot loops sit in the instruction cache.  The field micro-kernel (k_fe.cu) keeps the inlined form.
+#if defined(__CUDACC__)
+static __device__ __noinline__ fe fe_mul_nv(fe a, fe b) { fe r; fe_mul_inl(r, a, b); return r; }
+static __device__ __noinline__ fe fe_sqr_nv(fe a) { fe r; fe_sqr_inl(r, a); return r; }
+#endif
+HD void fe_mul(fe& r, const fe& a, const fe& b) {
+#if defined(__CUDA_ARCH__) && !defined(B200_INLINE_FE)
+    r = fe_mul_nv(a, b);
+#else
+    fe_mul_inl(r, a, b);
+#endif
+}
+HD void fe_sqr(fe& r, const fe& a) {
+#if defined(__CUDA_ARCH__) && !defined(B200_INLINE_FE)
+    r = fe_sqr_nv(a);
+#else
+    fe_sqr_inl(r, a);
+#endif
 }
 
 // r = a + b

@@ -1,0 +1,119 @@
+// k_rangeproof.cu -- rangeproof_verify (one warp per proof, one lane per ring) and pedersen_commit kernels.
+#include "rangeproof.cuh"
+#include "launch.h"
+
+namespace b200 {
+
+#define RP_WARPS 4
+#define RP_TAB_WORDS (32 * 8 * 16)                 // per warp: 32 lanes x 8 entries x 16 words
+#define RP_WARP_BYTES (RP_TAB_WORDS * 4 + 32 + 32 * 33 + 32)   // tables (aliased with the point-sum scratch) + m + R33[32] + pad
+#define RP_WARP_STRIDE ((RP_WARP_BYTES + 127) & ~127)
+
+__global__ void __launch_bounds__(RP_WARPS * 32, 3) k_rangeproof_verify(uint8_t* __restrict__ ok, uint64_t* __restrict__ minv, uint64_t* __restrict__ maxv,
+        const uint8_t* __restrict__ commit33, const uint8_t* __restrict__ proofs, size_t stride, const uint32_t* __restrict__ plen,
+        const uint8_t* __restrict__ gen64, size_t gen_stride, const uint8_t* __restrict__ extra, size_t extra_stride,
+        const uint32_t* __restrict__ extra_len, size_t n, ecmult_gtable gt) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t item = (size_t)blockIdx.x * RP_WARPS + warp;
+    if (item >= n) return;                                  // whole warp leaves together
+    uint8_t* wbase = smem_raw + (size_t)warp * RP_WARP_STRIDE;
+    uint32_t* tabw = reinterpret_cast<uint32_t*>(wbase);
+    gej* pts = reinterpret_cast<gej*>(wbase);               // aliases the table region (used before it)
+    uint8_t* m32 = wbase + RP_TAB_WORDS * 4;
+    uint8_t* r33 = m32 + 32;
+    const uint8_t* proof = proofs + item * stride;
+    const size_t pl = plen[item];
+    const uint8_t* c33 = commit33 + 33 * item;
+    const uint8_t* g64 = gen64 + gen_stride * item;
+    const uint8_t* ex = extra ? extra + extra_stride * item : nullptr;
+    const size_t exl = (extra && extra_len) ? extra_len[item] : 0;
+
+    rp_header h;
+    uint64_t mn = 0, mx = 0;
+    int hdr_ok = rp_parse_header(h, mn, mx, proof, pl);     // identical in all lanes
+    if (lane == 0) { minv[item] = mn; maxv[item] = mx; }
+    if (!hdr_ok) { if (lane == 0) ok[item] = 0; return; }
+
+    // ---- P1: decompress digit commitments (lanes < rings-1) and the value commitment (lane rings-1)
+    ge genp; rp_generator_load(genp, g64);
+    ge mine; mine.inf = 1;
+    int good = 1;
+    if (lane + 1 < h.rings) good = rp_digit_commitment_load(mine, h, proof, lane);
+    else if (lane + 1 == h.rings) good = rp_commitment_load(mine, c33);
+    {
+        gej t;
+        if (lane + 1 < h.rings && good) gej_set_ge(t, mine); else gej_set_infinity(t);
+        pts[lane] = t;
+    }
+    int gen_sq = fe_is_square(genp.y);                       // all lanes (uniform)
+    if (lane == 0) rp_message_hash(m32, h, proof, c33, g64, gen_sq, ex, exl);
+    good = __all_sync(0xffffffffu, good);
+    __syncwarp();
+    // ---- P2: accj = min_value*H + sum C_i
+    for (int d = 16; d >= 1; d >>= 1) {
+        if ((int)lane < d) { gej t; gej_add(t, pts[lane], pts[lane + d]); pts[lane] = t; }
+        __syncwarp();
+    }
+    gej pub; gej_set_infinity(pub);
+    if (lane + 1 == h.rings && good) {
+        gej acc = pts[0];
+        if (h.min_value) { gej mh, t; rp_small_mult(mh, h.min_value, genp); gej_add(t, acc, mh); acc = t; }
+        gej nacc; gej_neg(nacc, acc);
+        gej_add_ge(pub, nacc, mine);                         // commit - accj (rangeproof_impl.h:627-631)
+        if (pub.inf) good = 0;
+    } else if (lane + 1 < h.rings) {
+        gej_set_ge(pub, mine);
+    }
+    good = __all_sync(0xffffffffu, good);
+    __syncwarp();                                            // pts[] dead from here: the region becomes the tables
+    if (!good) { if (lane == 0) ok[item] = 0; return; }
+    // ---- P3/P4: ring walk
+    int ring_ok = 1;
+    if (lane < h.rings) {
+        gej base;
+        rp_ring_base(base, genp, h.exp, lane);
+        tab_shared tab = {tabw + lane, 32};
+        ring_ok = rp_ring_walk(r33 + 33 * lane, h, proof, m32, lane, pub, base, gt, tab);
+    }
+    ring_ok = __all_sync(0xffffffffu, ring_ok);
+    __syncwarp();
+    // ---- P5
+    if (lane == 0) ok[item] = (uint8_t)(ring_ok && rp_final_check(h, proof, r33, m32));
+}
+
+__global__ void __launch_bounds__(128) k_pedersen_commit(uint8_t* __restrict__ ok, uint8_t* __restrict__ out33, const uint8_t* __restrict__ blind32,
+        const uint64_t* __restrict__ value, const uint8_t* __restrict__ gen64, size_t gen_stride, size_t n, ecmult_gtable gt) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t b[32], g[64], o[33];
+    for (int k = 0; k < 32; k++) b[k] = blind32[32 * i + k];
+    for (int k = 0; k < 64; k++) g[k] = gen64[gen_stride * i + k];
+    int r = pedersen_commit_item(o, b, value[i], g, gt);
+    for (int k = 0; k < 33; k++) out33[33 * i + k] = o[k];
+    ok[i] = (uint8_t)r;
+}
+
+static inline ecmult_gtable to_gt(const gtable_dev& g) { ecmult_gtable t; t.data = g.data; t.gw = g.gw; t.windows = g.windows; return t; }
+
+cudaError_t launch_rangeproof_verify(uint8_t* ok, uint64_t* minv, uint64_t* maxv, const uint8_t* commit33, const uint8_t* proofs, size_t stride,
+                                     const uint32_t* plen, const uint8_t* gen64, size_t gen_stride, const uint8_t* extra, size_t extra_stride,
+                                     const uint32_t* extra_len, size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches) {
+    if (n == 0) return cudaSuccess;
+    const int smem = RP_WARPS * RP_WARP_STRIDE;
+    cudaError_t err = cudaFuncSetAttribute(k_rangeproof_verify, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return err;
+    k_rangeproof_verify<<<(unsigned)((n + RP_WARPS - 1) / RP_WARPS), RP_WARPS * 32, smem, s>>>(ok, minv, maxv, commit33, proofs, stride, plen,
+                                                                                            gen64, gen_stride, extra, extra_stride, extra_len, n, to_gt(gt));
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+cudaError_t launch_pedersen_commit(uint8_t* ok, uint8_t* out33, const uint8_t* blind32, const uint64_t* value, const uint8_t* gen64, size_t gen_stride,
+                                   size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches) {
+    if (n == 0) return cudaSuccess;
+    k_pedersen_commit<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(ok, out33, blind32, value, gen64, gen_stride, n, to_gt(gt));
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace b200

@@ -20,7 +20,7 @@ __device__ __forceinline__ void load_bytes_global(uint8_t* dst, const uint8_t* s
     }
 }
 
-__global__ void __launch_bounds__(VERIFY_BLOCK) k_ecmult(uint8_t* __restrict__ out64, const uint8_t* __restrict__ a64,
+__global__ void __launch_bounds__(VERIFY_BLOCK, 3) k_ecmult(uint8_t* __restrict__ out64, const uint8_t* __restrict__ a64,
         const uint8_t* __restrict__ na32, const uint8_t* __restrict__ ng32, size_t n, ecmult_gtable gt) {
     extern __shared__ uint32_t smem[];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(VERIFY_BLOCK) k_ecmult(uint8_t* __restrict__ o
     else for (int k = 0; k < 64; k++) out64[64 * i + k] = o[k];
 }
 
-__global__ void __launch_bounds__(VERIFY_BLOCK) k_schnorr_verify(uint8_t* __restrict__ ok, const uint8_t* __restrict__ sig64,
+__global__ void __launch_bounds__(VERIFY_BLOCK, 3) k_schnorr_verify(uint8_t* __restrict__ ok, const uint8_t* __restrict__ sig64,
         const uint8_t* __restrict__ msg, uint32_t msglen, const uint8_t* __restrict__ pk, int pkfmt, size_t n,
         bip340_midstate mid, ecmult_gtable gt) {
     extern __shared__ uint32_t smem[];
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(VERIFY_BLOCK) k_schnorr_verify(uint8_t* __rest
     ok[i] = (uint8_t)schnorr_verify_item(in, msg + (size_t)msglen * i, msglen, in + 64, pkfmt, mid, gt, tab);
 }
 
-__global__ void __launch_bounds__(VERIFY_BLOCK) k_ecdsa_verify(uint8_t* __restrict__ ok, const uint8_t* __restrict__ sig64, int sigfmt,
+__global__ void __launch_bounds__(VERIFY_BLOCK, 3) k_ecdsa_verify(uint8_t* __restrict__ ok, const uint8_t* __restrict__ sig64, int sigfmt,
         const uint8_t* __restrict__ msg32, const uint8_t* __restrict__ pk, int pkfmt, size_t n, ecmult_gtable gt) {
     extern __shared__ uint32_t smem[];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

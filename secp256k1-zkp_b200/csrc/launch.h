@@ -31,4 +31,13 @@ cudaError_t launch_ecdsa_verify(uint8_t* ok, const uint8_t* sig64, int sigfmt, c
 cudaError_t launch_schnorr_sign(uint8_t* sig64, uint8_t* pk32, uint8_t* ok, const uint8_t* sk32, const uint8_t* msg, uint32_t msglen, size_t n,
                                 const sign_consts_h& c, const gtable_dev& gt, cudaStream_t s, uint64_t* launches);
 
+cudaError_t launch_rangeproof_verify(uint8_t* ok, uint64_t* minv, uint64_t* maxv, const uint8_t* commit33, const uint8_t* proofs, size_t stride,
+                                     const uint32_t* plen, const uint8_t* gen64, size_t gen_stride, const uint8_t* extra, size_t extra_stride,
+                                     const uint32_t* extra_len, size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_pedersen_commit(uint8_t* ok, uint8_t* out33, const uint8_t* blind32, const uint64_t* value, const uint8_t* gen64, size_t gen_stride,
+                                   size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches);
+
+cudaError_t launch_codec(uint8_t* ok, uint8_t* out64, const uint8_t* in, size_t in_stride, uint32_t in_len, int fmt, size_t n,
+                         cudaStream_t s, uint64_t* launches);
+
 }  // namespace b200

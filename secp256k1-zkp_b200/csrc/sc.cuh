@@ -106,10 +106,20 @@ HD void sc_reduce512(sc& r, const uint32_t* t) {
     bn_add8(r.v, m3, add);
     sc_reduce_once(r);
 }
-HD void sc_mul(sc& r, const sc& a, const sc& b) {
+HD void sc_mul_inl(sc& r, const sc& a, const sc& b) {
     uint32_t t[16];
     bn_mul_wide(t, a.v, b.v);
     sc_reduce512(r, t);
+}
+#if defined(__CUDACC__)
+static __device__ __noinline__ sc sc_mul_nv(sc a, sc b) { sc r; sc_mul_inl(r, a, b); return r; }
+#endif
+HD void sc_mul(sc& r, const sc& a, const sc& b) {
+#if defined(__CUDA_ARCH__)
+    r = sc_mul_nv(a, b);      // one shared body per kernel instead of ~300 inlined instructions per call site
+#else
+    sc_mul_inl(r, a, b);
+#endif
 }
 HD void sc_sqr(sc& r, const sc& a) { sc_mul(r, a, a); }
 

@@ -13,7 +13,7 @@ struct sha256 {
 
 HD uint32_t sha_rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
 
-HD void sha256_compress(uint32_t* s, const uint32_t* win) {
+HDNI void sha256_compress(uint32_t* s, const uint32_t* win) {   // ~2500 instructions: never inline
     const uint32_t K[64] = {
         0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
         0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,

@@ -58,6 +58,11 @@ def load_library():
     lib.secp256k1_b200_engine_table_import_dev.argtypes = [vp, vp, vp]
     lib.secp256k1_b200_testdata_schnorrsig_sign_batch.argtypes = [vp, u8p, u8p, u8p, u8p, sz, sz]
     lib.secp256k1_b200_testdata_schnorrsig_sign_batch_dev.argtypes = [vp, u8p, u8p, u8p, u8p, sz, sz, vp]
+    u64p = ctypes.c_void_p
+    lib.secp256k1_b200_pedersen_commit_batch.argtypes = [vp, u8p, u8p, u8p, u64p, u8p, sz, sz]
+    lib.secp256k1_b200_pedersen_commit_batch_dev.argtypes = [vp, u8p, u8p, u8p, u64p, u8p, sz, sz, vp]
+    lib.secp256k1_b200_rangeproof_verify_batch.argtypes = [vp, u8p, u64p, u64p, u8p, u8p, sz, vp, u8p, sz, u8p, sz, vp, sz]
+    lib.secp256k1_b200_rangeproof_verify_batch_dev.argtypes = [vp, u8p, u64p, u64p, u8p, u8p, sz, vp, u8p, sz, u8p, sz, vp, sz, vp]
     lib.secp256k1_b200_imad_probe_dev.argtypes = [vp, vp, ci, ci, ci, vp]
     lib.secp256k1_b200_ecmult_batch.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
     lib.secp256k1_b200_ecmult_batch_dev.argtypes = [vp, u8p, u8p, u8p, u8p, sz, vp]
@@ -166,6 +171,51 @@ class Engine:
         ok = np.empty(n, dtype=np.uint8)
         self._ck(self._lib.secp256k1_b200_ecdsa_verify_batch(self._h, _p(ok), _p(sig), sigfmt, _p(m), _p(p), pkfmt, n))
         return ok
+
+    def pedersen_commit(self, blind32, values, gen64):
+        """gen64: 64 bytes (shared) or n*64 bytes (one generator per item)"""
+        b = _u8(blind32, len(blind32) if not hasattr(blind32, "size") else blind32.size, "blind32")
+        n = b.size // 32
+        v = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1)
+        if v.size != n:
+            raise ValueError("values: expected %d entries" % n)
+        g = _u8(gen64, len(gen64) if not hasattr(gen64, "size") else gen64.size, "gen64")
+        stride = 0 if g.size == 64 else 64
+        if stride and g.size != 64 * n:
+            raise ValueError("gen64: expected 64 or %d bytes" % (64 * n))
+        ok = np.empty(n, dtype=np.uint8)
+        out = np.empty(33 * n, dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_pedersen_commit_batch(self._h, _p(ok), _p(out), _p(b), _p(v), _p(g), stride, n))
+        return ok, out.reshape(n, 33)
+
+    def rangeproof_verify(self, commit33, proofs, plen, gen64, extra=None, extra_len=None):
+        """proofs: uint8 array (n, stride); plen: n lengths; gen64: 64 or n*64 bytes; extra: (n, estride) or None"""
+        pr = np.ascontiguousarray(proofs, dtype=np.uint8)
+        n, stride = pr.shape
+        c = _u8(commit33, 33 * n, "commit33")
+        pl = np.ascontiguousarray(plen, dtype=np.uint32).reshape(-1)
+        g = _u8(gen64, len(gen64) if not hasattr(gen64, "size") else gen64.size, "gen64")
+        gstride = 0 if g.size == 64 else 64
+        ex = el = None
+        estride = 0
+        if extra is not None:
+            ex = np.ascontiguousarray(extra, dtype=np.uint8)
+            estride = ex.shape[1]
+            el = np.ascontiguousarray(extra_len, dtype=np.uint32).reshape(-1)
+        ok = np.empty(n, dtype=np.uint8)
+        mn = np.zeros(n, dtype=np.uint64)
+        mx = np.zeros(n, dtype=np.uint64)
+        self._ck(self._lib.secp256k1_b200_rangeproof_verify_batch(self._h, _p(ok), _p(mn), _p(mx), _p(c), _p(pr), stride, _p(pl), _p(g), gstride,
+                                                                  _p(ex), estride, _p(el), n))
+        return ok, mn, mx
+
+    def rangeproof_verify_dev(self, d_ok, d_min, d_max, d_commit33, d_proofs, stride, d_plen, d_gen64, gen_stride, n, stream=0,
+                              d_extra=None, extra_stride=0, d_extra_len=None):
+        self._ck(self._lib.secp256k1_b200_rangeproof_verify_batch_dev(self._h, d_ok, d_min, d_max, d_commit33, d_proofs, stride, d_plen, d_gen64,
+                                                                      gen_stride, d_extra, extra_stride, d_extra_len, n, stream))
+
+    def pedersen_commit_dev(self, d_ok, d_commit33, d_blind32, d_value, d_gen64, gen_stride, n, stream=0):
+        self._ck(self._lib.secp256k1_b200_pedersen_commit_batch_dev(self._h, d_ok, d_commit33, d_blind32, d_value, d_gen64, gen_stride, n, stream))
 
     def testdata_schnorrsig_sign(self, sk32, msg, msglen=32):
         sk = _u8(sk32, len(sk32) if not hasattr(sk32, "size") else sk32.size, "sk32")

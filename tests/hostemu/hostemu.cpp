@@ -21,6 +21,7 @@ int emu_fe_is_zero(const uint8_t* a) { fe x; fe_set_b32(x, a); return fe_is_zero
 #include "../../secp256k1-zkp_b200/csrc/gtable.cuh"
 #include "../../secp256k1-zkp_b200/csrc/verify.cuh"
 #include "../../secp256k1-zkp_b200/csrc/testdata.cuh"
+#include "../../secp256k1-zkp_b200/csrc/rangeproof.cuh"
 #include <vector>
 #include <string.h>
 static std::vector<uint32_t> g_tab;
@@ -79,6 +80,48 @@ int emu_schnorr_sign(uint8_t* sig64, uint8_t* pk32, const uint8_t* sk32, const u
     const uint8_t zeros[32] = {0};
     sha256_init_tagged(h, (const uint8_t*)"BIP0340/aux", 11); sha256_write(h, zeros, 32); sha256_finalize(h, c.zero_mask);
     return schnorr_sign_item(sig64, pk32, sk32, msg, msglen, c, g_gt);
+}
+// same phases as k_rangeproof_verify, lanes executed one after the other
+int emu_rangeproof_verify(uint64_t* minv, uint64_t* maxv, const uint8_t* commit33, const uint8_t* proof, size_t plen,
+                          const uint8_t* gen64, const uint8_t* extra, size_t extra_len) {
+    rp_header h; uint64_t mn = 0, mx = 0;
+    int hdr_ok = rp_parse_header(h, mn, mx, proof, plen);
+    *minv = mn; *maxv = mx;
+    if (!hdr_ok) return 0;
+    ge genp; rp_generator_load(genp, gen64);
+    ge mine[32]; gej pts[32]; int good = 1;
+    for (uint32_t lane = 0; lane < 32; lane++) {
+        mine[lane].inf = 1; int g = 1;
+        if (lane + 1 < h.rings) g = rp_digit_commitment_load(mine[lane], h, proof, lane);
+        else if (lane + 1 == h.rings) g = rp_commitment_load(mine[lane], commit33);
+        if (lane + 1 < h.rings && g) gej_set_ge(pts[lane], mine[lane]); else gej_set_infinity(pts[lane]);
+        good &= g;
+    }
+    uint8_t m32[32], r33[32 * 33];
+    rp_message_hash(m32, h, proof, commit33, gen64, fe_is_square(genp.y), extra, extra_len);
+    for (int d = 16; d >= 1; d >>= 1) for (int lane = 0; lane < d; lane++) { gej t; gej_add(t, pts[lane], pts[lane + d]); pts[lane] = t; }
+    gej pub[32];
+    for (uint32_t lane = 0; lane < 32; lane++) {
+        gej_set_infinity(pub[lane]);
+        if (lane + 1 == h.rings && good) {
+            gej acc = pts[0];
+            if (h.min_value) { gej mh, t; rp_small_mult(mh, h.min_value, genp); gej_add(t, acc, mh); acc = t; }
+            gej nacc; gej_neg(nacc, acc);
+            gej_add_ge(pub[lane], nacc, mine[lane]);
+            if (pub[lane].inf) good = 0;
+        } else if (lane + 1 < h.rings) gej_set_ge(pub[lane], mine[lane]);
+    }
+    if (!good) return 0;
+    int ring_ok = 1;
+    for (uint32_t lane = 0; lane < h.rings; lane++) {
+        gej base; rp_ring_base(base, genp, h.exp, lane);
+        tab_local tab;
+        ring_ok &= rp_ring_walk(r33 + 33 * lane, h, proof, m32, lane, pub[lane], base, g_gt, tab);
+    }
+    return ring_ok && rp_final_check(h, proof, r33, m32);
+}
+int emu_pedersen_commit(uint8_t* out33, const uint8_t* blind32, uint64_t value, const uint8_t* gen64) {
+    return pedersen_commit_item(out33, blind32, value, gen64, g_gt);
 }
 int emu_ecdsa_verify(const uint8_t* sig, int sigfmt, const uint8_t* msg32, const uint8_t* pk, int pkfmt) {
     tab_local tab; return ecdsa_verify_item(sig, sigfmt, msg32, pk, pkfmt, g_gt, tab);

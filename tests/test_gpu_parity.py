@@ -269,3 +269,122 @@ def test_full_size_batch_properties(engine):
     exp = np.ones(n, dtype=np.uint8)
     exp[bad] = 0
     assert np.array_equal(ok, exp)
+
+
+# ---- Pedersen commitments and range proofs ----------------------------------------------------------
+def test_pedersen_commit_batch_vs_reference(engine, ref):
+    rnd = random.Random(21)
+    gen = ref.generator_h()
+    n = 3000
+    vals = [0, 1, 2**64 - 1, 2**63] + [rnd.getrandbits(64) for _ in range(n - 4)]
+    blinds = [0, 1, N - 1, N, 2**256 - 1] + [rnd.getrandbits(256) % N for _ in range(n - 5)]   # incl. blind = 0 (allowed) and >= n (rejected)
+    B = b"".join(b32(x) for x in blinds)
+    okr, cr = ref.pedersen_commit(B, vals, gen)
+    okg, cg = engine.pedersen_commit(B, vals, gen)
+    assert np.array_equal(okg, okr) and np.array_equal(cg, cr)
+    assert okr[3] == 0 and okr[4] == 0 and okr[0] == 0   # 0*G + 0*H = infinity is rejected too
+    # per-item generators: a few other valid generators = serialized points k*G as 64-byte x||y
+    gens = ref.ecmult_batch(G64 * 8, bytes(32 * 8), b"".join(b32(rnd.getrandbits(200) + 2) for _ in range(8))).tobytes()
+    for k in range(8):
+        g = gens[64 * k:64 * k + 64]
+        okr, cr = ref.pedersen_commit(B[:32 * 64], vals[:64], g)
+        okg, cg = engine.pedersen_commit(B[:32 * 64], vals[:64], g)
+        assert np.array_equal(okg, okr) and np.array_equal(cg, cr)
+
+
+def _rp_check(engine, ref, proofs, plen, commits, gen, extra=b""):
+    er = ref.rangeproof_verify(commits.tobytes(), proofs, plen, gen, extra)
+    if extra:
+        n = proofs.shape[0]
+        ex = np.frombuffer(extra * n, dtype=np.uint8).reshape(n, len(extra))
+        eg = engine.rangeproof_verify(commits, proofs, plen, gen, ex, [len(extra)] * n)
+    else:
+        eg = engine.rangeproof_verify(commits, proofs, plen, gen)
+    for a, b_ in zip(er, eg):
+        assert np.array_equal(a, b_), (a[:8], b_[:8])
+    return er[0]
+
+
+def test_rangeproof_golden_vectors_gpu(engine, ref):
+    gen = ref.generator_h()
+    vecs = json.load(open(os.path.join(GOLD, "rangeproof.json")))["vectors"]
+    stride = max(len(v["proof"]) // 2 for v in vecs) + 1
+    for v in vecs:
+        proof = np.frombuffer(bytes.fromhex(v["proof"]), dtype=np.uint8)
+        commit = np.frombuffer(bytes.fromhex(v["commit"]), dtype=np.uint8)
+        buf = np.zeros((1, stride), dtype=np.uint8)
+        buf[0, :proof.size] = proof
+        ok, mn, mx = engine.rangeproof_verify(commit, buf, [proof.size], gen)
+        assert (int(ok[0]), int(mn[0]), int(mx[0])) == (1, v["min_value"], v["max_value"]), v["name"]
+        ok, _, _ = engine.rangeproof_verify(commit, buf, [proof.size + 1], gen)      # trailing byte
+        assert int(ok[0]) == 0
+
+
+def test_rangeproof_every_bit_flip_of_one_proof(engine, ref):
+    """rangeproof/tests_impl.h:306-310: every single bit of a proof flipped must fail (here: all bits of a
+    3-bit proof and of the golden 64-bit proof's first 128 and last 64 bytes), min/max outputs compared too."""
+    gen = ref.generator_h()
+    blind = b32(0x1234567890ABCDEF1234567890ABCDEF)
+    proofs, plen, commits = ref.rangeproof_make(blind, [5], gen, min_value=0, exp=0, min_bits=3)
+    L = int(plen[0])
+    n = 8 * L
+    batch = np.repeat(proofs[:1, :L], n, axis=0).copy()
+    idx = np.arange(n)
+    batch[idx, idx // 8] ^= (1 << (idx % 8)).astype(np.uint8)
+    ok = _rp_check(engine, ref, batch, [L] * n, np.repeat(commits[:1], n, axis=0), gen)
+    assert not ok.any()
+    v = [x for x in json.load(open(os.path.join(GOLD, "rangeproof.json")))["vectors"] if x["name"] == "reproducible_0"][0]
+    proof = np.frombuffer(bytes.fromhex(v["proof"]), dtype=np.uint8)
+    commit = np.frombuffer(bytes.fromhex(v["commit"]), dtype=np.uint8).reshape(1, 33)
+    pos = np.concatenate([np.arange(0, 128 * 8), np.arange((proof.size - 64) * 8, proof.size * 8)])
+    batch = np.repeat(proof.reshape(1, -1), pos.size, axis=0).copy()
+    k = np.arange(pos.size)
+    batch[k, pos // 8] ^= (1 << (pos % 8)).astype(np.uint8)
+    ok = _rp_check(engine, ref, batch, [proof.size] * pos.size, np.repeat(commit, pos.size, axis=0), gen)
+    assert not ok.any()
+
+
+def test_rangeproof_random_parameters_vs_reference(engine, ref):
+    rnd = random.Random(33)
+    gen = ref.generator_h()
+    other_gen = ref.ecmult_batch(G64, bytes(32), b32(0xC0FFEE)).tobytes()
+    cases = [(0, 0, 64), (13, 1, 8), (100, 2, 13), (0, 0, 1), (0, 3, 0), (7, 0, 17), (0, 18, 3), (1, 0, 63)]
+    for (mv, ex, mb) in cases:
+        for g in (gen, other_gen):
+            m = 12
+            span = 1 if mb == 0 else min(2**mb, 2**62)
+            vals = [mv + (rnd.randrange(span) * (10**ex)) % (2**63) for _ in range(m)]
+            blinds = b"".join(b32(rnd.getrandbits(256) % N or 1) for _ in range(m))
+            try:
+                proofs, plen, commits = ref.rangeproof_make(blinds, vals, g, min_value=mv, exp=ex, min_bits=mb)
+            except AssertionError:
+                continue
+            proofs = proofs.copy()
+            for i in range(m):
+                if i % 3 == 1:
+                    p = rnd.randrange(int(plen[i]))
+                    proofs[i, p] ^= 1 << rnd.randrange(8)
+                if i % 5 == 2:
+                    commits[i, 1 + rnd.randrange(32)] ^= 1
+            ok = _rp_check(engine, ref, proofs, plen, commits, g)
+            ok2 = _rp_check(engine, ref, proofs, plen, commits, g, extra=b"extra-commit-data")
+            assert not ok2.any()            # proofs were made without extra_commit
+            assert ok.sum() >= m // 3
+
+
+def test_rangeproof_64bit_batch_vs_reference(engine, ref):
+    """SURVEY 8d config 4 shape (64-bit proofs, 5126 bytes), small batch with 1/8 corrupted."""
+    rnd = random.Random(44)
+    gen = ref.generator_h()
+    n = 256
+    vals = [rnd.getrandbits(64) for _ in range(n)]
+    blinds = b"".join(b32(rnd.getrandbits(256) % N or 1) for _ in range(n))
+    proofs, plen, commits = ref.rangeproof_make(blinds, vals, gen, min_value=0, exp=0, min_bits=64)
+    assert int(plen[0]) == 5126
+    for i in range(3, n, 8):
+        bit = int.from_bytes(hashlib.sha256(b"%d" % i).digest()[:4], "big") % (8 * 5126)
+        proofs[i, bit // 8] ^= 1 << (bit % 8)
+    ok = _rp_check(engine, ref, proofs, plen, commits, gen)
+    assert int(ok.sum()) == n - len(range(3, n, 8))
+    okc, cg = engine.pedersen_commit(blinds, vals, gen)
+    assert okc.all() and np.array_equal(cg, commits)
