@@ -115,6 +115,18 @@ SECP256K1_B200_API int secp256k1_b200_ecdsa_verify_batch(secp256k1_b200_engine *
 SECP256K1_B200_API int secp256k1_b200_ecdsa_verify_batch_dev(secp256k1_b200_engine *e, unsigned char *d_ok,
         const unsigned char *d_sig64, int sigfmt, const unsigned char *d_msghash32, const unsigned char *d_pk, int pkfmt, size_t n, void *stream);
 
+/* ---- batched point parsing / serialization (everything that needs a field square root) ------------------ */
+#define SECP256K1_B200_CODEC_XONLY32       1 /* 32-byte x-only key  -> 64-byte opaque secp256k1_xonly_pubkey (include/secp256k1_extrakeys.h:47) */
+#define SECP256K1_B200_CODEC_EC_PUBKEY     2 /* 33/65-byte SEC1 key -> 64-byte opaque secp256k1_pubkey (include/secp256k1.h:462) */
+#define SECP256K1_B200_CODEC_COMMIT33      3 /* 33-byte commitment  -> validity + affine x||y big-endian (include/secp256k1_generator.h:64) */
+#define SECP256K1_B200_CODEC_GENERATOR33   4 /* 33-byte generator   -> 64-byte secp256k1_generator (include/secp256k1_generator.h:27) */
+#define SECP256K1_B200_CODEC_GENERATOR_SER 5 /* 64-byte generator   -> 33-byte serialization in out64[0..32] (include/secp256k1_generator.h:42) */
+/* item i is read from in + i*in_stride (in_len bytes) and written to out64 + 64*i; ok[i] = parse result */
+SECP256K1_B200_API int secp256k1_b200_point_codec_batch(secp256k1_b200_engine *e, unsigned char *ok, unsigned char *out64,
+        const unsigned char *in, size_t in_stride, uint32_t in_len, int fmt, size_t n);
+SECP256K1_B200_API int secp256k1_b200_point_codec_batch_dev(secp256k1_b200_engine *e, unsigned char *d_ok, unsigned char *d_out64,
+        const unsigned char *d_in, size_t in_stride, uint32_t in_len, int fmt, size_t n, void *stream);
+
 /* ---- Pedersen commitments -------------------------------------------------------------------------- */
 /* commit33[i] = serialize(blind[i]*G + value[i]*gen[i]) (tag 8/9 + x); ok[i] = 0 (and zeros) if blind >= n or the
  * result is infinity.  gen64: 64-byte secp256k1_generator objects (x||y big-endian, include/secp256k1_generator.h:24);

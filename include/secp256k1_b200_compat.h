@@ -1,0 +1,88 @@
+/* secp256k1_b200_compat.h -- the reference-named C API for the accelerated path, exported by
+ * libsecp256k1_b200.so with the reference's own names, argument order and return conventions, so that code
+ * compiled against the reference's headers (include/secp256k1.h, secp256k1_extrakeys.h, secp256k1_schnorrsig.h,
+ * secp256k1_generator.h, secp256k1_rangeproof.h) links against this library unchanged for these symbols.
+ * Each declaration cites the reference declaration it mirrors (paths relative to the reference tree).
+ *
+ * Semantics: 1 = success/valid, 0 = failure/invalid.  API misuse (NULL where a pointer is required, a static context
+ * where a created one is required) calls the context's illegal callback and returns 0 (src/secp256k1.c:66-71); the
+ * default callbacks print and abort() (src/util.h:97-105).  CUDA failures go to the error callback.
+ * Every call that needs field or group arithmetic runs on the GPU as a batch of one through a process-wide engine
+ * (created lazily on the current CUDA device); device state never lives inside secp256k1_context, which stays a small
+ * clonable host object (src/secp256k1.c:82-88, :176-185).  For throughput use the *_batch entry points of
+ * secp256k1_b200.h -- a single call costs a kernel launch.
+ * Deviation: the SHA-256 compression override hook (include/secp256k1.h:443-446) is not honoured on the device.
+ */
+#ifndef SECP256K1_B200_COMPAT_H
+#define SECP256K1_B200_COMPAT_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "secp256k1_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* opaque types, same sizes as the reference's (include/secp256k1.h:62-64, :75-77; secp256k1_extrakeys.h:22-24;
+ * secp256k1_generator.h:24-26, :60-62) */
+typedef struct secp256k1_context_struct secp256k1_context;
+typedef struct { unsigned char data[64]; } secp256k1_pubkey;
+typedef struct { unsigned char data[64]; } secp256k1_xonly_pubkey;
+typedef struct { unsigned char data[64]; } secp256k1_ecdsa_signature;
+typedef struct { unsigned char data[64]; } secp256k1_generator;
+typedef struct { unsigned char data[64]; } secp256k1_pedersen_commitment;
+
+#ifndef SECP256K1_CONTEXT_NONE
+#define SECP256K1_CONTEXT_NONE 1u               /* include/secp256k1.h:215 */
+#define SECP256K1_CONTEXT_VERIFY (1u | (1u << 8))
+#define SECP256K1_CONTEXT_SIGN (1u | (1u << 9))
+#define SECP256K1_EC_COMPRESSED ((1u << 1) | (1u << 8))   /* :225 */
+#define SECP256K1_EC_UNCOMPRESSED (1u << 1)               /* :226 */
+#endif
+
+/* include/secp256k1.h:246-362 */
+SECP256K1_B200_API extern const secp256k1_context *secp256k1_context_static;
+SECP256K1_B200_API void secp256k1_selftest(void);
+SECP256K1_B200_API secp256k1_context *secp256k1_context_create(unsigned int flags);
+SECP256K1_B200_API secp256k1_context *secp256k1_context_clone(const secp256k1_context *ctx);
+SECP256K1_B200_API void secp256k1_context_destroy(secp256k1_context *ctx);
+SECP256K1_B200_API void secp256k1_context_set_illegal_callback(secp256k1_context *ctx, void (*fun)(const char *message, void *data), const void *data);
+SECP256K1_B200_API void secp256k1_context_set_error_callback(secp256k1_context *ctx, void (*fun)(const char *message, void *data), const void *data);
+SECP256K1_B200_API int secp256k1_context_randomize(secp256k1_context *ctx, const unsigned char *seed32);   /* :879 */
+
+/* include/secp256k1.h:462-495, :536, :622-627 */
+SECP256K1_B200_API int secp256k1_ec_pubkey_parse(const secp256k1_context *ctx, secp256k1_pubkey *pubkey, const unsigned char *input, size_t inputlen);
+SECP256K1_B200_API int secp256k1_ec_pubkey_serialize(const secp256k1_context *ctx, unsigned char *output, size_t *outputlen, const secp256k1_pubkey *pubkey, unsigned int flags);
+SECP256K1_B200_API int secp256k1_ecdsa_signature_parse_compact(const secp256k1_context *ctx, secp256k1_ecdsa_signature *sig, const unsigned char *input64);
+SECP256K1_B200_API int secp256k1_ecdsa_verify(const secp256k1_context *ctx, const secp256k1_ecdsa_signature *sig, const unsigned char *msghash32, const secp256k1_pubkey *pubkey);
+
+/* include/secp256k1_extrakeys.h:47 ; include/secp256k1_schnorrsig.h:178-184 */
+SECP256K1_B200_API int secp256k1_xonly_pubkey_parse(const secp256k1_context *ctx, secp256k1_xonly_pubkey *pubkey, const unsigned char *input32);
+SECP256K1_B200_API int secp256k1_xonly_pubkey_serialize(const secp256k1_context *ctx, unsigned char *output32, const secp256k1_xonly_pubkey *pubkey);
+SECP256K1_B200_API int secp256k1_schnorrsig_verify(const secp256k1_context *ctx, const unsigned char *sig64, const unsigned char *msg, size_t msglen, const secp256k1_xonly_pubkey *pubkey);
+
+/* include/secp256k1_generator.h:27-53, :64-153 */
+SECP256K1_B200_API extern const secp256k1_generator *secp256k1_generator_h;
+SECP256K1_B200_API int secp256k1_generator_parse(const secp256k1_context *ctx, secp256k1_generator *gen, const unsigned char *input);
+SECP256K1_B200_API int secp256k1_generator_serialize(const secp256k1_context *ctx, unsigned char *output, const secp256k1_generator *gen);
+SECP256K1_B200_API int secp256k1_pedersen_commitment_parse(const secp256k1_context *ctx, secp256k1_pedersen_commitment *commit, const unsigned char *input);
+SECP256K1_B200_API int secp256k1_pedersen_commitment_serialize(const secp256k1_context *ctx, unsigned char *output, const secp256k1_pedersen_commitment *commit);
+SECP256K1_B200_API int secp256k1_pedersen_commit(const secp256k1_context *ctx, secp256k1_pedersen_commitment *commit, const unsigned char *blind, uint64_t value, const secp256k1_generator *gen);
+
+/* include/secp256k1_rangeproof.h:70-80, :176-184 */
+SECP256K1_B200_API int secp256k1_rangeproof_verify(const secp256k1_context *ctx, uint64_t *min_value, uint64_t *max_value,
+        const secp256k1_pedersen_commitment *commit, const unsigned char *proof, size_t plen,
+        const unsigned char *extra_commit, size_t extra_commit_len, const secp256k1_generator *gen);
+SECP256K1_B200_API int secp256k1_rangeproof_info(const secp256k1_context *ctx, int *exp, int *mantissa, uint64_t *min_value, uint64_t *max_value,
+        const unsigned char *proof, size_t plen);
+
+/* the process-wide engine behind the calls above (created on first use); exposed so that a host application can
+ * pick the device / share the engine with the batch API */
+SECP256K1_B200_API secp256k1_b200_engine *secp256k1_b200_global_engine(void);
+SECP256K1_B200_API void secp256k1_b200_global_engine_shutdown(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

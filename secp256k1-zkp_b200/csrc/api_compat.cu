@@ -1,0 +1,348 @@
+// api_compat.cu -- the reference-named single-call C API (include/secp256k1_b200_compat.h) on top of the batch
+// engine: argument checks and byte shuffling on the host, every field/group computation as a batch of one on
+// the GPU.  Mirrors the control flow of src/secp256k1.c and the module main_impl.h files it cites; no reference
+// code is reused.
+#include "../../include/secp256k1_b200_compat.h"
+
+#include <mutex>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+struct secp256k1_callback_s {
+    void (*fn)(const char* text, void* data);
+    const void* data;
+};
+// src/secp256k1.c:82-88: {ecmult_gen_ctx, hash_ctx, illegal_callback, error_callback, declassify}; here the
+// "ecmult_gen built" bit is the only state a verification context needs.
+struct secp256k1_context_struct {
+    int proper;   // 0 for the static context (and copies of it): cannot sign / commit (generator/main_impl.h:317-320)
+    secp256k1_callback_s illegal_callback;
+    secp256k1_callback_s error_callback;
+};
+
+static void default_illegal_callback_fn(const char* str, void* data) {
+    (void)data;
+    fprintf(stderr, "[libsecp256k1] illegal argument: %s\n", str);
+    abort();
+}
+static void default_error_callback_fn(const char* str, void* data) {
+    (void)data;
+    fprintf(stderr, "[libsecp256k1] internal consistency check failed: %s\n", str);
+    abort();
+}
+static const secp256k1_context_struct static_ctx = {0, {default_illegal_callback_fn, nullptr}, {default_error_callback_fn, nullptr}};
+extern "C" const secp256k1_context* secp256k1_context_static = &static_ctx;
+
+static void callback_call(const secp256k1_callback_s& cb, const char* text) { cb.fn(text, const_cast<void*>(cb.data)); }
+#define ARG_CHECK(cond)                                          \
+    do {                                                         \
+        if (!(cond)) {                                           \
+            callback_call(ctx->illegal_callback, #cond);         \
+            return 0;                                            \
+        }                                                        \
+    } while (0)
+#define ARG_CHECK_VOID(cond)                                     \
+    do {                                                         \
+        if (!(cond)) {                                           \
+            callback_call(ctx->illegal_callback, #cond);         \
+            return;                                              \
+        }                                                        \
+    } while (0)
+
+// ---- process-wide engine ---------------------------------------------------------------------------------
+static std::mutex g_engine_mu;
+static secp256k1_b200_engine* g_engine = nullptr;
+extern "C" secp256k1_b200_engine* secp256k1_b200_global_engine(void) {
+    std::lock_guard<std::mutex> lock(g_engine_mu);
+    if (!g_engine) {
+        // small generator window (12 bits -> 5.5 MiB table, built in well under a millisecond of GPU time): single calls are
+        // launch-latency bound, a 64 MiB table would only slow the first call down
+        const char* w = getenv("SECP256K1_B200_GLOBAL_WINDOW");
+        if (!secp256k1_b200_engine_create(&g_engine, -1, w ? atoi(w) : 12, 1)) g_engine = nullptr;
+    }
+    return g_engine;
+}
+extern "C" void secp256k1_b200_global_engine_shutdown(void) {
+    std::lock_guard<std::mutex> lock(g_engine_mu);
+    if (g_engine) secp256k1_b200_engine_destroy(g_engine);
+    g_engine = nullptr;
+}
+static secp256k1_b200_engine* engine_or_error(const secp256k1_context* ctx) {
+    secp256k1_b200_engine* e = secp256k1_b200_global_engine();
+    if (!e) callback_call(ctx->error_callback, secp256k1_b200_last_error());
+    return e;
+}
+#define ENGINE_OR_FAIL(e)                              \
+    secp256k1_b200_engine* e = engine_or_error(ctx);   \
+    if (!e) return 0
+#define GPU_CALL(expr)                                                        \
+    do {                                                                      \
+        if (!(expr)) {                                                        \
+            callback_call(ctx->error_callback, secp256k1_b200_last_error());  \
+            return 0;                                                         \
+        }                                                                     \
+    } while (0)
+
+extern "C" {
+
+// ---- context (src/secp256k1.c:141-245) ---------------------------------------------------------------------
+void secp256k1_selftest(void) {
+    // the reference's self test is a SHA-256 known-answer test on the host (src/selftest.h:12-34); the device self test
+    // is the parity suite.  Nothing can fail here without a device, so this is a no-op by design.
+}
+secp256k1_context* secp256k1_context_create(unsigned int flags) {
+    if ((flags & 0xFFu) != 1u) {   // SECP256K1_FLAGS_TYPE_CONTEXT (src/secp256k1.c:120-124)
+        default_illegal_callback_fn("Invalid flags", nullptr);
+        return nullptr;
+    }
+    secp256k1_context* ctx = (secp256k1_context*)malloc(sizeof(secp256k1_context));
+    if (!ctx) { default_error_callback_fn("Out of memory", nullptr); return nullptr; }
+    ctx->proper = 1;
+    ctx->illegal_callback = {default_illegal_callback_fn, nullptr};
+    ctx->error_callback = {default_error_callback_fn, nullptr};
+    return ctx;
+}
+secp256k1_context* secp256k1_context_clone(const secp256k1_context* ctx) {
+    ARG_CHECK(ctx->proper);
+    secp256k1_context* ret = (secp256k1_context*)malloc(sizeof(secp256k1_context));
+    if (!ret) { callback_call(ctx->error_callback, "Out of memory"); return nullptr; }
+    memcpy(ret, ctx, sizeof(*ret));
+    return ret;
+}
+void secp256k1_context_destroy(secp256k1_context* ctx) {
+    if (ctx == nullptr) return;
+    ARG_CHECK_VOID(ctx->proper);
+    free(ctx);
+}
+void secp256k1_context_set_illegal_callback(secp256k1_context* ctx, void (*fun)(const char*, void*), const void* data) {
+    ARG_CHECK_VOID(ctx != secp256k1_context_static);
+    ctx->illegal_callback.fn = fun ? fun : default_illegal_callback_fn;
+    ctx->illegal_callback.data = data;
+}
+void secp256k1_context_set_error_callback(secp256k1_context* ctx, void (*fun)(const char*, void*), const void* data) {
+    ARG_CHECK_VOID(ctx != secp256k1_context_static);
+    ctx->error_callback.fn = fun ? fun : default_error_callback_fn;
+    ctx->error_callback.data = data;
+}
+int secp256k1_context_randomize(secp256k1_context* ctx, const unsigned char* seed32) {
+    // blinding of the constant-time generator multiplication (src/secp256k1.c:879): nothing to blind on the verification path
+    ARG_CHECK(ctx->proper);
+    (void)seed32;
+    return 1;
+}
+
+// ---- public keys -----------------------------------------------------------------------------------------------
+static int all_zero(const unsigned char* p, size_t n) { unsigned char x = 0; for (size_t i = 0; i < n; i++) x |= p[i]; return x == 0; }
+
+int secp256k1_ec_pubkey_parse(const secp256k1_context* ctx, secp256k1_pubkey* pubkey, const unsigned char* input, size_t inputlen) {
+    ARG_CHECK(pubkey != NULL);
+    memset(pubkey, 0, sizeof(*pubkey));
+    ARG_CHECK(input != NULL);
+    if (inputlen != 33 && inputlen != 65) return 0;
+    ENGINE_OR_FAIL(e);
+    unsigned char ok = 0, out[64];
+    GPU_CALL(secp256k1_b200_point_codec_batch(e, &ok, out, input, inputlen, (uint32_t)inputlen, 2, 1));
+    if (!ok) return 0;
+    memcpy(pubkey->data, out, 64);
+    return 1;
+}
+int secp256k1_ec_pubkey_serialize(const secp256k1_context* ctx, unsigned char* output, size_t* outputlen, const secp256k1_pubkey* pubkey, unsigned int flags) {
+    ARG_CHECK(outputlen != NULL);
+    ARG_CHECK(*outputlen >= ((flags & (1u << 8)) ? 33u : 65u));
+    size_t len = *outputlen;
+    *outputlen = 0;
+    ARG_CHECK(output != NULL);
+    memset(output, 0, len);
+    ARG_CHECK(pubkey != NULL);
+    ARG_CHECK((flags & 0xFFu) == (1u << 1));
+    ARG_CHECK(!all_zero(pubkey->data, 32));       // secp256k1_pubkey_load: x != 0 (src/secp256k1.c:282)
+    // opaque form = x,y little-endian (group_impl.h:999-1017): pure byte reversal, no arithmetic
+    for (int i = 0; i < 32; i++) output[1 + i] = pubkey->data[31 - i];
+    if (flags & (1u << 8)) {
+        output[0] = (pubkey->data[32] & 1) ? 0x03 : 0x02;
+        *outputlen = 33;
+    } else {
+        output[0] = 0x04;
+        for (int i = 0; i < 32; i++) output[33 + i] = pubkey->data[63 - i];
+        *outputlen = 65;
+    }
+    return 1;
+}
+int secp256k1_xonly_pubkey_parse(const secp256k1_context* ctx, secp256k1_xonly_pubkey* pubkey, const unsigned char* input32) {
+    ARG_CHECK(pubkey != NULL);
+    memset(pubkey, 0, sizeof(*pubkey));
+    ARG_CHECK(input32 != NULL);
+    ENGINE_OR_FAIL(e);
+    unsigned char ok = 0, out[64];
+    GPU_CALL(secp256k1_b200_point_codec_batch(e, &ok, out, input32, 32, 32, 1, 1));
+    if (!ok) return 0;
+    memcpy(pubkey->data, out, 64);
+    return 1;
+}
+int secp256k1_xonly_pubkey_serialize(const secp256k1_context* ctx, unsigned char* output32, const secp256k1_xonly_pubkey* pubkey) {
+    ARG_CHECK(output32 != NULL);
+    memset(output32, 0, 32);
+    ARG_CHECK(pubkey != NULL);
+    ARG_CHECK(!all_zero(pubkey->data, 32));
+    for (int i = 0; i < 32; i++) output32[i] = pubkey->data[31 - i];
+    return 1;
+}
+
+// ---- ECDSA (src/secp256k1.c:372-391, :498-512) -----------------------------------------------------------------
+static const unsigned char ORDER_BE[32] = {0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFE,
+                                           0xBA, 0xAE, 0xDC, 0xE6, 0xAF, 0x48, 0xA0, 0x3B, 0xBF, 0xD2, 0x5E, 0x8C, 0xD0, 0x36, 0x41, 0x41};
+int secp256k1_ecdsa_signature_parse_compact(const secp256k1_context* ctx, secp256k1_ecdsa_signature* sig, const unsigned char* input64) {
+    ARG_CHECK(sig != NULL);
+    ARG_CHECK(input64 != NULL);
+    int ret = 1;
+    for (int half = 0; half < 2; half++) {
+        if (memcmp(input64 + 32 * half, ORDER_BE, 32) >= 0) ret = 0;   // overflow: scalar >= n
+    }
+    if (ret) {
+        for (int half = 0; half < 2; half++)
+            for (int i = 0; i < 32; i++) sig->data[32 * half + i] = input64[32 * half + 31 - i];   // scalars as 4x64 little-endian
+    } else {
+        memset(sig, 0, sizeof(*sig));
+    }
+    return ret;
+}
+int secp256k1_ecdsa_verify(const secp256k1_context* ctx, const secp256k1_ecdsa_signature* sig, const unsigned char* msghash32, const secp256k1_pubkey* pubkey) {
+    ARG_CHECK(msghash32 != NULL);
+    ARG_CHECK(sig != NULL);
+    ARG_CHECK(pubkey != NULL);
+    ARG_CHECK(!all_zero(pubkey->data, 32));
+    ENGINE_OR_FAIL(e);
+    unsigned char ok = 0;
+    GPU_CALL(secp256k1_b200_ecdsa_verify_batch(e, &ok, sig->data, SECP256K1_B200_SIG_OPAQUE64, msghash32, pubkey->data, SECP256K1_B200_PK_OPAQUE64, 1));
+    return ok;
+}
+
+// ---- BIP-340 (modules/schnorrsig/main_impl.h:215-261) -------------------------------------------------------------
+int secp256k1_schnorrsig_verify(const secp256k1_context* ctx, const unsigned char* sig64, const unsigned char* msg, size_t msglen, const secp256k1_xonly_pubkey* pubkey) {
+    ARG_CHECK(sig64 != NULL);
+    ARG_CHECK(msg != NULL || msglen == 0);
+    ARG_CHECK(pubkey != NULL);
+    ARG_CHECK(!all_zero(pubkey->data, 32));
+    ENGINE_OR_FAIL(e);
+    unsigned char ok = 0, dummy = 0;
+    GPU_CALL(secp256k1_b200_schnorrsig_verify_batch(e, &ok, sig64, msglen ? msg : &dummy, msglen, pubkey->data, SECP256K1_B200_PK_OPAQUE64, 1));
+    return ok;
+}
+
+// ---- generators and Pedersen commitments (modules/generator/main_impl.h) -------------------------------------------
+// secp256k1_generator_h: lift_x(SHA256(uncompressed G)), the sage script in generator/main_impl.h:20-29 documents the derivation
+static const secp256k1_generator generator_h_internal = {{
+    0x50, 0x92, 0x9b, 0x74, 0xc1, 0xa0, 0x49, 0x54, 0xb7, 0x8b, 0x4b, 0x60, 0x35, 0xe9, 0x7a, 0x5e, 0x07, 0x8a, 0x5a, 0x0f, 0x28, 0xec, 0x96, 0xd5,
+    0x47, 0xbf, 0xee, 0x9a, 0xce, 0x80, 0x3a, 0xc0, 0x31, 0xd3, 0xc6, 0x86, 0x39, 0x73, 0x92, 0x6e, 0x04, 0x9e, 0x63, 0x7c, 0xb1, 0xb5, 0xf4, 0x0a,
+    0x36, 0xda, 0xc2, 0x8a, 0xf1, 0x76, 0x69, 0x68, 0xc3, 0x0c, 0x23, 0x13, 0xf3, 0xa3, 0x89, 0x04}};
+const secp256k1_generator* secp256k1_generator_h = &generator_h_internal;
+
+int secp256k1_generator_parse(const secp256k1_context* ctx, secp256k1_generator* gen, const unsigned char* input) {
+    ARG_CHECK(gen != NULL);
+    ARG_CHECK(input != NULL);
+    ENGINE_OR_FAIL(e);
+    unsigned char ok = 0, out[64];
+    GPU_CALL(secp256k1_b200_point_codec_batch(e, &ok, out, input, 33, 33, 4, 1));
+    if (!ok) return 0;
+    memcpy(gen->data, out, 64);
+    return 1;
+}
+int secp256k1_generator_serialize(const secp256k1_context* ctx, unsigned char* output, const secp256k1_generator* gen) {
+    ARG_CHECK(output != NULL);
+    ARG_CHECK(gen != NULL);
+    ENGINE_OR_FAIL(e);
+    unsigned char ok = 0, out[64];
+    GPU_CALL(secp256k1_b200_point_codec_batch(e, &ok, out, gen->data, 64, 64, 5, 1));
+    memcpy(output, out, 33);
+    return 1;
+}
+int secp256k1_pedersen_commitment_parse(const secp256k1_context* ctx, secp256k1_pedersen_commitment* commit, const unsigned char* input) {
+    ARG_CHECK(commit != NULL);
+    ARG_CHECK(input != NULL);
+    ENGINE_OR_FAIL(e);
+    unsigned char ok = 0, out[64];
+    GPU_CALL(secp256k1_b200_point_codec_batch(e, &ok, out, input, 33, 33, 3, 1));
+    if (!ok) return 0;
+    memcpy(commit->data, input, 33);
+    return 1;
+}
+int secp256k1_pedersen_commitment_serialize(const secp256k1_context* ctx, unsigned char* output, const secp256k1_pedersen_commitment* commit) {
+    ARG_CHECK(output != NULL);
+    ARG_CHECK(commit != NULL);
+    memcpy(output, commit->data, 33);
+    return 1;
+}
+int secp256k1_pedersen_commit(const secp256k1_context* ctx, secp256k1_pedersen_commitment* commit, const unsigned char* blind, uint64_t value, const secp256k1_generator* gen) {
+    ARG_CHECK(ctx->proper);                        // needs a created context (generator/main_impl.h:317-320)
+    ARG_CHECK(commit != NULL);
+    ARG_CHECK(blind != NULL);
+    ARG_CHECK(gen != NULL);
+    ENGINE_OR_FAIL(e);
+    unsigned char ok = 0, out[33];
+    GPU_CALL(secp256k1_b200_pedersen_commit_batch(e, &ok, out, blind, &value, gen->data, 0, 1));
+    if (!ok) return 0;
+    memcpy(commit->data, out, 33);                 // only bytes 0..32 of the 64-byte object are written (main_impl.h:275-279)
+    return 1;
+}
+
+// ---- range proofs (modules/rangeproof/main_impl.h:16-29, :54-70) -----------------------------------------------------
+int secp256k1_rangeproof_info(const secp256k1_context* ctx, int* exp, int* mantissa, uint64_t* min_value, uint64_t* max_value, const unsigned char* proof, size_t plen) {
+    ARG_CHECK(exp != NULL);
+    ARG_CHECK(mantissa != NULL);
+    ARG_CHECK(min_value != NULL);
+    ARG_CHECK(max_value != NULL);
+    ARG_CHECK(proof != NULL);
+    // header decoding is byte parsing only (rangeproof_impl.h:487-538): restated here for the host
+    size_t offset = 0;
+    if (plen < 65 || (proof[0] & 128) != 0) return 0;
+    int has_nz_range = proof[0] & 64, has_min = proof[0] & 32;
+    *exp = -1;
+    *mantissa = 0;
+    if (has_nz_range) {
+        *exp = proof[0] & 31;
+        offset += 1;
+        if (*exp > 18) return 0;
+        *mantissa = proof[offset] + 1;
+        if (*mantissa > 64) return 0;
+        *max_value = UINT64_MAX >> (64 - *mantissa);
+    } else {
+        *max_value = 0;
+    }
+    offset += 1;
+    for (int i = 0; i < *exp; i++) {
+        if (*max_value > UINT64_MAX / 10) return 0;
+        *max_value *= 10;
+    }
+    *min_value = 0;
+    if (has_min) {
+        if (plen - offset < 8) return 0;
+        for (int i = 0; i < 8; i++) *min_value = (*min_value << 8) | proof[offset + i];
+        offset += 8;
+    }
+    if (*max_value > UINT64_MAX - *min_value) return 0;
+    *max_value += *min_value;
+    return 1;
+}
+int secp256k1_rangeproof_verify(const secp256k1_context* ctx, uint64_t* min_value, uint64_t* max_value, const secp256k1_pedersen_commitment* commit,
+                                const unsigned char* proof, size_t plen, const unsigned char* extra_commit, size_t extra_commit_len, const secp256k1_generator* gen) {
+    ARG_CHECK(commit != NULL);
+    ARG_CHECK(proof != NULL);
+    ARG_CHECK(min_value != NULL);
+    ARG_CHECK(max_value != NULL);
+    ARG_CHECK(extra_commit != NULL || extra_commit_len == 0);
+    ARG_CHECK(gen != NULL);
+    if (plen > 0xFFFFFFFFull || extra_commit_len > 0xFFFFFFFFull) return 0;
+    ENGINE_OR_FAIL(e);
+    unsigned char ok = 0;
+    uint32_t pl = (uint32_t)plen, el = (uint32_t)extra_commit_len;
+    uint64_t mn = 0, mx = 0;
+    // the header outputs are written even when the proof fails later (rangeproof_impl.h:565); when the header itself is rejected
+    // the reference leaves the caller's variables partially written -- the device reports exactly what was written so far
+    GPU_CALL(secp256k1_b200_rangeproof_verify_batch(e, &ok, &mn, &mx, commit->data, proof, plen ? plen : 1, &pl, gen->data, 0,
+                                                    extra_commit_len ? extra_commit : NULL, extra_commit_len, extra_commit_len ? &el : NULL, 1));
+    if (plen >= 65 && (proof[0] & 128) == 0) { *min_value = mn; *max_value = mx; }
+    return ok;
+}
+
+}  // extern "C"

@@ -331,6 +331,33 @@ int secp256k1_b200_ecdsa_verify_batch(secp256k1_b200_engine* e, unsigned char* o
     return 1;
 }
 
+/* ---- batched point parsing / serialization ----------------------------------------------------------- */
+int secp256k1_b200_point_codec_batch_dev(secp256k1_b200_engine* e, unsigned char* d_ok, unsigned char* d_out64, const unsigned char* d_in,
+                                         size_t in_stride, uint32_t in_len, int fmt, size_t n, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (fmt < 1 || fmt > 5 || in_len > 65) { set_error("point_codec: bad format / length"); return 0; }
+    device_guard guard(e->device);
+    CK(launch_codec(d_ok, d_out64, d_in, in_stride, in_len, fmt, n, (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_point_codec_batch(secp256k1_b200_engine* e, unsigned char* ok, unsigned char* out64, const unsigned char* in,
+                                     size_t in_stride, uint32_t in_len, int fmt, size_t n) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (fmt < 1 || fmt > 5 || in_len > 65 || in_stride < in_len) { set_error("point_codec: bad format / length"); return 0; }
+    if (n == 0) return 1;
+    std::lock_guard<std::mutex> lock(e->mu);
+    device_guard guard(e->device);
+    carver c(e);
+    size_t oi = c.add(in_stride * n), oo = c.add(64 * n), ook = c.add(n);
+    if (!c.commit()) return 0;
+    CK(cudaMemcpyAsync(c.at(oi), in, in_stride * (n - 1) + in_len, cudaMemcpyHostToDevice, e->stream));
+    if (!secp256k1_b200_point_codec_batch_dev(e, c.at(ook), c.at(oo), c.at(oi), in_stride, in_len, fmt, n, e->stream)) return 0;
+    CK(cudaMemcpyAsync(ok, c.at(ook), n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(out64, c.at(oo), 64 * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
 /* ---- Pedersen commitments / range proofs --------------------------------------------------------------- */
 int secp256k1_b200_pedersen_commit_batch_dev(secp256k1_b200_engine* e, unsigned char* d_ok, unsigned char* d_commit33,
                                              const unsigned char* d_blind32, const uint64_t* d_value, const unsigned char* d_gen64,
