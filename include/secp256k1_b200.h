@@ -115,6 +115,17 @@ SECP256K1_B200_API int secp256k1_b200_ecdsa_verify_batch(secp256k1_b200_engine *
 SECP256K1_B200_API int secp256k1_b200_ecdsa_verify_batch_dev(secp256k1_b200_engine *e, unsigned char *d_ok,
         const unsigned char *d_sig64, int sigfmt, const unsigned char *d_msghash32, const unsigned char *d_pk, int pkfmt, size_t n, void *stream);
 
+/* ---- multi-scalar multiplication: out = g_scalar*G + sum_i scalars[i]*points[i] ----------------------------- */
+/* Pippenger bucket method on the GPU (replaces static secp256k1_ecmult_multi_var, src/ecmult.h:62; the callback
+ * interface becomes two flat arrays).  scalars32: n x 32 bytes big-endian (reduced mod n); points64: n x 64 bytes affine
+ * x||y big-endian, all-zero = infinity; g_scalar32 may be NULL.  out64: affine x||y big-endian, all-zero = infinity.
+ * The _dev variant needs a caller-provided device workspace of secp256k1_b200_ecmult_multi_workspace_bytes(n) bytes. */
+SECP256K1_B200_API size_t secp256k1_b200_ecmult_multi_workspace_bytes(size_t n);
+SECP256K1_B200_API int secp256k1_b200_ecmult_multi(secp256k1_b200_engine *e, unsigned char *out64, const unsigned char *g_scalar32,
+        const unsigned char *scalars32, const unsigned char *points64, size_t n);
+SECP256K1_B200_API int secp256k1_b200_ecmult_multi_dev(secp256k1_b200_engine *e, unsigned char *d_out64, const unsigned char *d_g_scalar32,
+        const unsigned char *d_scalars32, const unsigned char *d_points64, size_t n, void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* ---- batched point parsing / serialization (everything that needs a field square root) ------------------ */
 #define SECP256K1_B200_CODEC_XONLY32       1 /* 32-byte x-only key  -> 64-byte opaque secp256k1_xonly_pubkey (include/secp256k1_extrakeys.h:47) */
 #define SECP256K1_B200_CODEC_EC_PUBKEY     2 /* 33/65-byte SEC1 key -> 64-byte opaque secp256k1_pubkey (include/secp256k1.h:462) */

@@ -331,6 +331,37 @@ int secp256k1_b200_ecdsa_verify_batch(secp256k1_b200_engine* e, unsigned char* o
     return 1;
 }
 
+/* ---- multi-scalar multiplication (Pippenger) ------------------------------------------------------------ */
+size_t secp256k1_b200_ecmult_multi_workspace_bytes(size_t n) { return msm_workspace_bytes(n); }
+int secp256k1_b200_ecmult_multi_dev(secp256k1_b200_engine* e, unsigned char* d_out64, const unsigned char* d_g_scalar32,
+                                    const unsigned char* d_scalars32, const unsigned char* d_points64, size_t n,
+                                    void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (workspace_bytes < msm_workspace_bytes(n)) { set_error("ecmult_multi: workspace too small (see secp256k1_b200_ecmult_multi_workspace_bytes)"); return 0; }
+    device_guard guard(e->device);
+    CK(launch_msm(d_out64, d_g_scalar32, d_scalars32, d_points64, n, (uint8_t*)d_workspace, workspace_bytes, (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_ecmult_multi(secp256k1_b200_engine* e, unsigned char* out64, const unsigned char* g_scalar32,
+                                const unsigned char* scalars32, const unsigned char* points64, size_t n) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    std::lock_guard<std::mutex> lock(e->mu);
+    device_guard guard(e->device);
+    carver c(e);
+    size_t wsb = msm_workspace_bytes(n);
+    size_t os = c.add(32 * n + 32), op = c.add(64 * n + 64), og = c.add(32), oo = c.add(64), ow = c.add(wsb);
+    if (!c.commit()) return 0;
+    if (n) {
+        CK(cudaMemcpyAsync(c.at(os), scalars32, 32 * n, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(c.at(op), points64, 64 * n, cudaMemcpyHostToDevice, e->stream));
+    }
+    if (g_scalar32) CK(cudaMemcpyAsync(c.at(og), g_scalar32, 32, cudaMemcpyHostToDevice, e->stream));
+    if (!secp256k1_b200_ecmult_multi_dev(e, c.at(oo), g_scalar32 ? c.at(og) : nullptr, c.at(os), c.at(op), n, c.at(ow), wsb, e->stream)) return 0;
+    CK(cudaMemcpyAsync(out64, c.at(oo), 64, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
 /* ---- batched point parsing / serialization ----------------------------------------------------------- */
 int secp256k1_b200_point_codec_batch_dev(secp256k1_b200_engine* e, unsigned char* d_ok, unsigned char* d_out64, const unsigned char* d_in,
                                          size_t in_stride, uint32_t in_len, int fmt, size_t n, void* stream) {

@@ -63,6 +63,11 @@ def load_library():
     lib.secp256k1_b200_pedersen_commit_batch_dev.argtypes = [vp, u8p, u8p, u8p, u64p, u8p, sz, sz, vp]
     lib.secp256k1_b200_rangeproof_verify_batch.argtypes = [vp, u8p, u64p, u64p, u8p, u8p, sz, vp, u8p, sz, u8p, sz, vp, sz]
     lib.secp256k1_b200_rangeproof_verify_batch_dev.argtypes = [vp, u8p, u64p, u64p, u8p, u8p, sz, vp, u8p, sz, u8p, sz, vp, sz, vp]
+    lib.secp256k1_b200_ecmult_multi_workspace_bytes.argtypes = [sz]
+    lib.secp256k1_b200_ecmult_multi_workspace_bytes.restype = sz
+    lib.secp256k1_b200_ecmult_multi.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
+    lib.secp256k1_b200_ecmult_multi_dev.argtypes = [vp, u8p, u8p, u8p, u8p, sz, vp, sz, vp]
+    lib.secp256k1_b200_point_codec_batch.argtypes = [vp, u8p, u8p, u8p, sz, ctypes.c_uint32, ci, sz]
     lib.secp256k1_b200_imad_probe_dev.argtypes = [vp, vp, ci, ci, ci, vp]
     lib.secp256k1_b200_ecmult_batch.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
     lib.secp256k1_b200_ecmult_batch_dev.argtypes = [vp, u8p, u8p, u8p, u8p, sz, vp]
@@ -171,6 +176,30 @@ class Engine:
         ok = np.empty(n, dtype=np.uint8)
         self._ck(self._lib.secp256k1_b200_ecdsa_verify_batch(self._h, _p(ok), _p(sig), sigfmt, _p(m), _p(p), pkfmt, n))
         return ok
+
+    def ecmult_multi(self, scalars32, points64, g_scalar32=None):
+        """sum_i scalars[i]*points[i] (+ g_scalar*G); returns 64 bytes x||y (zeros = infinity)"""
+        sc = _u8(scalars32, len(scalars32) if not hasattr(scalars32, "size") else scalars32.size, "scalars32")
+        n = sc.size // 32
+        pt = _u8(points64, 64 * n, "points64")
+        g = _u8(g_scalar32, 32, "g_scalar32") if g_scalar32 is not None else None
+        out = np.zeros(64, dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_ecmult_multi(self._h, _p(out), _p(g), _p(sc) if n else None, _p(pt) if n else None, n))
+        return out.tobytes()
+
+    def ecmult_multi_workspace_bytes(self, n):
+        return int(self._lib.secp256k1_b200_ecmult_multi_workspace_bytes(n))
+
+    def ecmult_multi_dev(self, d_out64, d_g_scalar32, d_scalars32, d_points64, n, d_workspace, workspace_bytes, stream=0):
+        self._ck(self._lib.secp256k1_b200_ecmult_multi_dev(self._h, d_out64, d_g_scalar32, d_scalars32, d_points64, n, d_workspace, workspace_bytes, stream))
+
+    def point_codec(self, data, in_len, fmt):
+        a = _u8(data, len(data) if not hasattr(data, "size") else data.size, "data")
+        n = a.size // in_len
+        ok = np.empty(n, dtype=np.uint8)
+        out = np.empty(64 * n, dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_point_codec_batch(self._h, _p(ok), _p(out), _p(a), in_len, in_len, fmt, n))
+        return ok, out.reshape(n, 64)
 
     def pedersen_commit(self, blind32, values, gen64):
         """gen64: 64 bytes (shared) or n*64 bytes (one generator per item)"""

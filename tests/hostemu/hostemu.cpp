@@ -22,6 +22,7 @@ int emu_fe_is_zero(const uint8_t* a) { fe x; fe_set_b32(x, a); return fe_is_zero
 #include "../../secp256k1-zkp_b200/csrc/verify.cuh"
 #include "../../secp256k1-zkp_b200/csrc/testdata.cuh"
 #include "../../secp256k1-zkp_b200/csrc/rangeproof.cuh"
+#include "../../secp256k1-zkp_b200/csrc/msm.cuh"
 #include <vector>
 #include <string.h>
 static std::vector<uint32_t> g_tab;
@@ -122,6 +123,42 @@ int emu_rangeproof_verify(uint64_t* minv, uint64_t* maxv, const uint8_t* commit3
 }
 int emu_pedersen_commit(uint8_t* out33, const uint8_t* blind32, uint64_t value, const uint8_t* gen64) {
     return pedersen_commit_item(out33, blind32, value, gen64, g_gt);
+}
+// the k_msm_* kernel pipeline executed sequentially
+int emu_msm(uint8_t* out64, const uint8_t* g_sc32, const uint8_t* scalars32, const uint8_t* points64, size_t n) {
+    const size_t N = n + 1;
+    std::vector<uint32_t> scal(N * 8), pts(N * 16), hist((size_t)MSM_WINDOWS * MSM_BUCKETS, 0), offs(hist.size()), cur(hist.size(), 0), entries((size_t)MSM_WINDOWS * N);
+    for (size_t i = 0; i < N; i++) {
+        sc k;
+        if (i < n) { sc_set_b32(k, scalars32 + 32 * i); fe x, y; bn_from_be32(x.v, points64 + 64 * i); bn_from_be32(y.v, points64 + 64 * i + 32);
+                     for (int t = 0; t < 8; t++) { pts[16 * i + t] = x.v[t]; pts[16 * i + 8 + t] = y.v[t]; } }
+        else { if (g_sc32) sc_set_b32(k, g_sc32); else sc_set_zero(k); ge g; ge_set_generator(g); for (int t = 0; t < 8; t++) { pts[16 * i + t] = g.x.v[t]; pts[16 * i + 8 + t] = g.y.v[t]; } }
+        for (int t = 0; t < 8; t++) scal[8 * i + t] = k.v[t];
+    }
+    auto is_inf = [&](size_t i) { uint32_t z = 0; for (int t = 0; t < 16; t++) z |= pts[16 * i + t]; return z == 0; };
+    for (size_t i = 0; i < N; i++) {
+        if (is_inf(i)) continue;
+        sc k; for (int t = 0; t < 8; t++) k.v[t] = scal[8 * i + t];
+        int32_t d[MSM_WINDOWS]; msm_digits(d, k);
+        for (int w = 0; w < MSM_WINDOWS; w++) if (d[w]) hist[(size_t)w * MSM_BUCKETS + (uint32_t)(d[w] < 0 ? -d[w] : d[w]) - 1]++;
+    }
+    for (int w = 0; w < MSM_WINDOWS; w++) { uint32_t run = 0; for (int b = 0; b < MSM_BUCKETS; b++) { offs[(size_t)w * MSM_BUCKETS + b] = run; run += hist[(size_t)w * MSM_BUCKETS + b]; } }
+    for (size_t i = 0; i < N; i++) {
+        if (is_inf(i)) continue;
+        sc k; for (int t = 0; t < 8; t++) k.v[t] = scal[8 * i + t];
+        int32_t d[MSM_WINDOWS]; msm_digits(d, k);
+        for (int w = 0; w < MSM_WINDOWS; w++) if (d[w]) {
+            uint32_t neg = d[w] < 0; size_t wb = (size_t)w * MSM_BUCKETS + (uint32_t)(neg ? -d[w] : d[w]) - 1;
+            entries[(size_t)w * N + offs[wb] + cur[wb]++] = (uint32_t)i | (neg << 31);
+        }
+    }
+    std::vector<gej_store> buckets(hist.size()), chunks((size_t)MSM_WINDOWS * MSM_CHUNKS), groups(MSM_WINDOWS * 32), windows(MSM_WINDOWS);
+    for (size_t t = 0; t < hist.size(); t++) { gej acc; msm_bucket_sum(acc, entries.data() + (t / MSM_BUCKETS) * N, offs[t], offs[t] + hist[t], pts.data()); msm_store_gej(buckets[t], acc); }
+    for (size_t t = 0; t < chunks.size(); t++) { gej o; msm_chunk_reduce(o, buckets.data() + (t / MSM_CHUNKS) * MSM_BUCKETS, (uint32_t)(t % MSM_CHUNKS) * MSM_CHUNK); msm_store_gej(chunks[t], o); }
+    for (size_t t = 0; t < groups.size(); t++) { gej o; msm_sum_range(o, chunks.data() + t * 32, 32); msm_store_gej(groups[t], o); }
+    for (size_t t = 0; t < windows.size(); t++) { gej o; msm_sum_range(o, groups.data() + t * 32, 32); msm_store_gej(windows[t], o); }
+    gej r; msm_horner(r, windows.data());
+    return gej_to_xy64(out64, r);
 }
 int emu_ecdsa_verify(const uint8_t* sig, int sigfmt, const uint8_t* msg32, const uint8_t* pk, int pkfmt) {
     tab_local tab; return ecdsa_verify_item(sig, sigfmt, msg32, pk, pkfmt, g_gt, tab);

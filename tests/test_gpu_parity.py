@@ -388,3 +388,43 @@ def test_rangeproof_64bit_batch_vs_reference(engine, ref):
     assert int(ok.sum()) == n - len(range(3, n, 8))
     okc, cg = engine.pedersen_commit(blinds, vals, gen)
     assert okc.all() and np.array_equal(cg, commits)
+
+
+# ---- multi-scalar multiplication ---------------------------------------------------------------------
+def test_ecmult_multi_vs_reference(engine, ref):
+    rnd = random.Random(55)
+    for m in (0, 1, 2, 87, 88, 300, 5000):
+        ks = [rnd.getrandbits(256) % N for _ in range(m)]
+        pts = bytearray(ref.ecmult_batch(G64 * m, bytes(32 * m), b"".join(b32(k) for k in ks)).tobytes()) if m else bytearray()
+        scs = [rnd.choice([0, 1, N - 1, 2**255, 32768, 32769, 65535 << 16, N - 32768]) if i % 4 == 0 else rnd.getrandbits(256) % N for i in range(m)]
+        if m >= 87:
+            pts[64 * 3:64 * 4] = bytes(64)                       # point at infinity
+            pts[64 * 5:64 * 6] = pts[64 * 4:64 * 5]              # cancelling pair
+            scs[5] = (N - scs[4]) % N
+            for i in range(10, 40):                              # many points in ONE bucket (same scalar)
+                scs[i] = scs[10]
+        sc = b"".join(b32(x) for x in scs)
+        for g in (None, b32(rnd.getrandbits(256) % N), b32(0)):
+            ok, exp = ref.ecmult_multi(sc, bytes(pts), g, scratch_bytes=1 << 24)
+            assert ok == 1
+            assert engine.ecmult_multi(sc, bytes(pts), g) == exp, (m, g is None)
+
+
+def test_ecmult_multi_2pow20_bench_identity(engine, ref):
+    """bench_ecmult's teardown identity at the BASELINE size (src/bench_ecmult.c:73-93, :250-260): with P_i = sk_i*G the
+    MSM must equal (sum s_i*sk_i mod n)*G -- checked with scalars only, no oracle MSM needed -- plus a 2^15-term prefix
+    against the reference's own Pippenger."""
+    n = 1 << 20
+    rng = np.random.default_rng(77)
+    sk = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); sk[:, 0] &= 0x7F
+    s = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); s[:, 0] &= 0x7F
+    pts = engine.ecmult(np.zeros((n, 64), dtype=np.uint8), np.zeros((n, 32), dtype=np.uint8), sk)       # sk_i * G
+    got = engine.ecmult_multi(s, pts)
+    ski = [int.from_bytes(bytes(r), "big") for r in sk]
+    si = [int.from_bytes(bytes(r), "big") for r in s]
+    tot = sum(a * b for a, b in zip(ski, si)) % N
+    exp = bytes(engine.ecmult(bytes(64), bytes(32), b32(tot))[0])
+    assert got == exp
+    m = 1 << 15
+    ok, exp = ref.ecmult_multi(s[:m].tobytes(), pts[:m].tobytes(), None, scratch_bytes=64 << 20)
+    assert ok == 1 and engine.ecmult_multi(s[:m], pts[:m]) == exp

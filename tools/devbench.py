@@ -78,5 +78,28 @@ def main():
         print(json.dumps({"bench": "ecdsa_verify_comp33", "n": n, "ms": ms, "ops_s": n / ms * 1e3, "accepted": int(ok.sum())}))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+
+
+def bench_msm_and_rangeproof():
+    import hashlib
+    torch.cuda.init()
+    eng = b200.Engine()
+    stream = torch.cuda.current_stream().cuda_stream
+    for lg in (16, 20):
+        n = 1 << lg
+        ng = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda"); ng[:, 0] = 0x7F
+        pts = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
+        eng.ecmult_dev(pts.data_ptr(), torch.zeros((n, 64), dtype=torch.uint8, device="cuda").data_ptr(),
+                       torch.zeros((n, 32), dtype=torch.uint8, device="cuda").data_ptr(), ng.data_ptr(), n, stream)
+        sc = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda"); sc[:, 0] &= 0x7F
+        wsb = eng.ecmult_multi_workspace_bytes(n)
+        ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+        out = torch.empty(64, dtype=torch.uint8, device="cuda")
+        ms = timed(lambda: eng.ecmult_multi_dev(out.data_ptr(), None, sc.data_ptr(), pts.data_ptr(), n, ws.data_ptr(), wsb, stream), warm=1, reps=3)
+        print(json.dumps({"bench": "ecmult_multi_pippenger", "n": n, "ms": ms, "terms_s": n / ms * 1e3, "workspace_mib": wsb / 2**20}))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "msm":
+    bench_msm_and_rangeproof()
