@@ -126,6 +126,25 @@ SECP256K1_B200_API int secp256k1_b200_ecmult_multi(secp256k1_b200_engine *e, uns
 SECP256K1_B200_API int secp256k1_b200_ecmult_multi_dev(secp256k1_b200_engine *e, unsigned char *d_out64, const unsigned char *d_g_scalar32,
         const unsigned char *d_scalars32, const unsigned char *d_points64, size_t n, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* ---- Bulletproofs++ norm-product argument (the only BP++ proof this reference snapshot implements) ------------- */
+/* Replaces static secp256k1_bppp_rangeproof_norm_product_verify (src/modules/bppp/bppp_norm_product_impl.h:425).
+ * All proofs of a batch share the geometry (g_len G-generators, h_len H-generators, both powers of two <= 64) and the generator
+ * list gens64 ((g_len+h_len) x 64 bytes affine x||y big-endian, G's first).  Per proof: proof bytes (65*rounds + 64),
+ * commitment (64 bytes x||y), rho (32 bytes), c_vec (h_len x 32 bytes) and the parent protocol's transcript: a 104-byte
+ * SHA-256 object {8 x u32 state (little-endian words), 64-byte block buffer, u64 byte count (little-endian)} in the state
+ * the reference's `secp256k1_sha256 *transcript` argument would be in.  Helpers: _sha256_state_init = a fresh SHA-256
+ * (what the reference's verify vectors use, modules/bppp/tests_impl.h:548); _bppp_transcript_init = the set-up of the
+ * reference's round-trip tests (modules/bppp/tests_impl.h:273-311).  Both are host-side hashing only. */
+SECP256K1_B200_API void secp256k1_b200_sha256_state_init(unsigned char *state104);
+SECP256K1_B200_API void secp256k1_b200_bppp_transcript_init(unsigned char *state104, const unsigned char *commit_xy64, const unsigned char *rho32,
+        const unsigned char *gens64, size_t g_len, size_t n_gens, const unsigned char *c_vec32, size_t c_len);
+SECP256K1_B200_API int secp256k1_b200_bppp_norm_verify_batch(secp256k1_b200_engine *e, unsigned char *ok, const unsigned char *proofs, size_t proof_stride,
+        const uint32_t *plen, const unsigned char *transcripts104, const unsigned char *rho32, const unsigned char *gens64, size_t g_len,
+        const unsigned char *c_vec32, size_t h_len, const unsigned char *commits64, size_t n);
+SECP256K1_B200_API int secp256k1_b200_bppp_norm_verify_batch_dev(secp256k1_b200_engine *e, unsigned char *d_ok, const unsigned char *d_proofs, size_t proof_stride,
+        const uint32_t *d_plen, const unsigned char *d_transcripts104, const unsigned char *d_rho32, const unsigned char *d_gens64, size_t g_len,
+        const unsigned char *d_c_vec32, size_t h_len, const unsigned char *d_commits64, size_t n, void *stream);
+
 /* ---- batched point parsing / serialization (everything that needs a field square root) ------------------ */
 #define SECP256K1_B200_CODEC_XONLY32       1 /* 32-byte x-only key  -> 64-byte opaque secp256k1_xonly_pubkey (include/secp256k1_extrakeys.h:47) */
 #define SECP256K1_B200_CODEC_EC_PUBKEY     2 /* 33/65-byte SEC1 key -> 64-byte opaque secp256k1_pubkey (include/secp256k1.h:462) */

@@ -362,6 +362,78 @@ int secp256k1_b200_ecmult_multi(secp256k1_b200_engine* e, unsigned char* out64, 
     return 1;
 }
 
+/* ---- BP++ norm-product argument ---------------------------------------------------------------------------- */
+static void sha_state_export(unsigned char* out104, const sha256& h) {
+    for (int k = 0; k < 8; k++) { out104[4 * k] = (unsigned char)h.s[k]; out104[4 * k + 1] = (unsigned char)(h.s[k] >> 8); out104[4 * k + 2] = (unsigned char)(h.s[k] >> 16); out104[4 * k + 3] = (unsigned char)(h.s[k] >> 24); }
+    memcpy(out104 + 32, h.buf, 64);
+    for (int k = 0; k < 8; k++) out104[96 + k] = (unsigned char)(h.bytes >> (8 * k));
+}
+void secp256k1_b200_sha256_state_init(unsigned char* state104) {
+    sha256 h; sha256_init(h); memset(h.buf, 0, 64);
+    sha_state_export(state104, h);
+}
+/* transcript set-up used by the reference's own norm-argument tests (modules/bppp/tests_impl.h:273-311): host-side hashing only */
+void secp256k1_b200_bppp_transcript_init(unsigned char* state104, const unsigned char* commit_xy64, const unsigned char* rho32,
+                                         const unsigned char* gens64, size_t g_len, size_t n_gens, const unsigned char* c_vec32, size_t c_len) {
+    sha256 h;
+    memset(h.buf, 0, 64);
+    sha256_init_tagged(h, (const uint8_t*)"Bulletproofs_pp/v0/commitment", 29);
+    unsigned char ser[33], le[8];
+    ser[0] = (commit_xy64[63] & 1) ? 3 : 2; memcpy(ser + 1, commit_xy64, 32);
+    sha256_write(h, ser, 33);
+    sha256_write(h, rho32, 32);
+    for (int k = 0; k < 8; k++) le[k] = (unsigned char)((uint64_t)g_len >> (8 * k));
+    sha256_write(h, le, 8);
+    for (int k = 0; k < 8; k++) le[k] = (unsigned char)((uint64_t)n_gens >> (8 * k));
+    sha256_write(h, le, 8);
+    for (size_t i = 0; i < n_gens; i++) {
+        ser[0] = (gens64[64 * i + 63] & 1) ? 3 : 2; memcpy(ser + 1, gens64 + 64 * i, 32);
+        sha256_write(h, ser, 33);
+    }
+    for (int k = 0; k < 8; k++) le[k] = (unsigned char)((uint64_t)c_len >> (8 * k));
+    sha256_write(h, le, 8);
+    sha256_write(h, c_vec32, 32 * c_len);
+    sha_state_export(state104, h);
+}
+int secp256k1_b200_bppp_norm_verify_batch_dev(secp256k1_b200_engine* e, unsigned char* d_ok, const unsigned char* d_proofs, size_t proof_stride,
+                                              const uint32_t* d_plen, const unsigned char* d_transcripts104, const unsigned char* d_rho32,
+                                              const unsigned char* d_gens64, size_t g_len, const unsigned char* d_c_vec32, size_t h_len,
+                                              const unsigned char* d_commits64, size_t n, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    device_guard guard(e->device);
+    CK(launch_bppp_norm_verify(d_ok, d_proofs, proof_stride, d_plen, d_transcripts104, d_rho32, d_gens64, (uint32_t)g_len, d_c_vec32, (uint32_t)h_len,
+                               d_commits64, n, e->gt(), (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_bppp_norm_verify_batch(secp256k1_b200_engine* e, unsigned char* ok, const unsigned char* proofs, size_t proof_stride,
+                                          const uint32_t* plen, const unsigned char* transcripts104, const unsigned char* rho32,
+                                          const unsigned char* gens64, size_t g_len, const unsigned char* c_vec32, size_t h_len,
+                                          const unsigned char* commits64, size_t n) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (n == 0) return 1;
+    if (g_len == 0 || h_len == 0 || g_len > 64 || h_len > 64) { memset(ok, 0, n); return 1; }   /* the reference returns 0 for empty vectors (:448) */
+    for (size_t i = 0; i < n; i++) if (plen[i] > proof_stride) { set_error("bppp_norm_verify_batch: plen[i] > proof_stride"); return 0; }
+    std::lock_guard<std::mutex> lock(e->mu);
+    device_guard guard(e->device);
+    carver c(e);
+    size_t ng = g_len + h_len;
+    size_t op = c.add(proof_stride * n), ol = c.add(4 * n), ot = c.add(104 * n), orh = c.add(32 * n), og = c.add(64 * ng),
+           oc = c.add(32 * h_len * n), ocm = c.add(64 * n), ook = c.add(n);
+    if (!c.commit()) return 0;
+    CK(cudaMemcpyAsync(c.at(op), proofs, proof_stride * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(ol), plen, 4 * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(ot), transcripts104, 104 * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(orh), rho32, 32 * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(og), gens64, 64 * ng, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(oc), c_vec32, 32 * h_len * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(ocm), commits64, 64 * n, cudaMemcpyHostToDevice, e->stream));
+    if (!secp256k1_b200_bppp_norm_verify_batch_dev(e, c.at(ook), c.at(op), proof_stride, (const uint32_t*)c.at(ol), c.at(ot), c.at(orh), c.at(og), g_len,
+                                                   c.at(oc), h_len, c.at(ocm), n, e->stream)) return 0;
+    CK(cudaMemcpyAsync(ok, c.at(ook), n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
 /* ---- batched point parsing / serialization ----------------------------------------------------------- */
 int secp256k1_b200_point_codec_batch_dev(secp256k1_b200_engine* e, unsigned char* d_ok, unsigned char* d_out64, const unsigned char* d_in,
                                          size_t in_stride, uint32_t in_len, int fmt, size_t n, void* stream) {

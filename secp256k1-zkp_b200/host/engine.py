@@ -68,6 +68,12 @@ def load_library():
     lib.secp256k1_b200_ecmult_multi.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
     lib.secp256k1_b200_ecmult_multi_dev.argtypes = [vp, u8p, u8p, u8p, u8p, sz, vp, sz, vp]
     lib.secp256k1_b200_point_codec_batch.argtypes = [vp, u8p, u8p, u8p, sz, ctypes.c_uint32, ci, sz]
+    lib.secp256k1_b200_sha256_state_init.argtypes = [u8p]
+    lib.secp256k1_b200_sha256_state_init.restype = None
+    lib.secp256k1_b200_bppp_transcript_init.argtypes = [u8p, u8p, u8p, u8p, sz, sz, u8p, sz]
+    lib.secp256k1_b200_bppp_transcript_init.restype = None
+    lib.secp256k1_b200_bppp_norm_verify_batch.argtypes = [vp, u8p, u8p, sz, vp, u8p, u8p, u8p, sz, u8p, sz, u8p, sz]
+    lib.secp256k1_b200_bppp_norm_verify_batch_dev.argtypes = [vp, u8p, u8p, sz, vp, u8p, u8p, u8p, sz, u8p, sz, u8p, sz, vp]
     lib.secp256k1_b200_imad_probe_dev.argtypes = [vp, vp, ci, ci, ci, vp]
     lib.secp256k1_b200_ecmult_batch.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
     lib.secp256k1_b200_ecmult_batch_dev.argtypes = [vp, u8p, u8p, u8p, u8p, sz, vp]
@@ -200,6 +206,37 @@ class Engine:
         out = np.empty(64 * n, dtype=np.uint8)
         self._ck(self._lib.secp256k1_b200_point_codec_batch(self._h, _p(ok), _p(out), _p(a), in_len, in_len, fmt, n))
         return ok, out.reshape(n, 64)
+
+    def bppp_transcripts(self, commits64, rho32, gens64, g_len, c_vec32, h_len, mode="tests"):
+        """104-byte SHA-256 transcript objects: mode 'plain' = fresh SHA-256 (the reference's verify vectors),
+        'tests' = commit to the initial public data like modules/bppp/tests_impl.h:273-311 (host-side hashing)"""
+        cm = _u8(commits64, len(commits64) if not hasattr(commits64, "size") else commits64.size, "commits64")
+        n = cm.size // 64
+        out = np.zeros((n, 104), dtype=np.uint8)
+        if mode == "plain":
+            self._lib.secp256k1_b200_sha256_state_init(_p(out))
+            out[:] = out[0]
+            return out
+        rho = _u8(rho32, 32 * n, "rho32")
+        g = _u8(gens64, 64 * (g_len + h_len), "gens64")
+        cv = _u8(c_vec32, 32 * h_len * n, "c_vec32")
+        for i in range(n):
+            self._lib.secp256k1_b200_bppp_transcript_init(out[i].ctypes.data, cm[64 * i:].ctypes.data, rho[32 * i:].ctypes.data, _p(g), g_len,
+                                                          g_len + h_len, cv[32 * h_len * i:].ctypes.data, h_len)
+        return out
+
+    def bppp_norm_verify(self, proofs, plen, transcripts104, rho32, gens64, g_len, c_vec32, h_len, commits64):
+        pr = np.ascontiguousarray(proofs, dtype=np.uint8)
+        n, stride = pr.shape
+        pl = np.ascontiguousarray(plen, dtype=np.uint32).reshape(-1)
+        tr = _u8(transcripts104, 104 * n, "transcripts104")
+        rho = _u8(rho32, 32 * n, "rho32")
+        g = _u8(gens64, 64 * (g_len + h_len), "gens64")
+        cv = _u8(c_vec32, 32 * h_len * n, "c_vec32")
+        cm = _u8(commits64, 64 * n, "commits64")
+        ok = np.empty(n, dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_bppp_norm_verify_batch(self._h, _p(ok), _p(pr), stride, _p(pl), _p(tr), _p(rho), _p(g), g_len, _p(cv), h_len, _p(cm), n))
+        return ok
 
     def pedersen_commit(self, blind32, values, gen64):
         """gen64: 64 bytes (shared) or n*64 bytes (one generator per item)"""

@@ -23,6 +23,7 @@ int emu_fe_is_zero(const uint8_t* a) { fe x; fe_set_b32(x, a); return fe_is_zero
 #include "../../secp256k1-zkp_b200/csrc/testdata.cuh"
 #include "../../secp256k1-zkp_b200/csrc/rangeproof.cuh"
 #include "../../secp256k1-zkp_b200/csrc/msm.cuh"
+#include "../../secp256k1-zkp_b200/csrc/bppp.cuh"
 #include <vector>
 #include <string.h>
 static std::vector<uint32_t> g_tab;
@@ -159,6 +160,44 @@ int emu_msm(uint8_t* out64, const uint8_t* g_sc32, const uint8_t* scalars32, con
     for (size_t t = 0; t < windows.size(); t++) { gej o; msm_sum_range(o, groups.data() + t * 32, 32); msm_store_gej(windows[t], o); }
     gej r; msm_horner(r, windows.data());
     return gej_to_xy64(out64, r);
+}
+// k_bppp_norm_verify lane by lane; mode 0 = plain SHA-256 transcript, 1 = tests' initial-data transcript
+int emu_bppp_norm_verify(const uint8_t* proof, size_t plen, const uint8_t* commit64, const uint8_t* rho32, const uint8_t* gens64, uint32_t g_len,
+                         const uint8_t* c_vec32, uint32_t h_len, int mode) {
+    sha256 tr; memset(tr.buf, 0, 64);
+    if (mode == 0) sha256_init(tr);
+    else {
+        sha256_init_tagged(tr, (const uint8_t*)"Bulletproofs_pp/v0/commitment", 29);
+        uint8_t ser[33], le[8];
+        ser[0] = (commit64[63] & 1) ? 3 : 2; memcpy(ser + 1, commit64, 32); sha256_write(tr, ser, 33);
+        sha256_write(tr, rho32, 32);
+        for (int k = 0; k < 8; k++) le[k] = (uint8_t)((uint64_t)g_len >> (8 * k)); sha256_write(tr, le, 8);
+        for (int k = 0; k < 8; k++) le[k] = (uint8_t)((uint64_t)(g_len + h_len) >> (8 * k)); sha256_write(tr, le, 8);
+        for (uint32_t i = 0; i < g_len + h_len; i++) { ser[0] = (gens64[64 * i + 63] & 1) ? 3 : 2; memcpy(ser + 1, gens64 + 64 * i, 32); sha256_write(tr, ser, 33); }
+        for (int k = 0; k < 8; k++) le[k] = (uint8_t)((uint64_t)h_len >> (8 * k)); sha256_write(tr, le, 8);
+        sha256_write(tr, c_vec32, 32 * (size_t)h_len);
+    }
+    sc rho; if (sc_set_b32(rho, rho32)) return 0;
+    bppp_ctx c;
+    if (!bppp_prepare(c, proof, plen, tr, rho, g_len, h_len)) return 0;
+    gej total; gej_set_infinity(total);
+    uint32_t T = bppp_num_terms(c);
+    sc zero; sc_set_zero(zero);
+    for (uint32_t t = 0; t < T; t++) {
+        ge pt; sc s;
+        if (!bppp_term(pt, s, c, t, proof, gens64)) return 0;
+        if (pt.inf) continue;
+        gej pj, r, sum; gej_set_ge(pj, pt);
+        tab_local tab; ecmult(r, pj, s, zero, g_gt, tab);
+        gej_add(sum, total, r); total = sum;
+    }
+    sc v; bppp_v(v, c, c_vec32); sc_negate(v, v);
+    gej inf, r, sum; gej_set_infinity(inf);
+    tab_local tab; ecmult(r, inf, zero, v, g_gt, tab);
+    gej_add(sum, total, r); total = sum;
+    ge cm; ge_from_xy64(cm, commit64);
+    if (!cm.inf) { gej_add_ge(sum, total, cm); total = sum; }
+    return total.inf;
 }
 int emu_ecdsa_verify(const uint8_t* sig, int sigfmt, const uint8_t* msg32, const uint8_t* pk, int pkfmt) {
     tab_local tab; return ecdsa_verify_item(sig, sigfmt, msg32, pk, pkfmt, g_gt, tab);

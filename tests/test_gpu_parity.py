@@ -146,6 +146,7 @@ def test_ecdsa_verify_batch_vs_reference(engine, ref):
 
 
 # ---- the reference's own golden vectors through the C ABI ------------------------------------------
+import ctypes
 import json
 import os
 
@@ -428,3 +429,54 @@ def test_ecmult_multi_2pow20_bench_identity(engine, ref):
     m = 1 << 15
     ok, exp = ref.ecmult_multi(s[:m].tobytes(), pts[:m].tobytes(), None, scratch_bytes=64 << 20)
     assert ok == 1 and engine.ecmult_multi(s[:m], pts[:m]) == exp
+
+
+# ---- BP++ norm-product argument ---------------------------------------------------------------------------
+def test_bppp_golden_vectors_gpu(engine):
+    d = json.load(open(os.path.join(GOLD, "bppp_verify.json")))
+    gens = bytes.fromhex(d["gens_xy"])
+    for v in d["vectors"]:
+        g, h = v["g_len"], v["h_len"]
+        pr = np.frombuffer(bytes.fromhex(v["proof"]), dtype=np.uint8).reshape(1, -1)
+        cm, rho, cv = bytes.fromhex(v["commit_xy"]), bytes.fromhex(v["r32"]), bytes.fromhex(v["c_vec32"])
+        if g == 0:
+            tr = engine.bppp_transcripts(cm, rho, b"", 0, cv, h, mode="plain")
+            ok = engine._lib.secp256k1_b200_bppp_norm_verify_batch  # shape guard path: g_len = 0 -> rejected
+            out = np.ones(1, dtype=np.uint8)
+            assert ok(engine._h, out.ctypes.data, pr.ctypes.data, pr.shape[1], np.array([pr.shape[1]], dtype=np.uint32).ctypes.data, tr.ctypes.data,
+                      np.frombuffer(rho, dtype=np.uint8).ctypes.data, None, 0, np.frombuffer(cv, dtype=np.uint8).ctypes.data, h,
+                      np.frombuffer(cm, dtype=np.uint8).ctypes.data, 1) == 1
+            assert int(out[0]) == 0
+            continue
+        tr = engine.bppp_transcripts(cm, rho, gens[:64 * (g + h)], g, cv, h, mode="plain")
+        got = engine.bppp_norm_verify(pr, [pr.shape[1]], tr, rho, gens[:64 * (g + h)], g, cv, h, cm)
+        assert int(got[0]) == v["expected"], v["index"]
+
+
+def test_bppp_norm_verify_batch_vs_reference(engine, ref):
+    """SURVEY 8d config 5 geometry (16 G + 8 H generators), proofs made by the reference prover, 1/4 tampered;
+    plus other geometries."""
+    L = ref.lib
+    L.secp256k1_bppp_generators_create.restype = ctypes.c_void_p
+    rnd = random.Random(66)
+    for (g, h, n) in [(16, 8, 96), (1, 1, 8), (64, 1, 4), (1, 64, 4), (8, 16, 8), (32, 32, 4)]:
+        gs = ctypes.c_void_p(L.secp256k1_bppp_generators_create(ref.ctx, ctypes.c_size_t(g + h)))
+        gxy = ctypes.create_string_buffer(64 * (g + h)); L.ref_bppp_generators_xy(gxy, gs)
+        proofs, rhos, cvs, cms, exp = [], [], [], [], []
+        for i in range(n):
+            nv = b"".join(b32(rnd.getrandbits(256) % N) for _ in range(g)); lv = b"".join(b32(rnd.getrandbits(256) % N) for _ in range(h))
+            cv = b"".join(b32(rnd.getrandbits(256) % N) for _ in range(h)); rho = b32(rnd.getrandbits(256) % N or 1)
+            proof = ctypes.create_string_buffer(1000); plen = ctypes.c_size_t(1000); cm = ctypes.create_string_buffer(64)
+            assert L.ref_bppp_norm_prove(ref.ctx, proof, ctypes.byref(plen), cm, rho, gs, nv, ctypes.c_size_t(g), lv, cv, ctypes.c_size_t(h)) == 1
+            pr = bytearray(proof.raw[:plen.value])
+            if i % 4 == 1:
+                pr[rnd.randrange(len(pr))] ^= 1 << rnd.randrange(8)
+            if i % 16 == 5:
+                pr[-1] ^= 1          # the SURVEY 8d pattern: flip the last byte
+            e = L.ref_bppp_norm_verify(ref.ctx, bytes(pr), ctypes.c_size_t(len(pr)), cm.raw, rho, gs, ctypes.c_size_t(g), cv, ctypes.c_size_t(h))
+            proofs.append(bytes(pr)); rhos.append(rho); cvs.append(cv); cms.append(cm.raw); exp.append(e)
+        P = np.frombuffer(b"".join(proofs), dtype=np.uint8).reshape(n, -1)
+        tr = engine.bppp_transcripts(b"".join(cms), b"".join(rhos), gxy.raw, g, b"".join(cvs), h, mode="tests")
+        got = engine.bppp_norm_verify(P, [P.shape[1]] * n, tr, b"".join(rhos), gxy.raw, g, b"".join(cvs), h, b"".join(cms))
+        assert list(got) == exp, (g, h)
+        assert sum(exp) >= n // 2

@@ -197,3 +197,81 @@ def test_schnorr_and_ecdsa_random_vs_reference(emu, ref):
     exp = ref.ecdsa_verify(bytes(sig), bytes(m), bytes(pk))
     for i in range(n):
         assert emu.emu_ecdsa_verify(bytes(sig[64 * i:64 * i + 64]), 1, bytes(m[32 * i:32 * i + 32]), bytes(pk[33 * i:33 * i + 33]), 2) == exp[i]
+
+
+# ---- rangeproof / pedersen / MSM / BP++ logic (the warp-cooperative kernels, lanes run sequentially) ---------------
+def _emu_rp(emu, commit, proof, gen, extra=b""):
+    mn, mx = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    ok = emu.emu_rangeproof_verify(ctypes.byref(mn), ctypes.byref(mx), bytes(commit), bytes(proof), ctypes.c_size_t(len(proof)), bytes(gen),
+                                   extra if extra else None, ctypes.c_size_t(len(extra)))
+    return ok, mn.value, mx.value
+
+
+def test_rangeproof_and_pedersen_logic(emu, ref):
+    gen = ref.generator_h()
+    for v in json.load(open(os.path.join(GOLD, "rangeproof.json")))["vectors"]:
+        pr, c = bytes.fromhex(v["proof"]), bytes.fromhex(v["commit"])
+        assert _emu_rp(emu, c, pr, gen) == (1, v["min_value"], v["max_value"]), v["name"]
+        bad = bytearray(pr); bad[len(bad) // 3] ^= 8
+        assert _emu_rp(emu, c, bytes(bad), gen)[0] == 0
+        assert _emu_rp(emu, c, pr + b"\0", gen)[0] == 0
+    rnd = random.Random(3)
+    vals = [0, 1, 2**64 - 1] + [rnd.getrandbits(64) for _ in range(4)]
+    blinds = b"".join(b32(rnd.getrandbits(256) % N) for _ in vals)
+    okr, cr = ref.pedersen_commit(blinds, vals, gen)
+    for i, v in enumerate(vals):
+        out = ctypes.create_string_buffer(33)
+        assert emu.emu_pedersen_commit(out, blinds[32 * i:32 * i + 32], ctypes.c_uint64(v), gen) == 1 and out.raw == bytes(cr[i])
+    for (mv, ex, mb, vs) in [(13, 1, 8, [77, 200]), (100, 2, 13, [100 + 4500, 100 + 123400]), (0, 0, 1, [0, 1]), (0, 3, 0, [7000, 9000])]:
+        proofs, plen, commits = ref.rangeproof_make(blinds[:64], vs, gen, min_value=mv, exp=ex, min_bits=mb)
+        for i in range(2):
+            pr = bytes(proofs[i][:int(plen[i])])
+            e = ref.rangeproof_verify_one(bytes(commits[i]), pr, gen)
+            assert e == _emu_rp(emu, bytes(commits[i]), pr, gen) and e[0] == 1
+            for pos in random.Random(i).sample(range(len(pr)), 8):
+                bad = bytearray(pr); bad[pos] ^= 1 << (pos % 8)
+                assert ref.rangeproof_verify_one(bytes(commits[i]), bytes(bad), gen) == _emu_rp(emu, bytes(commits[i]), bytes(bad), gen)
+
+
+def test_msm_pipeline_logic(emu, ref):
+    rnd = random.Random(5)
+    for m in (0, 1, 7, 100, 300):
+        ks = [rnd.getrandbits(256) % N for _ in range(m)]
+        pts = bytearray(ref.ecmult_batch(G64 * m, bytes(32 * m), b"".join(b32(k) for k in ks)).tobytes()) if m else bytearray()
+        scs = [rnd.choice([0, 1, N - 1, 2**255, 32768, 32769, 65535 << 16, N - 32768]) if i % 4 == 0 else rnd.getrandbits(256) % N for i in range(m)]
+        if m >= 7:
+            pts[64 * 3:64 * 4] = bytes(64)
+            pts[64 * 5:64 * 6] = pts[64 * 4:64 * 5]; scs[5] = (N - scs[4]) % N
+        sc = b"".join(b32(x) for x in scs)
+        for g in (None, b32(rnd.getrandbits(256) % N)):
+            out = ctypes.create_string_buffer(64)
+            emu.emu_msm(out, g, sc if m else None, bytes(pts) if m else None, ctypes.c_size_t(m))
+            ok, exp = ref.ecmult_multi(sc, bytes(pts), g, scratch_bytes=1 << 22)
+            assert ok == 1 and out.raw == exp, (m, g is None)
+
+
+def test_bppp_norm_verify_logic(emu, ref):
+    d = json.load(open(os.path.join(GOLD, "bppp_verify.json")))
+    gens = bytes.fromhex(d["gens_xy"])
+    for v in d["vectors"]:
+        pr = bytes.fromhex(v["proof"])
+        got = emu.emu_bppp_norm_verify(pr, ctypes.c_size_t(len(pr)), bytes.fromhex(v["commit_xy"]), bytes.fromhex(v["r32"]), gens, v["g_len"],
+                                       bytes.fromhex(v["c_vec32"]), v["h_len"], 0)
+        assert got == v["expected"], v["index"]
+    L = ref.lib
+    L.secp256k1_bppp_generators_create.restype = ctypes.c_void_p
+    rnd = random.Random(8)
+    for (g, h) in [(16, 8), (1, 1), (8, 16)]:
+        gs = ctypes.c_void_p(L.secp256k1_bppp_generators_create(ref.ctx, ctypes.c_size_t(g + h)))
+        gxy = ctypes.create_string_buffer(64 * (g + h)); L.ref_bppp_generators_xy(gxy, gs)
+        nv = b"".join(b32(rnd.getrandbits(256) % N) for _ in range(g)); lv = b"".join(b32(rnd.getrandbits(256) % N) for _ in range(h))
+        cv = b"".join(b32(rnd.getrandbits(256) % N) for _ in range(h)); rho = b32(rnd.getrandbits(256) % N)
+        proof = ctypes.create_string_buffer(1000); plen = ctypes.c_size_t(1000); cm = ctypes.create_string_buffer(64)
+        assert L.ref_bppp_norm_prove(ref.ctx, proof, ctypes.byref(plen), cm, rho, gs, nv, ctypes.c_size_t(g), lv, cv, ctypes.c_size_t(h)) == 1
+        pr = proof.raw[:plen.value]
+        for mut in (None, plen.value - 1, plen.value - 33, 0, 7):
+            p2 = bytearray(pr)
+            if mut is not None: p2[mut] ^= 1
+            p2 = bytes(p2)
+            e = L.ref_bppp_norm_verify(ref.ctx, p2, ctypes.c_size_t(len(p2)), cm.raw, rho, gs, ctypes.c_size_t(g), cv, ctypes.c_size_t(h))
+            assert e == emu.emu_bppp_norm_verify(p2, ctypes.c_size_t(len(p2)), cm.raw, rho, gxy.raw, g, cv, h, 1), (g, h, mut)

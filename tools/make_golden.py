@@ -162,11 +162,45 @@ def rangeproof(ref):
     return {"source": "src/modules/rangeproof/tests_impl.h:589-812 and :883-1349; generator = secp256k1_generator_h", "vectors": out}
 
 
+def bppp_vectors(ref):
+    """verify_vector_0..12 (src/modules/bppp/test_vectors/verify.h; driver tests_impl.h:540-598: fresh SHA-256 transcript).
+    Generators / commitments are stored both as in the file (33-byte compressed) and decompressed by the reference (x||y)."""
+    t = read("src/modules/bppp/test_vectors/verify.h")
+    arrs = {n: b for n, b, _ in parse_arrays(t)}
+    L = ref.lib
+
+    def decompress(c33):
+        if c33 == bytes(33):
+            return bytes(64)
+        pk = ctypes.create_string_buffer(64)
+        assert L.secp256k1_ec_pubkey_parse(ref.ctx, pk, c33, ctypes.c_size_t(33)) == 1
+        xy = ctypes.create_string_buffer(64)
+        L.ref_pubkey_to_xy(xy, pk)
+        return xy.raw
+    gens33 = arrs["verify_vector_gens"]
+    gens_xy = b"".join(decompress(gens33[33 * i:33 * i + 33]) for i in range(len(gens33) // 33))
+    out = []
+    for i in range(13):
+        pre = "verify_vector_%d_" % i
+        g_len = int(re.search(pre + r"n_vec_len = (\d+);", t).group(1))
+        c_raw = re.search(pre + r"c_vec32\[(\d+)\]\[32\] = \{(.*?)\};", t, re.S)
+        h_len = int(c_raw.group(1))
+        cv = bytes(int(h, 16) for h in re.findall(r"0x([0-9a-fA-F]{2})", c_raw.group(2)))
+        assert len(cv) == 32 * h_len
+        result = int(re.search(pre + r"result = (\d);", t).group(1))
+        out.append({"index": i, "g_len": g_len, "h_len": h_len, "proof": arrs[pre + "proof"].hex(), "r32": arrs[pre + "r32"].hex(),
+                    "c_vec32": cv.hex(), "commit33": arrs[pre + "commit33"].hex(), "commit_xy": decompress(arrs[pre + "commit33"]).hex(),
+                    "expected": result})
+    return {"source": "src/modules/bppp/test_vectors/verify.h (driver src/modules/bppp/tests_impl.h:540-598, plain SHA-256 transcript)",
+            "gens33": gens33.hex(), "gens_xy": gens_xy.hex(), "vectors": out}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     from tests.refshim import RefLib
     ref = RefLib()
     jobs = {"bip340.json": bip340, "ecmult.json": ecmult_golden, "wycheproof_ecdsa.json": lambda: wycheproof(ref)}
+    jobs["bppp_verify.json"] = lambda: bppp_vectors(ref)
     if hasattr(ref, "rangeproof_verify_one"):
         jobs["rangeproof.json"] = lambda: rangeproof(ref)
     for name, fn in jobs.items():
