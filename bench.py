@@ -30,11 +30,12 @@ BYTES_PER_VERIFY = 64 + 32 + 32 + 1
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=20, help="verifies per GPU per step = 2^log2n")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (rangeproof / MSM / BP++)")
     return ap.parse_args()
 
 
@@ -161,6 +162,116 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# secondary workloads of BASELINE.json (configs 2..4): MSM, 64-bit range proofs, BP++ norm argument.  Inputs: GPU-generated
+# points / committed fixtures made by the reference prover (tools/make_*_fixture.py), tiled to the batch size.
+def _time_dev(torch, dist, world, fn, warm=2, reps=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def run_extra_workloads(eng, b200, torch, dist, D, dev, stream, rank, world, imad_peak):
+    import numpy as np
+    out = {}
+    gold = os.path.join(ROOT, "tests", "golden")
+    # ---- config 2: Pippenger 2^20-term MSM, strong scaling: rank r owns terms [r*N/W, (r+1)*N/W), partial sums all-gathered
+    n_total = 1 << 20
+    lo, hi = D.shard_range(n_total, rank, world)
+    m = hi - lo
+    gen = torch.Generator(device=dev); gen.manual_seed(777 + rank)
+    sk = torch.randint(0, 256, (m, 32), dtype=torch.uint8, device=dev, generator=gen); sk[:, 0] &= 0x7F
+    sc = torch.randint(0, 256, (m, 32), dtype=torch.uint8, device=dev, generator=gen); sc[:, 0] &= 0x7F
+    pts = torch.empty((m, 64), dtype=torch.uint8, device=dev)
+    z64, z32 = torch.zeros((m, 64), dtype=torch.uint8, device=dev), torch.zeros((m, 32), dtype=torch.uint8, device=dev)
+    eng.ecmult_dev(pts.data_ptr(), z64.data_ptr(), z32.data_ptr(), sk.data_ptr(), m, stream)     # P_i = sk_i * G
+    wsb = eng.ecmult_multi_workspace_bytes(max(m, 64))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    part = torch.empty(64, dtype=torch.uint8, device=dev)
+    final = torch.empty(64, dtype=torch.uint8, device=dev)
+    ones = torch.zeros((world, 32), dtype=torch.uint8, device=dev); ones[:, 31] = 1
+
+    def msm_step():
+        eng.ecmult_multi_dev(part.data_ptr(), None, sc.data_ptr(), pts.data_ptr(), m, ws.data_ptr(), wsb, stream)
+        if world > 1:
+            allp = D.allgather_points(part)
+            eng.ecmult_multi_dev(final.data_ptr(), None, ones.data_ptr(), allp.data_ptr(), world, ws.data_ptr(), wsb, stream)
+    ms = _time_dev(torch, dist, world, msm_step)
+    # identity check of bench_ecmult's teardown (src/bench_ecmult.c:73-93): MSM == (sum s_i*sk_i) * G, scalars on the host
+    res = (final if world > 1 else part).cpu().numpy().tobytes()
+    N_ORD = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+    skh, sch = sk.cpu().numpy(), sc.cpu().numpy()
+    tot = sum(int.from_bytes(a.tobytes(), "big") * int.from_bytes(b.tobytes(), "big") for a, b in zip(skh, sch)) % N_ORD
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, tot)
+        tot = sum(parts) % N_ORD
+    exp = eng.ecmult(bytes(64), bytes(32), tot.to_bytes(32, "big"))[0].tobytes()
+    out["msm_pippenger"] = {"terms": n_total, "ms": ms, "terms_per_s": n_total / ms * 1e3, "scaling": "strong", "identity_check_ok": res == exp,
+                            "roofline_frac_ref_mac": n_total / world * 2.5e4 / (ms / 1e3) / 1e12 / imad_peak if world == 1 else None}
+    del ws, pts, sk, sc, z64, z32
+    # ---- config 3: 64-bit range proofs, 8192 per GPU (65536 on 8 GPUs), reference-made fixture tiled, 1/32 corrupted
+    fx = np.load(os.path.join(gold, "rangeproof64_fixture.npz"))
+    per = 8192
+    reps = per // fx["proofs"].shape[0]
+    proofs = torch.from_numpy(np.tile(fx["proofs"], (reps, 1))).to(dev)
+    commits = torch.from_numpy(np.tile(fx["commits"], (reps, 1))).to(dev)
+    bad = torch.arange(3, per, 32, device=dev)
+    proofs[bad, (bad * 7919) % 5126] ^= 1
+    plen = torch.full((per,), 5126, dtype=torch.int32, device=dev)
+    g64 = torch.from_numpy(fx["gen64"].copy()).to(dev)
+    okr = torch.zeros(per, dtype=torch.uint8, device=dev)
+    mn = torch.zeros(per, dtype=torch.int64, device=dev); mx = torch.zeros(per, dtype=torch.int64, device=dev)
+
+    def rp_step():
+        eng.rangeproof_verify_dev(okr.data_ptr(), mn.data_ptr(), mx.data_ptr(), commits.data_ptr(), proofs.data_ptr(), 5126, plen.data_ptr(),
+                                  g64.data_ptr(), 0, per, stream)
+        if world > 1:
+            D.allgather_bitmaps(D.pack_bitmap(okr))
+    ms = _time_dev(torch, dist, world, rp_step, warm=1, reps=3)
+    expok = torch.ones(per, dtype=torch.uint8, device=dev); expok[bad] = 0
+    out["rangeproof_verify_64bit"] = {"proofs": per * world, "per_gpu": per, "ms": ms, "verify_per_s": per * world / ms * 1e3, "scaling": "weak",
+                                      "accept_pattern_ok": bool(torch.equal(okr, expok)), "max_value_ok": bool((mx == -1).all()),
+                                      "roofline_frac_ref_mac": per * 2.7e7 / (ms / 1e3) / 1e12 / imad_peak,
+                                      "data": "64 distinct reference-signed proofs (tests/golden/rangeproof64_fixture.npz) tiled"}
+    del proofs, commits
+    # ---- config 4: BP++ norm-product argument, 16 G + 8 H generators, 512 per GPU (4096 on 8 GPUs)
+    fb = np.load(os.path.join(gold, "bppp_fixture.npz"))
+    per = 512
+    reps = per // fb["proofs"].shape[0]
+    bp = np.tile(fb["proofs"], (reps, 1)); rho = np.tile(fb["rho"], (reps, 1)); cv = np.tile(fb["c_vec"], (reps, 1)); cm = np.tile(fb["commits"], (reps, 1))
+    badi = np.arange(5, per, 16)
+    bp[badi, 323] ^= 1
+    tr = eng.bppp_transcripts(cm, rho, fb["gens"], 16, cv, 8, mode="tests")
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in (("p", bp), ("rho", rho), ("cv", cv), ("cm", cm), ("tr", tr), ("g", fb["gens"]))}
+    pl = torch.full((per,), 324, dtype=torch.int32, device=dev)
+    okb = torch.zeros(per, dtype=torch.uint8, device=dev)
+
+    def bp_step():
+        eng._ck(eng._lib.secp256k1_b200_bppp_norm_verify_batch_dev(eng._h, okb.data_ptr(), d["p"].data_ptr(), 324, pl.data_ptr(), d["tr"].data_ptr(),
+                                                                   d["rho"].data_ptr(), d["g"].data_ptr(), 16, d["cv"].data_ptr(), 8, d["cm"].data_ptr(), per, stream))
+        if world > 1:
+            D.allgather_bitmaps(D.pack_bitmap(okb))
+    ms = _time_dev(torch, dist, world, bp_step, warm=1, reps=3)
+    expb = np.ones(per, dtype=np.uint8); expb[badi] = 0
+    out["bppp_norm_verify_16g8h"] = {"proofs": per * world, "per_gpu": per, "ms": ms, "verify_per_s": per * world / ms * 1e3, "scaling": "weak",
+                                     "accept_pattern_ok": bool(np.array_equal(okb.cpu().numpy(), expb)),
+                                     "note": "norm-product argument only: this reference snapshot has no full BP++ range proof (SURVEY fact 3)"}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -184,16 +295,9 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
 
     # ---- engine + generator table: rank 0 builds, ONE NCCL broadcast replicates it ---------------
+    from secp256k1_zkp_b200.host import dist as D
     eng = b200.Engine(device=local_rank, build_tables=(rank == 0))
-    if world > 1:
-        tab = torch.empty(eng.table_bytes, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            eng.table_export_dev(tab.data_ptr(), stream)
-        dist.broadcast(tab, src=0)
-        if rank != 0:
-            eng.table_import_dev(tab.data_ptr(), stream)
-        torch.cuda.synchronize()
-        del tab
+    D.replicate_engine_table(eng, rank, dev, stream)
 
     # ---- synthetic workload, generated on the GPU -----------------------------------------------------
     n = 1 << args.log2n
@@ -212,7 +316,6 @@ def main():
     expected = torch.ones(n, dtype=torch.uint8, device=dev)
     expected[bad] = 0
     ok = torch.zeros(n, dtype=torch.uint8, device=dev)
-    weights = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.uint8, device=dev)
     gathered = torch.empty(world * n // 8, dtype=torch.uint8, device=dev) if world > 1 else None
     torch.cuda.synchronize()
 
@@ -227,8 +330,7 @@ def main():
             e1.record()
             kernel_ms.append((e0, e1))
         if world > 1:
-            packed = (ok.view(-1, 8) * weights).sum(dim=1, dtype=torch.uint8)
-            dist.all_gather_into_tensor(gathered, packed)
+            D.allgather_bitmaps(D.pack_bitmap(ok), gathered)
 
     # ---- integer-pipe peak, measured live (register-resident IMAD.WIDE.U32 saturation) ------------------
     pblocks, pthreads, piters = 148 * 8, 256, 4096
@@ -313,6 +415,13 @@ def main():
         except OSError as e:
             parity.update({"oracle": "unavailable: %s" % e})
 
+    extra = None
+    if not args.no_extra:
+        try:
+            extra = run_extra_workloads(eng, b200, torch, dist, D, dev, stream, rank, world, imad_peak_tmacs)
+        except Exception as ex:  # the headline line must survive a failing secondary workload
+            extra = {"error": repr(ex)}
+
     if rank == 0:
         total = world * n
         value = total / (ms / 1e3)
@@ -344,6 +453,8 @@ def main():
         }
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
+        if extra is not None:
+            line["extra"] = extra
         print(json.dumps(line))
     eng.close()
     if world > 1:

@@ -172,7 +172,8 @@ SECP256K1_B200_API int secp256k1_b200_pedersen_commit_batch_dev(secp256k1_b200_e
  * secp256k1_pedersen_commitment_serialize emits / the first 33 bytes of the opaque object); generators as above;
  * extra: optional extra_commit data (extra + i*extra_stride, extra_len[i] bytes; NULL = none).
  * ok[i] = accept bit; min_value[i]/max_value[i] are written from the proof header exactly when the reference writes
- * them (also for proofs that fail later), 0 if the header itself is rejected first. */
+ * them (also for proofs that fail later); both are 0 if the header is rejected before they are written or if the
+ * commitment does not parse (the reference caller would not get past secp256k1_pedersen_commitment_parse). */
 SECP256K1_B200_API int secp256k1_b200_rangeproof_verify_batch(secp256k1_b200_engine *e, unsigned char *ok, uint64_t *min_value, uint64_t *max_value,
         const unsigned char *commit33, const unsigned char *proofs, size_t proof_stride, const uint32_t *plen,
         const unsigned char *gen64, size_t gen_stride, const unsigned char *extra, size_t extra_stride, const uint32_t *extra_len, size_t n);

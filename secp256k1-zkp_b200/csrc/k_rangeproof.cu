@@ -48,6 +48,10 @@ __global__ void __launch_bounds__(RP_WARPS * 32, 3) k_rangeproof_verify(uint8_t*
     }
     int gen_sq = fe_is_square(genp.y);                       // all lanes (uniform)
     if (lane == 0) rp_message_hash(m32, h, proof, c33, g64, gen_sq, ex, exl);
+    // a commitment that does not parse is rejected without looking at the proof: the reference caller never reaches
+    // secp256k1_rangeproof_verify (secp256k1_pedersen_commitment_parse fails first), so min/max stay untouched (0 here)
+    int commit_ok = __shfl_sync(0xffffffffu, good, (int)h.rings - 1);
+    if (!commit_ok && lane == 0) { minv[item] = 0; maxv[item] = 0; }
     good = __all_sync(0xffffffffu, good);
     __syncwarp();
     // ---- P2: accj = min_value*H + sum C_i

@@ -97,6 +97,7 @@ int emu_rangeproof_verify(uint64_t* minv, uint64_t* maxv, const uint8_t* commit3
         if (lane + 1 < h.rings) g = rp_digit_commitment_load(mine[lane], h, proof, lane);
         else if (lane + 1 == h.rings) g = rp_commitment_load(mine[lane], commit33);
         if (lane + 1 < h.rings && g) gej_set_ge(pts[lane], mine[lane]); else gej_set_infinity(pts[lane]);
+        if (lane + 1 == h.rings && !g) { *minv = 0; *maxv = 0; }
         good &= g;
     }
     uint8_t m32[32], r33[32 * 33];
