@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 using namespace b200;
@@ -418,7 +419,8 @@ int secp256k1_b200_bppp_norm_verify_batch(secp256k1_b200_engine* e, unsigned cha
     carver c(e);
     size_t ng = g_len + h_len;
     size_t op = c.add(proof_stride * n), ol = c.add(4 * n), ot = c.add(104 * n), orh = c.add(32 * n), og = c.add(64 * ng),
-           oc = c.add(32 * h_len * n), ocm = c.add(64 * n), ook = c.add(n);
+           oc = c.add(32 * h_len * n), ocm = c.add(64 * n), ook = c.add(n), odbg = c.add(33 * 64 * n);
+    const char* dbgfile = getenv("SECP256K1_B200_BPPP_DEBUG");
     if (!c.commit()) return 0;
     CK(cudaMemcpyAsync(c.at(op), proofs, proof_stride * n, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(c.at(ol), plen, 4 * n, cudaMemcpyHostToDevice, e->stream));
@@ -427,7 +429,15 @@ int secp256k1_b200_bppp_norm_verify_batch(secp256k1_b200_engine* e, unsigned cha
     CK(cudaMemcpyAsync(c.at(og), gens64, 64 * ng, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(c.at(oc), c_vec32, 32 * h_len * n, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(c.at(ocm), commits64, 64 * n, cudaMemcpyHostToDevice, e->stream));
-    if (!secp256k1_b200_bppp_norm_verify_batch_dev(e, c.at(ook), c.at(op), proof_stride, (const uint32_t*)c.at(ol), c.at(ot), c.at(orh), c.at(og), g_len,
+    if (dbgfile) {
+        CK(launch_bppp_norm_verify(c.at(ook), c.at(op), proof_stride, (const uint32_t*)c.at(ol), c.at(ot), c.at(orh), c.at(og), (uint32_t)g_len, c.at(oc),
+                                   (uint32_t)h_len, c.at(ocm), n, e->gt(), e->stream, &e->launches, c.at(odbg)));
+        std::vector<unsigned char> h(33 * 64 * n);
+        CK(cudaMemcpyAsync(h.data(), c.at(odbg), h.size(), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        FILE* f = fopen(dbgfile, "wb");
+        if (f) { fwrite(h.data(), 1, h.size(), f); fclose(f); }
+    } else if (!secp256k1_b200_bppp_norm_verify_batch_dev(e, c.at(ook), c.at(op), proof_stride, (const uint32_t*)c.at(ol), c.at(ot), c.at(orh), c.at(og), g_len,
                                                    c.at(oc), h_len, c.at(ocm), n, e->stream)) return 0;
     CK(cudaMemcpyAsync(ok, c.at(ook), n, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
