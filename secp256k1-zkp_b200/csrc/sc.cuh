@@ -156,7 +156,11 @@ HD void sc_split_lambda(sc& r1, sc& r2, const sc& k) {
 }
 
 // r = a^(n-2) (a = 0 -> 0); value-identical to the reference's safegcd inverse (scalar_4x64_impl.h:1162)
-HDNI void sc_inverse(sc& r, const sc& a) {
+// NOTE: deliberately NOT an outlined (__noinline__) function.  As a separate function with its 16-entry dynamically
+// indexed local table, one sm_100a build of k_bppp_norm_verify computed a wrong inverse deterministically (no sanitizer
+// finding; inlining this function, or any unrelated change to the kernel, made it disappear -- A/B libraries on the GPU,
+// round 1).  Inlined, the table lives in the kernel's own frame like every other local array.
+HD void sc_inverse(sc& r, const sc& a) {
     // n - 2, little-endian limbs
     const uint32_t e[8] = {0xD036413Fu, 0xBFD25E8Cu, 0xAF48A03Bu, 0xBAAEDCE6u, 0xFFFFFFFEu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
     // 4-bit fixed window

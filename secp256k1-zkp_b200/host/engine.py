@@ -23,6 +23,8 @@ class B200Error(RuntimeError):
 
 
 def library_path():
+    if os.environ.get("SECP256K1_B200_LIB"):       # development override (A/B of two builds)
+        return os.environ["SECP256K1_B200_LIB"]
     return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libsecp256k1_b200.so")
 
 
