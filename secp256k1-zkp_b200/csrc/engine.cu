@@ -38,6 +38,7 @@ struct secp256k1_b200_engine {
     bip340_midstate_h mid;
     sign_consts_h sign;
     cudaStream_t stream;       // engine-owned stream for host-buffer calls
+    cudaStream_t stream2;      // second stream: chunked host-buffer calls overlap H2D of chunk k+1 with the kernel of chunk k
     uint8_t* d_scratch;        // grow-only device scratch for host-buffer calls
     size_t scratch_bytes;
     uint64_t launches;
@@ -116,7 +117,7 @@ int secp256k1_b200_engine_create(secp256k1_b200_engine** out, int device, int ge
     e->windows = (256 + gw - 1) / gw;
     e->gtab_bytes = (size_t)e->windows * ((size_t)1 << gw) * 64;
     e->d_gtab = nullptr; e->d_bases = nullptr; e->d_scratch = nullptr; e->scratch_bytes = 0; e->launches = 0;
-    e->stream = nullptr;
+    e->stream = nullptr; e->stream2 = nullptr;
     {
         sha256 h;
         sha256_init_tagged(h, (const uint8_t*)"BIP0340/challenge", 17);
@@ -129,6 +130,7 @@ int secp256k1_b200_engine_create(secp256k1_b200_engine** out, int device, int ge
         sha256_finalize(h, e->sign.zero_mask);
     }
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc((void**)&e->d_gtab, e->gtab_bytes) != cudaSuccess ||
         cudaMalloc((void**)&e->d_bases, (size_t)e->windows * 64) != cudaSuccess) {
         set_error("engine_create: device allocation failed", cudaGetLastError());
@@ -147,6 +149,7 @@ void secp256k1_b200_engine_destroy(secp256k1_b200_engine* e) {
     if (!e) return;
     device_guard guard(e->device);
     if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+    if (e->stream2) { cudaStreamSynchronize(e->stream2); cudaStreamDestroy(e->stream2); }
     if (e->d_gtab) cudaFree(e->d_gtab);
     if (e->d_bases) cudaFree(e->d_bases);
     if (e->d_scratch) cudaFree(e->d_scratch);
@@ -254,12 +257,22 @@ int secp256k1_b200_schnorrsig_verify_batch(secp256k1_b200_engine* e, unsigned ch
     size_t pl = pk_len(pkfmt);
     size_t os = c.add(64 * n), om = c.add(msglen * n + 16), op = c.add(pl * n), oo = c.add(n);
     if (!c.commit()) return 0;
-    CK(cudaMemcpyAsync(c.at(os), sig64, 64 * n, cudaMemcpyHostToDevice, e->stream));
-    if (msglen) CK(cudaMemcpyAsync(c.at(om), msg, msglen * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(c.at(op), pk, pl * n, cudaMemcpyHostToDevice, e->stream));
-    if (!secp256k1_b200_schnorrsig_verify_batch_dev(e, c.at(oo), c.at(os), c.at(om), msglen, c.at(op), pkfmt, n, e->stream)) return 0;
-    CK(cudaMemcpyAsync(ok, c.at(oo), n, cudaMemcpyDeviceToHost, e->stream));
+    // chunked + double-buffered: the copies of chunk k+1 (stream B) overlap the kernel of chunk k (stream A); with pinned
+    // host buffers the whole call costs ~one kernel time + one chunk of transfer instead of kernel + full transfer
+    const size_t chunk = n > (1u << 17) ? ((size_t)1 << 17) : n;
+    cudaStream_t st[2] = {e->stream, e->stream2};
+    int k = 0;
+    for (size_t lo = 0; lo < n; lo += chunk, k ^= 1) {
+        size_t m = n - lo < chunk ? n - lo : chunk;
+        cudaStream_t s = st[k];
+        CK(cudaMemcpyAsync(c.at(os) + 64 * lo, sig64 + 64 * lo, 64 * m, cudaMemcpyHostToDevice, s));
+        if (msglen) CK(cudaMemcpyAsync(c.at(om) + msglen * lo, msg + msglen * lo, msglen * m, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(c.at(op) + pl * lo, pk + pl * lo, pl * m, cudaMemcpyHostToDevice, s));
+        if (!secp256k1_b200_schnorrsig_verify_batch_dev(e, c.at(oo) + lo, c.at(os) + 64 * lo, c.at(om) + msglen * lo, msglen, c.at(op) + pl * lo, pkfmt, m, s)) return 0;
+        CK(cudaMemcpyAsync(ok + lo, c.at(oo) + lo, m, cudaMemcpyDeviceToHost, s));
+    }
     CK(cudaStreamSynchronize(e->stream));
+    CK(cudaStreamSynchronize(e->stream2));
     return 1;
 }
 
