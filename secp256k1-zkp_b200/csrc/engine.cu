@@ -41,6 +41,8 @@ struct secp256k1_b200_engine {
     cudaStream_t stream2;      // second stream: chunked host-buffer calls overlap H2D of chunk k+1 with the kernel of chunk k
     uint8_t* d_scratch;        // grow-only device scratch for host-buffer calls
     size_t scratch_bytes;
+    uint8_t* h_pinned;         // grow-only pinned host staging for results (a D2H copy into pageable memory would block the host
+    size_t pinned_bytes;       //  and serialize the chunk pipeline)
     uint64_t launches;
     std::mutex mu;             // the reference context is usable from many threads (secp256k1.h:42-49): serialize here
 
@@ -117,6 +119,7 @@ int secp256k1_b200_engine_create(secp256k1_b200_engine** out, int device, int ge
     e->windows = (256 + gw - 1) / gw;
     e->gtab_bytes = (size_t)e->windows * ((size_t)1 << gw) * 64;
     e->d_gtab = nullptr; e->d_bases = nullptr; e->d_scratch = nullptr; e->scratch_bytes = 0; e->launches = 0;
+    e->h_pinned = nullptr; e->pinned_bytes = 0;
     e->stream = nullptr; e->stream2 = nullptr;
     {
         sha256 h;
@@ -153,6 +156,7 @@ void secp256k1_b200_engine_destroy(secp256k1_b200_engine* e) {
     if (e->d_gtab) cudaFree(e->d_gtab);
     if (e->d_bases) cudaFree(e->d_bases);
     if (e->d_scratch) cudaFree(e->d_scratch);
+    if (e->h_pinned) cudaFreeHost(e->h_pinned);
     delete e;
 }
 
@@ -259,6 +263,12 @@ int secp256k1_b200_schnorrsig_verify_batch(secp256k1_b200_engine* e, unsigned ch
     if (!c.commit()) return 0;
     // chunked + double-buffered: the copies of chunk k+1 (stream B) overlap the kernel of chunk k (stream A); with pinned
     // host buffers the whole call costs ~one kernel time + one chunk of transfer instead of kernel + full transfer
+    if (n > e->pinned_bytes) {
+        if (e->h_pinned) cudaFreeHost(e->h_pinned);
+        e->h_pinned = nullptr; e->pinned_bytes = 0;
+        CK(cudaHostAlloc((void**)&e->h_pinned, n + (n >> 2), cudaHostAllocDefault));
+        e->pinned_bytes = n + (n >> 2);
+    }
     const size_t chunk = n > (1u << 17) ? ((size_t)1 << 17) : n;
     cudaStream_t st[2] = {e->stream, e->stream2};
     int k = 0;
@@ -269,10 +279,11 @@ int secp256k1_b200_schnorrsig_verify_batch(secp256k1_b200_engine* e, unsigned ch
         if (msglen) CK(cudaMemcpyAsync(c.at(om) + msglen * lo, msg + msglen * lo, msglen * m, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(c.at(op) + pl * lo, pk + pl * lo, pl * m, cudaMemcpyHostToDevice, s));
         if (!secp256k1_b200_schnorrsig_verify_batch_dev(e, c.at(oo) + lo, c.at(os) + 64 * lo, c.at(om) + msglen * lo, msglen, c.at(op) + pl * lo, pkfmt, m, s)) return 0;
-        CK(cudaMemcpyAsync(ok + lo, c.at(oo) + lo, m, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(e->h_pinned + lo, c.at(oo) + lo, m, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaStreamSynchronize(e->stream2));
+    memcpy(ok, e->h_pinned, n);
     return 1;
 }
 
