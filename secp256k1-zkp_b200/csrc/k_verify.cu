@@ -20,32 +20,66 @@ __device__ __forceinline__ void load_bytes_global(uint8_t* dst, const uint8_t* s
     }
 }
 
+// One field inversion per thread block (Montgomery's trick as a product tree in shared memory).  Every thread of the
+// block must call it (z = 1 for threads without work); returns 1/z.  `nodes` needs 2*blockDim.x field elements and may
+// alias the per-thread tables (they are dead by now).  Cost per 128-thread block: ~24 warp-level multiplications + ONE
+// 270-multiplication inversion executed by a single warp, instead of 4 warps x 270.
+__device__ __forceinline__ void fe_block_inverse(fe& zinv, const fe& z, fe* nodes) {
+    const uint32_t t = threadIdx.x, nt = blockDim.x;      // nt is a power of two
+    __syncthreads();                                        // table use finished everywhere
+    nodes[nt + t] = z;
+    __syncthreads();
+    for (uint32_t s = nt >> 1; s >= 1; s >>= 1) {
+        if (t < s) { fe r; fe_mul(r, nodes[2 * (s + t)], nodes[2 * (s + t) + 1]); nodes[s + t] = r; }
+        __syncthreads();
+    }
+    if (t == 0) { fe r; fe_inv(r, nodes[1]); nodes[1] = r; }
+    __syncthreads();
+    for (uint32_t s = 1; s < nt; s <<= 1) {
+        if (t < s) {
+            fe inv = nodes[s + t], l = nodes[2 * (s + t)], r = nodes[2 * (s + t) + 1], a, b;
+            fe_mul(a, inv, r);
+            fe_mul(b, inv, l);
+            nodes[2 * (s + t)] = a;
+            nodes[2 * (s + t) + 1] = b;
+        }
+        __syncthreads();
+    }
+    zinv = nodes[nt + t];
+}
+
 __global__ void __launch_bounds__(VERIFY_BLOCK, 3) k_ecmult(uint8_t* __restrict__ out64, const uint8_t* __restrict__ a64,
         const uint8_t* __restrict__ na32, const uint8_t* __restrict__ ng32, size_t n, ecmult_gtable gt) {
     extern __shared__ uint32_t smem[];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     tab_shared tab = {smem + threadIdx.x, (int)blockDim.x};
-    __align__(16) uint8_t in[128];
-    load_bytes_global(in, a64 + 64 * i, 64);
-    load_bytes_global(in + 64, na32 + 32 * i, 32);
-    if (ng32) load_bytes_global(in + 96, ng32 + 32 * i, 32);
-    ge a;
-    int z = 1;
-    for (int k = 0; k < 64; k++) z &= (in[k] == 0);
-    if (z) ge_set_infinity(a);
-    else { fe_set_b32(a.x, in); fe_set_b32(a.y, in + 32); a.inf = 0; }
-    sc na, ng;
-    sc_set_b32(na, in + 64);
-    if (ng32) sc_set_b32(ng, in + 96); else sc_set_zero(ng);
-    gej aj, R;
-    gej_set_ge(aj, a);
-    ecmult(R, aj, na, ng, gt, tab);
+    gej R; gej_set_infinity(R);
+    if (i < n) {
+        __align__(16) uint8_t in[128];
+        load_bytes_global(in, a64 + 64 * i, 64);
+        load_bytes_global(in + 64, na32 + 32 * i, 32);
+        if (ng32) load_bytes_global(in + 96, ng32 + 32 * i, 32);
+        ge a;
+        int z = 1;
+        for (int k = 0; k < 64; k++) z &= (in[k] == 0);
+        if (z) ge_set_infinity(a);
+        else { fe_set_b32(a.x, in); fe_set_b32(a.y, in + 32); a.inf = 0; }
+        sc na, ng;
+        sc_set_b32(na, in + 64);
+        if (ng32) sc_set_b32(ng, in + 96); else sc_set_zero(ng);
+        gej aj;
+        gej_set_ge(aj, a);
+        ecmult(R, aj, na, ng, gt, tab);
+    }
+    fe zz, zinv;
+    if (!R.inf) zz = R.z; else fe_set_int(zz, 1);
+    fe_block_inverse(zinv, zz, reinterpret_cast<fe*>(smem));
+    if (i >= n) return;
     __align__(16) uint8_t o[64];
     if (R.inf) {
         for (int k = 0; k < 64; k++) o[k] = 0;
     } else {
-        ge Ra; ge_set_gej(Ra, R);
+        ge Ra; ge_set_gej_zinv(Ra, R, zinv);
         fe_get_b32(o, Ra.x); fe_get_b32(o + 32, Ra.y);
     }
     uint4* q = reinterpret_cast<uint4*>(out64 + 64 * i);
@@ -59,14 +93,20 @@ __global__ void __launch_bounds__(VERIFY_BLOCK, 3) k_schnorr_verify(uint8_t* __r
         bip340_midstate mid, ecmult_gtable gt) {
     extern __shared__ uint32_t smem[];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     tab_shared tab = {smem + threadIdx.x, (int)blockDim.x};
-    __align__(16) uint8_t in[64 + 64];
-    load_bytes_global(in, sig64 + 64 * i, 64);
-    int pklen = pkfmt == PK_OPAQUE64 ? 64 : (pkfmt == PK_XONLY32 ? 32 : 33);
-    load_bytes_global(in + 64, pk + (size_t)pklen * i, pklen);
-    // messages of arbitrary (batch-uniform) length are hashed straight from global memory
-    ok[i] = (uint8_t)schnorr_verify_item(in, msg + (size_t)msglen * i, msglen, in + 64, pkfmt, mid, gt, tab);
+    gej R; fe rx, z, zinv;
+    int live = 0;
+    if (i < n) {
+        __align__(16) uint8_t in[64 + 64];
+        load_bytes_global(in, sig64 + 64 * i, 64);
+        int pklen = pkfmt == PK_OPAQUE64 ? 64 : (pkfmt == PK_XONLY32 ? 32 : 33);
+        load_bytes_global(in + 64, pk + (size_t)pklen * i, pklen);
+        // messages of arbitrary (batch-uniform) length are hashed straight from global memory
+        live = schnorr_verify_prepare(R, rx, in, msg + (size_t)msglen * i, msglen, in + 64, pkfmt, mid, gt, tab);
+    }
+    if (live) z = R.z; else fe_set_int(z, 1);
+    fe_block_inverse(zinv, z, reinterpret_cast<fe*>(smem));   // all threads of the block take part
+    if (i < n) ok[i] = (uint8_t)(live && schnorr_verify_finish(R, rx, zinv));
 }
 
 __global__ void __launch_bounds__(VERIFY_BLOCK, 3) k_ecdsa_verify(uint8_t* __restrict__ ok, const uint8_t* __restrict__ sig64, int sigfmt,

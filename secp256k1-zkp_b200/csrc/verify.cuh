@@ -57,10 +57,13 @@ HD int pubkey_load(ge& p, const uint8_t* pk, int fmt) {
 
 struct bip340_midstate { uint32_t s[8]; };   // SHA256 state after SHA256(tag)||SHA256(tag), tag = "BIP0340/challenge"
 
+// BIP-340 verification, split so that the kernel can share ONE field inversion per thread block between all its
+// signatures (Montgomery's trick as a shared-memory tree, see fe_block_inverse in k_verify.cu):
+//   prepare : parse, challenge hash, R = s*G - e*P (Jacobian).  returns 0 if the signature is already rejected.
+//   finish  : given 1/R.z, check y(R) even and x(R) == r.
 template <class Tab>
-HD int schnorr_verify_item(const uint8_t* sig64, const uint8_t* msg, uint32_t msglen, const uint8_t* pk, int pkfmt,
-                           const bip340_midstate& mid, const ecmult_gtable& gt, Tab& tab) {
-    fe rx;
+HD int schnorr_verify_prepare(gej& R, fe& rx, const uint8_t* sig64, const uint8_t* msg, uint32_t msglen, const uint8_t* pk, int pkfmt,
+                              const bip340_midstate& mid, const ecmult_gtable& gt, Tab& tab) {
     sc s, e;
     ge P;
     if (!fe_set_b32(rx, sig64)) return 0;            // r >= p           (main_impl.h:231)
@@ -81,14 +84,24 @@ HD int schnorr_verify_item(const uint8_t* sig64, const uint8_t* msg, uint32_t ms
         sc_set_b32(e, eb);
     }
     sc_negate(e, e);
-    gej Pj, R;
+    gej Pj;
     gej_set_ge(Pj, P);
     ecmult(R, Pj, e, s, gt, tab);                    // R = s*G - e*P    (:249-251)
-    if (R.inf) return 0;
+    return !R.inf;                                   // (:254)
+}
+HD int schnorr_verify_finish(const gej& R, const fe& rx, const fe& zinv) {
     ge Ra;
-    ge_set_gej(Ra, R);
+    ge_set_gej_zinv(Ra, R, zinv);
     if (fe_is_odd(Ra.y)) return 0;                   // (:258-259)
     return fe_equal(rx, Ra.x);
+}
+template <class Tab>
+HD int schnorr_verify_item(const uint8_t* sig64, const uint8_t* msg, uint32_t msglen, const uint8_t* pk, int pkfmt,
+                           const bip340_midstate& mid, const ecmult_gtable& gt, Tab& tab) {
+    gej R; fe rx, zi;
+    if (!schnorr_verify_prepare(R, rx, sig64, msg, msglen, pk, pkfmt, mid, gt, tab)) return 0;
+    fe_inv(zi, R.z);
+    return schnorr_verify_finish(R, rx, zi);
 }
 
 template <class Tab>
