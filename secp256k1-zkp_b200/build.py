@@ -9,8 +9,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libsecp256k1_b200.so")
+# development A/B builds: B200_EXTRA_NVCC_FLAGS="-DFOO" B200_BUILD_TAG=foo -> build_foo/ and libsecp256k1_b200_foo.so
+_TAG = os.environ.get("B200_BUILD_TAG", "")
+EXTRA = os.environ.get("B200_EXTRA_NVCC_FLAGS", "").split()
+OBJ = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(HERE, "libsecp256k1_b200" + ("_" + _TAG if _TAG else "") + ".so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -41,7 +44,7 @@ def _compile(unit, flags, force, hdr_time):
     if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
             and os.path.getmtime(obj) > hdr_time):
         return obj, ""
-    cmd = [NVCC] + ARCH + COMMON + flags + ["-c", "-o", obj, src]
+    cmd = [NVCC] + ARCH + COMMON + EXTRA + flags + ["-c", "-o", obj, src]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (unit, p.stdout, p.stderr))

@@ -83,7 +83,49 @@ __device__ __forceinline__ void bn_cmad1(uint32_t* acc, uint32_t a0, uint32_t b)
 
 // r[0..15] = a[0..7] * b[0..7]
 HD void bn_mul_wide(uint32_t* r, const uint32_t* a, const uint32_t* b) {
-#if BN_PTX
+#if BN_PTX && defined(BN_MUL_SPLIT4)
+    // four accumulator sets (rows 0-3 and rows 4-7 apart): the serial IMAD.WIDE.X dependency per accumulator halves
+    // (16 instead of 32 links) at the price of ~20 more adds on the (idle) ALU pipe
+    uint32_t e0[13], o0[13], e1[13], o1[13];
+#pragma unroll
+    for (int i = 0; i < 13; i++) { e0[i] = 0; o0[i] = 0; e1[i] = 0; o1[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 4; i += 2) {
+        bn_cmad4(e0 + i, a[0], a[2], a[4], a[6], b[i]);
+        bn_cmad4(e1 + i, a[0], a[2], a[4], a[6], b[4 + i]);
+        bn_cmad4(o0 + i, a[1], a[3], a[5], a[7], b[i]);
+        bn_cmad4(o1 + i, a[1], a[3], a[5], a[7], b[4 + i]);
+        bn_cmad4(o0 + i, a[0], a[2], a[4], a[6], b[i + 1]);
+        bn_cmad4(o1 + i, a[0], a[2], a[4], a[6], b[4 + i + 1]);
+        bn_cmad4(e0 + i + 2, a[1], a[3], a[5], a[7], b[i + 1]);
+        bn_cmad4(e1 + i + 2, a[1], a[3], a[5], a[7], b[4 + i + 1]);
+    }
+    // lo = e0 + (o0 << 32)  (12 limbs: a * b[0..3] < 2^384), hi likewise
+    uint32_t lo[12], hi[12], c;
+    lo[0] = e0[0]; hi[0] = e1[0];
+    asm("add.cc.u32  %0, %12, %23;\n\taddc.cc.u32 %1, %13, %24;\n\taddc.cc.u32 %2, %14, %25;\n\taddc.cc.u32 %3, %15, %26;\n\t"
+        "addc.cc.u32 %4, %16, %27;\n\taddc.cc.u32 %5, %17, %28;\n\taddc.cc.u32 %6, %18, %29;\n\taddc.cc.u32 %7, %19, %30;\n\t"
+        "addc.cc.u32 %8, %20, %31;\n\taddc.cc.u32 %9, %21, %32;\n\taddc.u32 %10, %22, %33;\n\tmov.u32 %11, 0;\n\t"
+        : "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3]), "=r"(lo[4]), "=r"(lo[5]), "=r"(lo[6]), "=r"(lo[7]), "=r"(lo[8]), "=r"(lo[9]), "=r"(lo[10]), "=r"(lo[11]), "=r"(c)
+        : "r"(e0[1]), "r"(e0[2]), "r"(e0[3]), "r"(e0[4]), "r"(e0[5]), "r"(e0[6]), "r"(e0[7]), "r"(e0[8]), "r"(e0[9]), "r"(e0[10]), "r"(e0[11]),
+          "r"(o0[0]), "r"(o0[1]), "r"(o0[2]), "r"(o0[3]), "r"(o0[4]), "r"(o0[5]), "r"(o0[6]), "r"(o0[7]), "r"(o0[8]), "r"(o0[9]), "r"(o0[10]));
+    asm("add.cc.u32  %0, %12, %23;\n\taddc.cc.u32 %1, %13, %24;\n\taddc.cc.u32 %2, %14, %25;\n\taddc.cc.u32 %3, %15, %26;\n\t"
+        "addc.cc.u32 %4, %16, %27;\n\taddc.cc.u32 %5, %17, %28;\n\taddc.cc.u32 %6, %18, %29;\n\taddc.cc.u32 %7, %19, %30;\n\t"
+        "addc.cc.u32 %8, %20, %31;\n\taddc.cc.u32 %9, %21, %32;\n\taddc.u32 %10, %22, %33;\n\tmov.u32 %11, 0;\n\t"
+        : "=r"(hi[1]), "=r"(hi[2]), "=r"(hi[3]), "=r"(hi[4]), "=r"(hi[5]), "=r"(hi[6]), "=r"(hi[7]), "=r"(hi[8]), "=r"(hi[9]), "=r"(hi[10]), "=r"(hi[11]), "=r"(c)
+        : "r"(e1[1]), "r"(e1[2]), "r"(e1[3]), "r"(e1[4]), "r"(e1[5]), "r"(e1[6]), "r"(e1[7]), "r"(e1[8]), "r"(e1[9]), "r"(e1[10]), "r"(e1[11]),
+          "r"(o1[0]), "r"(o1[1]), "r"(o1[2]), "r"(o1[3]), "r"(o1[4]), "r"(o1[5]), "r"(o1[6]), "r"(o1[7]), "r"(o1[8]), "r"(o1[9]), "r"(o1[10]));
+    // r = lo + (hi << 128)
+    r[0] = lo[0]; r[1] = lo[1]; r[2] = lo[2]; r[3] = lo[3];
+    asm("add.cc.u32  %0, %12, %20;\n\taddc.cc.u32 %1, %13, %21;\n\taddc.cc.u32 %2, %14, %22;\n\taddc.cc.u32 %3, %15, %23;\n\t"
+        "addc.cc.u32 %4, %16, %24;\n\taddc.cc.u32 %5, %17, %25;\n\taddc.cc.u32 %6, %18, %26;\n\taddc.cc.u32 %7, %19, %27;\n\t"
+        "addc.cc.u32 %8, %28, 0;\n\taddc.cc.u32 %9, %29, 0;\n\taddc.cc.u32 %10, %30, 0;\n\taddc.u32 %11, %31, 0;\n\t"
+        : "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]), "r"(lo[8]), "r"(lo[9]), "r"(lo[10]), "r"(lo[11]),
+          "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]),
+          "r"(hi[8]), "r"(hi[9]), "r"(hi[10]), "r"(hi[11]));
+    (void)c;
+#elif BN_PTX
     uint32_t e[17], o[17];
 #pragma unroll
     for (int i = 0; i < 17; i++) { e[i] = 0; o[i] = 0; }

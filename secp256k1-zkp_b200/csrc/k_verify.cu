@@ -48,6 +48,32 @@ __device__ __forceinline__ void fe_block_inverse(fe& zinv, const fe& z, fe* node
     zinv = nodes[nt + t];
 }
 
+// same tree for scalars mod n (ECDSA's s^-1): every thread calls it (1 for threads without work)
+__device__ __forceinline__ void sc_block_inverse(sc& sinv, const sc& x, sc* nodes) {
+    const uint32_t t = threadIdx.x, nt = blockDim.x;
+    __syncthreads();
+    nodes[nt + t] = x;
+    __syncthreads();
+    for (uint32_t s = nt >> 1; s >= 1; s >>= 1) {
+        if (t < s) { sc r; sc_mul(r, nodes[2 * (s + t)], nodes[2 * (s + t) + 1]); nodes[s + t] = r; }
+        __syncthreads();
+    }
+    if (t == 0) { sc r; sc_inverse(r, nodes[1]); nodes[1] = r; }
+    __syncthreads();
+    for (uint32_t s = 1; s < nt; s <<= 1) {
+        if (t < s) {
+            sc inv = nodes[s + t], l = nodes[2 * (s + t)], r = nodes[2 * (s + t) + 1], a, b;
+            sc_mul(a, inv, r);
+            sc_mul(b, inv, l);
+            nodes[2 * (s + t)] = a;
+            nodes[2 * (s + t) + 1] = b;
+        }
+        __syncthreads();
+    }
+    sinv = nodes[nt + t];
+    __syncthreads();                                        // the region is about to become the tables
+}
+
 __global__ void __launch_bounds__(VERIFY_BLOCK, 3) k_ecmult(uint8_t* __restrict__ out64, const uint8_t* __restrict__ a64,
         const uint8_t* __restrict__ na32, const uint8_t* __restrict__ ng32, size_t n, ecmult_gtable gt) {
     extern __shared__ uint32_t smem[];
@@ -113,14 +139,21 @@ __global__ void __launch_bounds__(VERIFY_BLOCK, 3) k_ecdsa_verify(uint8_t* __res
         const uint8_t* __restrict__ msg32, const uint8_t* __restrict__ pk, int pkfmt, size_t n, ecmult_gtable gt) {
     extern __shared__ uint32_t smem[];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     tab_shared tab = {smem + threadIdx.x, (int)blockDim.x};
-    __align__(16) uint8_t in[64 + 32 + 64];
-    load_bytes_global(in, sig64 + 64 * i, 64);
-    load_bytes_global(in + 64, msg32 + 32 * i, 32);
-    int pklen = pkfmt == PK_OPAQUE64 ? 64 : (pkfmt == PK_XONLY32 ? 32 : 33);
-    load_bytes_global(in + 96, pk + (size_t)pklen * i, pklen);
-    ok[i] = (uint8_t)ecdsa_verify_item(in, sigfmt, in + 64, in + 96, pkfmt, gt, tab);
+    ecdsa_state st;
+    int live = 0;
+    if (i < n) {
+        __align__(16) uint8_t in[64 + 32 + 64];
+        load_bytes_global(in, sig64 + 64 * i, 64);
+        load_bytes_global(in + 64, msg32 + 32 * i, 32);
+        int pklen = pkfmt == PK_OPAQUE64 ? 64 : (pkfmt == PK_XONLY32 ? 32 : 33);
+        load_bytes_global(in + 96, pk + (size_t)pklen * i, pklen);
+        live = ecdsa_verify_parse(st, in, sigfmt, in + 64, in + 96, pkfmt);
+    }
+    sc x, sn;
+    if (live) x = st.s; else sc_set_int(x, 1);
+    sc_block_inverse(sn, x, reinterpret_cast<sc*>(smem));     // one inversion mod n per block
+    if (i < n) ok[i] = (uint8_t)(live && ecdsa_verify_finish(st, sn, gt, tab));
 }
 
 template <class K>

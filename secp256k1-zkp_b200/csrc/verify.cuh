@@ -104,42 +104,53 @@ HD int schnorr_verify_item(const uint8_t* sig64, const uint8_t* msg, uint32_t ms
     return schnorr_verify_finish(R, rx, zi);
 }
 
-template <class Tab>
-HD int ecdsa_verify_item(const uint8_t* sig, int sigfmt, const uint8_t* msghash32, const uint8_t* pk, int pkfmt,
-                         const ecmult_gtable& gt, Tab& tab) {
-    sc r, s, m;
-    ge P;
+// ECDSA verification split around the scalar inversion so that a thread block can share ONE inversion mod n
+// (sc_block_inverse in k_verify.cu): parse -> [s^-1] -> finish.
+struct ecdsa_state { sc r, s, m; ge P; };
+HD int ecdsa_verify_parse(ecdsa_state& st, const uint8_t* sig, int sigfmt, const uint8_t* msghash32, const uint8_t* pk, int pkfmt) {
     if (sigfmt == SIG_COMPACT64) {
         // secp256k1_ecdsa_signature_parse_compact: overflow in r or s => parse failure (secp256k1.c:372-391)
-        if (sc_set_b32(r, sig)) return 0;
-        if (sc_set_b32(s, sig + 32)) return 0;
+        if (sc_set_b32(st.r, sig)) return 0;
+        if (sc_set_b32(st.s, sig + 32)) return 0;
     } else {
-        sc_from_le32(r, sig);
-        sc_from_le32(s, sig + 32);
+        sc_from_le32(st.r, sig);
+        sc_from_le32(st.s, sig + 32);
     }
-    sc_set_b32(m, msghash32);                        // reduced silently (secp256k1.c:507)
-    if (sc_is_high(s)) return 0;                     // (:509)
-    if (!pubkey_load(P, pk, pkfmt)) return 0;
-    if (sc_is_zero(r) || sc_is_zero(s)) return 0;    // (ecdsa_impl.h:205-207)
-    sc sn, u1, u2;
-    sc_inverse(sn, s);
-    sc_mul(u1, sn, m);
-    sc_mul(u2, sn, r);
+    sc_set_b32(st.m, msghash32);                     // reduced silently (secp256k1.c:507)
+    if (sc_is_high(st.s)) return 0;                  // (:509)
+    if (!pubkey_load(st.P, pk, pkfmt)) return 0;
+    if (sc_is_zero(st.r) || sc_is_zero(st.s)) return 0;    // (ecdsa_impl.h:205-207)
+    return 1;
+}
+template <class Tab>
+HD int ecdsa_verify_finish(const ecdsa_state& st, const sc& sn /* s^-1 */, const ecmult_gtable& gt, Tab& tab) {
+    sc u1, u2;
+    sc_mul(u1, sn, st.m);
+    sc_mul(u2, sn, st.r);
     gej Pj, R;
-    gej_set_ge(Pj, P);
+    gej_set_ge(Pj, st.P);
     ecmult(R, Pj, u2, u1, gt, tab);
     if (R.inf) return 0;
     // inversion-free comparison x(R) mod n == r        (ecdsa_impl.h:231-270)
     fe xr;
 #pragma unroll
-    for (int i = 0; i < 8; i++) xr.v[i] = r.v[i];   // r < n < p
+    for (int i = 0; i < 8; i++) xr.v[i] = st.r.v[i];   // r < n < p
     if (gej_eq_x(xr, R)) return 1;
     // second chance only if r + n < p, i.e. r < p - n
     const uint32_t pmn[8] = {0x2FC9BAEEu, 0x402DA172u, 0x50B75FC4u, 0x45512319u, 1u, 0u, 0u, 0u};  // p - n
-    if (bn_gte8(r.v, pmn)) return 0;
+    if (bn_gte8(st.r.v, pmn)) return 0;
     const uint32_t n[8] = SC_N_LIMBS;
-    bn_add8(xr.v, r.v, n);
+    bn_add8(xr.v, st.r.v, n);
     return gej_eq_x(xr, R);
+}
+template <class Tab>
+HD int ecdsa_verify_item(const uint8_t* sig, int sigfmt, const uint8_t* msghash32, const uint8_t* pk, int pkfmt,
+                         const ecmult_gtable& gt, Tab& tab) {
+    ecdsa_state st;
+    if (!ecdsa_verify_parse(st, sig, sigfmt, msghash32, pk, pkfmt)) return 0;
+    sc sn;
+    sc_inverse(sn, st.s);
+    return ecdsa_verify_finish(st, sn, gt, tab);
 }
 
 }  // namespace B200_NS

@@ -480,3 +480,38 @@ def test_bppp_norm_verify_batch_vs_reference(engine, ref):
         got = engine.bppp_norm_verify(P, [P.shape[1]] * n, tr, b"".join(rhos), gxy.raw, g, b"".join(cvs), h, b"".join(cms))
         assert list(got) == exp, (g, h)
         assert sum(exp) >= n // 2
+
+
+# ---- BASELINE.json full-size batches through size-independent properties -----------------------------------
+def test_rangeproof_65536_batch_properties(engine):
+    """config 4 size: 65536 64-bit proofs (reference-signed fixture tiled).  One flipped bit in every 32nd proof, at a
+    position derived from the index: exactly those must be rejected, min/max must be the header values everywhere."""
+    fx = np.load(os.path.join(GOLD, "rangeproof64_fixture.npz"))
+    n = 65536
+    proofs = np.tile(fx["proofs"], (n // 64, 1))
+    commits = np.tile(fx["commits"], (n // 64, 1))
+    bad = np.arange(3, n, 32)
+    pos = (bad * 7919 + 11) % (5126 * 8)
+    pos = np.where(pos < 16, pos + 64, pos)            # keep the header bytes intact so min/max stay comparable
+    proofs[bad, pos // 8] ^= (1 << (pos % 8)).astype(np.uint8)
+    ok, mn, mx = engine.rangeproof_verify(commits, proofs, np.full(n, 5126, dtype=np.uint32), fx["gen64"].tobytes())
+    exp = np.ones(n, dtype=np.uint8); exp[bad] = 0
+    assert np.array_equal(ok, exp)
+    assert (mn == 0).all() and (mx == np.uint64(2**64 - 1)).all()
+    okc, cg = engine.pedersen_commit(np.tile(fx["blinds"], (n // 64, 1)), np.tile(fx["values"], n // 64), fx["gen64"].tobytes())
+    assert okc.all() and np.array_equal(cg, commits)
+
+
+def test_bppp_4096_batch_properties(engine):
+    """config 5 size: 4096 norm-product arguments at 16 G + 8 H generators (reference-made fixture tiled), last byte
+    flipped for i = 5 (mod 16)."""
+    fb = np.load(os.path.join(GOLD, "bppp_fixture.npz"))
+    n = 4096
+    r = n // 64
+    bp, rho, cv, cm = (np.tile(fb[k], (r, 1)) for k in ("proofs", "rho", "c_vec", "commits"))
+    bad = np.arange(5, n, 16)
+    bp[bad, 323] ^= 1
+    tr = engine.bppp_transcripts(cm, rho, fb["gens"], 16, cv, 8, mode="tests")
+    ok = engine.bppp_norm_verify(bp, np.full(n, 324, dtype=np.uint32), tr, rho, fb["gens"], 16, cv, 8, cm)
+    exp = np.ones(n, dtype=np.uint8); exp[bad] = 0
+    assert np.array_equal(ok, exp)
