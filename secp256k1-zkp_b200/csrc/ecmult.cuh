@@ -192,7 +192,7 @@ HD void ecmult(gej& r, const gej& a, const sc& na, const sc& ng, const ecmult_gt
         for (int i = 32; i >= 0; i--) {
             if (!r.inf) {
 #pragma unroll 1
-                for (int k = 0; k < 4; k++) { gej t; gej_double(t, r); r = t; }
+                for (int k = 0; k < 4; k++) { gej t; gej_double_hot(t, r); r = t; }
             }
 #pragma unroll 1
             for (int half = 0; half < 2; half++) {
@@ -205,7 +205,7 @@ HD void ecmult(gej& r, const gej& a, const sc& na, const sc& ng, const ecmult_gt
                 if (half) fe_mul(e.x, e.x, beta);
                 if (neg) fe_neg(e.y, e.y);
                 gej q;
-                gej_add_ge(q, r, e);
+                gej_add_ge_hot(q, r, e);
                 r = q;
             }
         }

@@ -139,6 +139,9 @@ HD void fe_sqr(fe& r, const fe& a) {
     fe_sqr_inl(r, a);
 #endif
 }
+// INL = true: always the inlined body (used inside the outlined group operations, ge.cuh); false: the default policy
+template <bool INL> HD void fe_mul_t(fe& r, const fe& a, const fe& b) { if (INL) fe_mul_inl(r, a, b); else fe_mul(r, a, b); }
+template <bool INL> HD void fe_sqr_t(fe& r, const fe& a) { if (INL) fe_sqr_inl(r, a); else fe_sqr(r, a); }
 
 // r = a + b
 HD void fe_add(fe& r, const fe& a, const fe& b) {
