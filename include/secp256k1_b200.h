@@ -126,6 +126,23 @@ SECP256K1_B200_API int secp256k1_b200_ecmult_multi(secp256k1_b200_engine *e, uns
 SECP256K1_B200_API int secp256k1_b200_ecmult_multi_dev(secp256k1_b200_engine *e, unsigned char *d_out64, const unsigned char *d_g_scalar32,
         const unsigned char *d_scalars32, const unsigned char *d_points64, size_t n, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* ---- surjection proofs and commitment tallies (Confidential Assets) ---------------------------- */
+/* secp256k1_surjectionproof_parse + _verify (include/secp256k1_surjectionproof.h:71, src/modules/surjection/main_impl.h:360) per item.
+ * proofs: SERIALIZED proofs (proofs + i*proof_stride, plen[i] bytes).  Ephemeral input tags of all items are concatenated in
+ * in_tags64 (64-byte secp256k1_generator objects); item i owns tags [tag_offset[i], tag_offset[i+1]) (tag_offset has n+1
+ * entries).  out_tags64: one 64-byte output tag per item. */
+SECP256K1_B200_API int secp256k1_b200_surjectionproof_verify_batch(secp256k1_b200_engine *e, unsigned char *ok, const unsigned char *proofs, size_t proof_stride,
+        const uint32_t *plen, const unsigned char *in_tags64, const uint32_t *tag_offset, const unsigned char *out_tags64, size_t n);
+SECP256K1_B200_API int secp256k1_b200_surjectionproof_verify_batch_dev(secp256k1_b200_engine *e, unsigned char *d_ok, const unsigned char *d_proofs, size_t proof_stride,
+        const uint32_t *d_plen, const unsigned char *d_in_tags64, const uint32_t *d_tag_offset, const unsigned char *d_out_tags64, size_t n, void *stream);
+/* secp256k1_pedersen_verify_tally (include/secp256k1_generator.h, src/modules/generator/main_impl.h:371): item i checks
+ * sum(pos33[pos_offset[i] .. pos_offset[i+1])) - sum(neg33[neg_offset[i] .. neg_offset[i+1])) == infinity over 33-byte serialized
+ * commitments; a commitment that does not parse rejects the item. */
+SECP256K1_B200_API int secp256k1_b200_pedersen_verify_tally_batch(secp256k1_b200_engine *e, unsigned char *ok, const unsigned char *pos33, const uint32_t *pos_offset,
+        const unsigned char *neg33, const uint32_t *neg_offset, size_t n);
+SECP256K1_B200_API int secp256k1_b200_pedersen_verify_tally_batch_dev(secp256k1_b200_engine *e, unsigned char *d_ok, const unsigned char *d_pos33, const uint32_t *d_pos_offset,
+        const unsigned char *d_neg33, const uint32_t *d_neg_offset, size_t n, void *stream);
+
 /* ---- Bulletproofs++ norm-product argument (the only BP++ proof this reference snapshot implements) ------------- */
 /* Replaces static secp256k1_bppp_rangeproof_norm_product_verify (src/modules/bppp/bppp_norm_product_impl.h:425).
  * All proofs of a batch share the geometry (g_len G-generators, h_len H-generators, both powers of two <= 64) and the generator

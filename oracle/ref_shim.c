@@ -411,3 +411,64 @@ REF_EXPORT size_t ref_sizeof(int what) {
     default: return 0;
     }
 }
+
+/* ---- surjection proofs (modules/surjection/main_impl.h:46, :238-357 generate, :360-402 verify) --------------------- */
+/* Makes one proof: n_inputs fixed asset tags A_i = SHA256-derived from tag_seed32 (tag i = seed with byte 0 += i),
+ * output asset = input `real_index`, ephemeral tags = generator_generate_blinded(A_i, blind_i) with blinds derived the
+ * same way.  Writes the n ephemeral input tags (64 bytes each), the ephemeral output tag and the SERIALIZED proof. */
+REF_EXPORT int ref_surjection_make(const secp256k1_context *ctx, unsigned char *proof_ser, size_t *plen, unsigned char *eph_in64,
+        unsigned char *eph_out64, size_t n_inputs, size_t n_to_use, size_t real_index, const unsigned char *seed32) {
+    secp256k1_fixed_asset_tag *fixed = malloc(sizeof(*fixed) * n_inputs), fixed_out;
+    secp256k1_generator *eph = malloc(sizeof(*eph) * n_inputs), eph_out;
+    unsigned char (*blind)[32] = malloc(32 * n_inputs), out_blind[32], tmp[33];
+    secp256k1_surjectionproof proof;
+    secp256k1_sha256 sha;
+    const secp256k1_hash_ctx *hash_ctx = secp256k1_get_hash_context(ctx);
+    size_t i, input_index = 0;
+    int ok = 1;
+    for (i = 0; i < n_inputs; i++) {
+        memcpy(tmp, seed32, 32); tmp[32] = (unsigned char)i;
+        secp256k1_sha256_initialize(&sha); secp256k1_sha256_write(hash_ctx, &sha, (const unsigned char *)"tag", 3); secp256k1_sha256_write(hash_ctx, &sha, tmp, 33);
+        secp256k1_sha256_finalize(hash_ctx, &sha, fixed[i].data);
+        secp256k1_sha256_initialize(&sha); secp256k1_sha256_write(hash_ctx, &sha, (const unsigned char *)"bld", 3); secp256k1_sha256_write(hash_ctx, &sha, tmp, 33);
+        secp256k1_sha256_finalize(hash_ctx, &sha, blind[i]);
+        blind[i][0] &= 0x7F;
+        ok &= secp256k1_generator_generate_blinded(ctx, &eph[i], fixed[i].data, blind[i]);
+        memcpy(eph_in64 + 64 * i, eph[i].data, 64);
+    }
+    fixed_out = fixed[real_index];
+    secp256k1_sha256_initialize(&sha); secp256k1_sha256_write(hash_ctx, &sha, (const unsigned char *)"out", 3); secp256k1_sha256_write(hash_ctx, &sha, seed32, 32);
+    secp256k1_sha256_finalize(hash_ctx, &sha, out_blind);
+    out_blind[0] &= 0x7F;
+    ok &= secp256k1_generator_generate_blinded(ctx, &eph_out, fixed_out.data, out_blind);
+    memcpy(eph_out64, eph_out.data, 64);
+    if (ok) ok = secp256k1_surjectionproof_initialize(ctx, &proof, &input_index, fixed, n_inputs, n_to_use, &fixed_out, 100, seed32) > 0;
+    if (ok) ok = secp256k1_surjectionproof_generate(ctx, &proof, eph, n_inputs, &eph_out, input_index, blind[input_index], out_blind);
+    if (ok) ok = secp256k1_surjectionproof_serialize(ctx, proof_ser, plen, &proof);
+    free(fixed); free(eph); free(blind);
+    return ok;
+}
+/* parse + verify, as a caller of the public API would */
+REF_EXPORT int ref_surjection_verify(const secp256k1_context *ctx, const unsigned char *proof_ser, size_t plen, const unsigned char *eph_in64,
+        size_t n_inputs, const unsigned char *eph_out64) {
+    secp256k1_surjectionproof proof;
+    secp256k1_generator *eph = malloc(sizeof(*eph) * (n_inputs ? n_inputs : 1)), eph_out;
+    size_t i; int ok;
+    for (i = 0; i < n_inputs; i++) memcpy(eph[i].data, eph_in64 + 64 * i, 64);
+    memcpy(eph_out.data, eph_out64, 64);
+    ok = secp256k1_surjectionproof_parse(ctx, &proof, proof_ser, plen);
+    if (ok) ok = secp256k1_surjectionproof_verify(ctx, &proof, eph, n_inputs, &eph_out);
+    free(eph);
+    return ok;
+}
+/* secp256k1_pedersen_verify_tally (modules/generator/main_impl.h:371-396) over serialized commitments; unparsable -> 0 */
+REF_EXPORT int ref_pedersen_verify_tally(const secp256k1_context *ctx, const unsigned char *pos33, size_t pcnt, const unsigned char *neg33, size_t ncnt) {
+    secp256k1_pedersen_commitment *c = malloc(sizeof(*c) * (pcnt + ncnt + 1));
+    const secp256k1_pedersen_commitment **pp = malloc(sizeof(*pp) * (pcnt + ncnt + 1));
+    size_t i; int ok = 1;
+    for (i = 0; i < pcnt && ok; i++) { ok = secp256k1_pedersen_commitment_parse(ctx, &c[i], pos33 + 33 * i); pp[i] = &c[i]; }
+    for (i = 0; i < ncnt && ok; i++) { ok = secp256k1_pedersen_commitment_parse(ctx, &c[pcnt + i], neg33 + 33 * i); pp[pcnt + i] = &c[pcnt + i]; }
+    if (ok) ok = secp256k1_pedersen_verify_tally(ctx, pp, pcnt, pp + pcnt, ncnt);
+    free(c); free(pp);
+    return ok;
+}

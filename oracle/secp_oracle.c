@@ -562,6 +562,56 @@ int orc_rangeproof_verify(uint64_t *min_value, uint64_t *max_value, const unsign
     return memcmp(e0, tmp, 32) == 0;
 }
 
+/* ---- surjection proof verify: modules/surjection/main_impl.h:46-83 (parse), :360-402 (verify), surjection_impl.h:18-36, :66-92 */
+int orc_surjectionproof_verify(const unsigned char *proof, size_t plen, const unsigned char *in_tags64, size_t n_tags, const unsigned char *out_tag64) {
+    size_t n_inputs, bm, n_used = 0, i, j, k; const unsigned char *e0, *sd; unsigned char m[32], tmp[33], ser[33]; sha256_t h; ge outp; sc ens; int overflow;
+    if (plen < 2) return 0;
+    n_inputs = (size_t)proof[0] | ((size_t)proof[1] << 8);
+    if (n_inputs > 256) return 0;
+    bm = (n_inputs + 7) / 8;
+    if (plen < 2 + bm) return 0;
+    if (n_inputs % 8 != 0 && (proof[2 + bm - 1] & (unsigned char)(0xFFu << (n_inputs % 8)))) return 0;
+    for (i = 0; i < bm; i++) for (k = 0; k < 8; k++) n_used += (proof[2 + i] >> k) & 1;
+    if (plen != 2 + bm + 32 * (1 + n_used)) return 0;
+    if (n_used == 0 || n_used > n_inputs || n_inputs != n_tags) return 0;
+    e0 = proof + 2 + bm; sd = e0 + 32;
+    for (j = 0; j < n_used; j++) { sc t; if (sc_set_b32(&t, sd + 32 * j)) return 0; }
+    sha_init(&h);
+    for (i = 0; i <= n_inputs; i++) {
+        const unsigned char *t = i < n_inputs ? in_tags64 + 64 * i : out_tag64;
+        ser[0] = 2 + (t[63] & 1); memcpy(ser + 1, t, 32); sha_write(&h, ser, 33);
+    }
+    sha_final(&h, m);
+    generator_load(&outp, out_tag64);
+    borromean_hash(tmp, m, 32, e0, 32, 0, 0);
+    overflow = sc_set_b32(&ens, tmp);
+    j = 0;
+    for (i = 0; i < n_inputs; i++) {
+        ge inp, rge; gej pub, rgej; sc s;
+        if (!((proof[2 + (i >> 3)] >> (i & 7)) & 1)) continue;
+        generator_load(&inp, in_tags64 + 64 * i); ge_neg(&inp, &inp);
+        gej_set_ge(&pub, &inp); gej_add_ge(&pub, &pub, &outp);
+        sc_set_b32(&s, sd + 32 * j);
+        if (overflow || u256_is_zero(&s) || u256_is_zero(&ens) || pub.inf) return 0;
+        ecmult(&rgej, &pub, &ens, &s);
+        if (rgej.inf) return 0;
+        ge_set_gej(&rge, &rgej); ge_serialize33(tmp, &rge);
+        j++;
+        if (j != n_used) { borromean_hash(tmp, m, 32, tmp, 33, 0, j); overflow = sc_set_b32(&ens, tmp); }
+    }
+    sha_init(&h); sha_write(&h, tmp, 33); sha_write(&h, m, 32); sha_final(&h, ser);
+    return memcmp(ser, e0, 32) == 0;
+}
+/* secp256k1_pedersen_verify_tally (modules/generator/main_impl.h:371-396) over serialized commitments */
+int orc_pedersen_verify_tally(const unsigned char *pos33, size_t pcnt, const unsigned char *neg33, size_t ncnt) {
+    gej acc; size_t i; ge c;
+    gej_set_inf(&acc);
+    for (i = 0; i < ncnt; i++) { if (!commitment_parse(&c, neg33 + 33 * i)) return 0; gej_add_ge(&acc, &acc, &c); }
+    gej_neg(&acc, &acc);
+    for (i = 0; i < pcnt; i++) { if (!commitment_parse(&c, pos33 + 33 * i)) return 0; gej_add_ge(&acc, &acc, &c); }
+    return acc.inf;
+}
+
 /* ---- BP++ norm-product argument verify: modules/bppp/bppp_norm_product_impl.h:425-552; transcript set-up as
  *      modules/bppp/tests_impl.h:273-311; point pair codec bppp_util.h:28-45; challenge bppp_transcript_impl.h:25-33 */
 static size_t ilog2(size_t n) { size_t k = 0; while (n >>= 1) k++; return k; }

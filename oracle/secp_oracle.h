@@ -43,6 +43,8 @@ ORC_API int  orc_rangeproof_verify(uint64_t *min_value, uint64_t *max_value, con
                                    const unsigned char *proof, size_t plen, const unsigned char *extra, size_t extra_len,
                                    const unsigned char *gen64);
 
+ORC_API int  orc_surjectionproof_verify(const unsigned char *proof, size_t plen, const unsigned char *in_tags64, size_t n_tags, const unsigned char *out_tag64);
+ORC_API int  orc_pedersen_verify_tally(const unsigned char *pos33, size_t pcnt, const unsigned char *neg33, size_t ncnt);
 ORC_API int  orc_bppp_norm_verify(const unsigned char *proof, size_t plen, const unsigned char *commit_xy64, const unsigned char *rho32,
                                   const unsigned char *gens_xy64, size_t g_len, const unsigned char *c_vec32, size_t h_len);
 #endif

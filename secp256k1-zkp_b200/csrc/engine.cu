@@ -387,6 +387,70 @@ int secp256k1_b200_ecmult_multi(secp256k1_b200_engine* e, unsigned char* out64, 
     return 1;
 }
 
+/* ---- surjection proofs / Pedersen tallies ------------------------------------------------- */
+int secp256k1_b200_surjectionproof_verify_batch_dev(secp256k1_b200_engine* e, unsigned char* d_ok, const unsigned char* d_proofs, size_t proof_stride,
+                                                    const uint32_t* d_plen, const unsigned char* d_in_tags64, const uint32_t* d_tag_offset,
+                                                    const unsigned char* d_out_tags64, size_t n, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    device_guard guard(e->device);
+    CK(launch_surjection_verify(d_ok, d_proofs, proof_stride, d_plen, d_in_tags64, d_tag_offset, d_out_tags64, n, e->gt(), (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_surjectionproof_verify_batch(secp256k1_b200_engine* e, unsigned char* ok, const unsigned char* proofs, size_t proof_stride,
+                                                const uint32_t* plen, const unsigned char* in_tags64, const uint32_t* tag_offset,
+                                                const unsigned char* out_tags64, size_t n) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (n == 0) return 1;
+    for (size_t i = 0; i < n; i++) {
+        if (plen[i] > proof_stride) { set_error("surjectionproof_verify_batch: plen[i] > proof_stride"); return 0; }
+        if (tag_offset[i + 1] < tag_offset[i]) { set_error("surjectionproof_verify_batch: tag_offset must be non-decreasing"); return 0; }
+    }
+    std::lock_guard<std::mutex> lock(e->mu);
+    device_guard guard(e->device);
+    carver c(e);
+    size_t ntags = tag_offset[n];
+    size_t op = c.add(proof_stride * n), ol = c.add(4 * n), ot = c.add(64 * ntags + 64), oo = c.add(4 * (n + 1)), oout = c.add(64 * n), ook = c.add(n);
+    if (!c.commit()) return 0;
+    CK(cudaMemcpyAsync(c.at(op), proofs, proof_stride * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(ol), plen, 4 * n, cudaMemcpyHostToDevice, e->stream));
+    if (ntags) CK(cudaMemcpyAsync(c.at(ot), in_tags64, 64 * ntags, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(oo), tag_offset, 4 * (n + 1), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(oout), out_tags64, 64 * n, cudaMemcpyHostToDevice, e->stream));
+    if (!secp256k1_b200_surjectionproof_verify_batch_dev(e, c.at(ook), c.at(op), proof_stride, (const uint32_t*)c.at(ol), c.at(ot), (const uint32_t*)c.at(oo),
+                                                         c.at(oout), n, e->stream)) return 0;
+    CK(cudaMemcpyAsync(ok, c.at(ook), n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+int secp256k1_b200_pedersen_verify_tally_batch_dev(secp256k1_b200_engine* e, unsigned char* d_ok, const unsigned char* d_pos33, const uint32_t* d_pos_offset,
+                                                   const unsigned char* d_neg33, const uint32_t* d_neg_offset, size_t n, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    device_guard guard(e->device);
+    CK(launch_pedersen_tally(d_ok, d_pos33, d_pos_offset, d_neg33, d_neg_offset, n, (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_pedersen_verify_tally_batch(secp256k1_b200_engine* e, unsigned char* ok, const unsigned char* pos33, const uint32_t* pos_offset,
+                                               const unsigned char* neg33, const uint32_t* neg_offset, size_t n) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (n == 0) return 1;
+    for (size_t i = 0; i < n; i++)
+        if (pos_offset[i + 1] < pos_offset[i] || neg_offset[i + 1] < neg_offset[i]) { set_error("pedersen_verify_tally_batch: offsets must be non-decreasing"); return 0; }
+    std::lock_guard<std::mutex> lock(e->mu);
+    device_guard guard(e->device);
+    carver c(e);
+    size_t np = pos_offset[n], nn = neg_offset[n];
+    size_t opp = c.add(33 * np + 64), opo = c.add(4 * (n + 1)), onn = c.add(33 * nn + 64), ono = c.add(4 * (n + 1)), ook = c.add(n);
+    if (!c.commit()) return 0;
+    if (np) CK(cudaMemcpyAsync(c.at(opp), pos33, 33 * np, cudaMemcpyHostToDevice, e->stream));
+    if (nn) CK(cudaMemcpyAsync(c.at(onn), neg33, 33 * nn, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(opo), pos_offset, 4 * (n + 1), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(ono), neg_offset, 4 * (n + 1), cudaMemcpyHostToDevice, e->stream));
+    if (!secp256k1_b200_pedersen_verify_tally_batch_dev(e, c.at(ook), c.at(opp), (const uint32_t*)c.at(opo), c.at(onn), (const uint32_t*)c.at(ono), n, e->stream)) return 0;
+    CK(cudaMemcpyAsync(ok, c.at(ook), n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
 /* ---- BP++ norm-product argument ---------------------------------------------------------------------------- */
 static void sha_state_export(unsigned char* out104, const sha256& h) {
     for (int k = 0; k < 8; k++) { out104[4 * k] = (unsigned char)h.s[k]; out104[4 * k + 1] = (unsigned char)(h.s[k] >> 8); out104[4 * k + 2] = (unsigned char)(h.s[k] >> 16); out104[4 * k + 3] = (unsigned char)(h.s[k] >> 24); }

@@ -1,0 +1,43 @@
+// k_surjection.cu -- surjection proof verification / Pedersen tally kernels (one thread per item).
+#include "surjection.cuh"
+#include "launch.h"
+
+namespace b200 {
+
+__global__ void __launch_bounds__(128, 3) k_surjection_verify(uint8_t* __restrict__ ok, const uint8_t* __restrict__ proofs, size_t stride,
+        const uint32_t* __restrict__ plen, const uint8_t* __restrict__ in_tags64, const uint32_t* __restrict__ tag_off,
+        const uint8_t* __restrict__ out_tags64, size_t n, ecmult_gtable gt) {
+    extern __shared__ uint32_t smem[];
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    tab_shared tab = {smem + threadIdx.x, (int)blockDim.x};
+    uint32_t t0 = tag_off[i], t1 = tag_off[i + 1];
+    ok[i] = (uint8_t)surjection_verify_item(proofs + stride * i, plen[i], in_tags64 + 64 * (size_t)t0, t1 - t0, out_tags64 + 64 * i, gt, tab);
+}
+__global__ void __launch_bounds__(128) k_pedersen_tally(uint8_t* __restrict__ ok, const uint8_t* __restrict__ pos33, const uint32_t* __restrict__ pos_off,
+        const uint8_t* __restrict__ neg33, const uint32_t* __restrict__ neg_off, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ok[i] = (uint8_t)pedersen_tally_item(pos33 + 33 * (size_t)pos_off[i], pos_off[i + 1] - pos_off[i], neg33 + 33 * (size_t)neg_off[i], neg_off[i + 1] - neg_off[i]);
+}
+
+cudaError_t launch_surjection_verify(uint8_t* ok, const uint8_t* proofs, size_t stride, const uint32_t* plen, const uint8_t* in_tags64,
+                                     const uint32_t* tag_off, const uint8_t* out_tags64, size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches) {
+    if (n == 0) return cudaSuccess;
+    const int smem = 128 * 8 * 16 * 4;
+    cudaError_t err = cudaFuncSetAttribute(k_surjection_verify, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return err;
+    ecmult_gtable g; g.data = gt.data; g.gw = gt.gw; g.windows = gt.windows;
+    k_surjection_verify<<<(unsigned)((n + 127) / 128), 128, smem, s>>>(ok, proofs, stride, plen, in_tags64, tag_off, out_tags64, n, g);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+cudaError_t launch_pedersen_tally(uint8_t* ok, const uint8_t* pos33, const uint32_t* pos_off, const uint8_t* neg33, const uint32_t* neg_off, size_t n,
+                                  cudaStream_t s, uint64_t* launches) {
+    if (n == 0) return cudaSuccess;
+    k_pedersen_tally<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(ok, pos33, pos_off, neg33, neg_off, n);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace b200

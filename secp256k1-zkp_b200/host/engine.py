@@ -76,6 +76,10 @@ def load_library():
     lib.secp256k1_b200_bppp_transcript_init.restype = None
     lib.secp256k1_b200_bppp_norm_verify_batch.argtypes = [vp, u8p, u8p, sz, vp, u8p, u8p, u8p, sz, u8p, sz, u8p, sz]
     lib.secp256k1_b200_bppp_norm_verify_batch_dev.argtypes = [vp, u8p, u8p, sz, vp, u8p, u8p, u8p, sz, u8p, sz, u8p, sz, vp]
+    lib.secp256k1_b200_surjectionproof_verify_batch.argtypes = [vp, u8p, u8p, sz, vp, u8p, vp, u8p, sz]
+    lib.secp256k1_b200_surjectionproof_verify_batch_dev.argtypes = [vp, u8p, u8p, sz, vp, u8p, vp, u8p, sz, vp]
+    lib.secp256k1_b200_pedersen_verify_tally_batch.argtypes = [vp, u8p, u8p, vp, u8p, vp, sz]
+    lib.secp256k1_b200_pedersen_verify_tally_batch_dev.argtypes = [vp, u8p, u8p, vp, u8p, vp, sz, vp]
     lib.secp256k1_b200_imad_probe_dev.argtypes = [vp, vp, ci, ci, ci, vp]
     lib.secp256k1_b200_ecmult_batch.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
     lib.secp256k1_b200_ecmult_batch_dev.argtypes = [vp, u8p, u8p, u8p, u8p, sz, vp]
@@ -238,6 +242,28 @@ class Engine:
         cm = _u8(commits64, 64 * n, "commits64")
         ok = np.empty(n, dtype=np.uint8)
         self._ck(self._lib.secp256k1_b200_bppp_norm_verify_batch(self._h, _p(ok), _p(pr), stride, _p(pl), _p(tr), _p(rho), _p(g), g_len, _p(cv), h_len, _p(cm), n))
+        return ok
+
+    def surjectionproof_verify(self, proofs, plen, in_tags64, tag_offset, out_tags64):
+        """proofs (n, stride) serialized; in_tags64 flat (ntags*64); tag_offset n+1 entries; out_tags64 (n*64)"""
+        pr = np.ascontiguousarray(proofs, dtype=np.uint8)
+        n, stride = pr.shape
+        pl = np.ascontiguousarray(plen, dtype=np.uint32).reshape(-1)
+        off = np.ascontiguousarray(tag_offset, dtype=np.uint32).reshape(-1)
+        tags = _u8(in_tags64, 64 * int(off[-1]), "in_tags64") if int(off[-1]) else np.zeros(64, dtype=np.uint8)
+        outs = _u8(out_tags64, 64 * n, "out_tags64")
+        ok = np.empty(n, dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_surjectionproof_verify_batch(self._h, _p(ok), _p(pr), stride, _p(pl), _p(tags), _p(off), _p(outs), n))
+        return ok
+
+    def pedersen_verify_tally(self, pos33, pos_offset, neg33, neg_offset):
+        po = np.ascontiguousarray(pos_offset, dtype=np.uint32).reshape(-1)
+        no = np.ascontiguousarray(neg_offset, dtype=np.uint32).reshape(-1)
+        n = po.size - 1
+        p = _u8(pos33, 33 * int(po[-1]), "pos33") if int(po[-1]) else np.zeros(33, dtype=np.uint8)
+        q = _u8(neg33, 33 * int(no[-1]), "neg33") if int(no[-1]) else np.zeros(33, dtype=np.uint8)
+        ok = np.empty(n, dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_pedersen_verify_tally_batch(self._h, _p(ok), _p(p), _p(po), _p(q), _p(no), n))
         return ok
 
     def pedersen_commit(self, blind32, values, gen64):

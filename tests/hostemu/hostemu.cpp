@@ -24,6 +24,7 @@ int emu_fe_is_zero(const uint8_t* a) { fe x; fe_set_b32(x, a); return fe_is_zero
 #include "../../secp256k1-zkp_b200/csrc/rangeproof.cuh"
 #include "../../secp256k1-zkp_b200/csrc/msm.cuh"
 #include "../../secp256k1-zkp_b200/csrc/bppp.cuh"
+#include "../../secp256k1-zkp_b200/csrc/surjection.cuh"
 #include <vector>
 #include <string.h>
 static std::vector<uint32_t> g_tab;
@@ -200,6 +201,10 @@ int emu_bppp_norm_verify(const uint8_t* proof, size_t plen, const uint8_t* commi
     if (!cm.inf) { gej_add_ge(sum, total, cm); total = sum; }
     return total.inf;
 }
+int emu_surjection_verify(const uint8_t* proof, size_t plen, const uint8_t* in_tags64, uint32_t n_tags, const uint8_t* out_tag64) {
+    tab_local tab; return surjection_verify_item(proof, plen, in_tags64, n_tags, out_tag64, g_gt, tab);
+}
+int emu_pedersen_tally(const uint8_t* pos33, uint32_t pcnt, const uint8_t* neg33, uint32_t ncnt) { return pedersen_tally_item(pos33, pcnt, neg33, ncnt); }
 int emu_ecdsa_verify(const uint8_t* sig, int sigfmt, const uint8_t* msg32, const uint8_t* pk, int pkfmt) {
     tab_local tab; return ecdsa_verify_item(sig, sigfmt, msg32, pk, pkfmt, g_gt, tab);
 }

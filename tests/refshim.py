@@ -174,3 +174,17 @@ class PortLib:
         ok = self.lib.orc_rangeproof_verify(ctypes.byref(mn), ctypes.byref(mx), bytes(commit33), proof, ctypes.c_size_t(len(proof)),
                                             bytes(extra) if extra else None, ctypes.c_size_t(len(extra)), bytes(gen64))
         return ok, mn.value, mx.value
+
+
+def surjection_make(ref, n_in, n_use, real, seed32):
+    """(serialized proof, ephemeral input tags n_in*64, ephemeral output tag 64) made by the reference, or None"""
+    proof = ctypes.create_string_buffer(9000)
+    plen = ctypes.c_size_t(9000)
+    tin = ctypes.create_string_buffer(64 * n_in)
+    tout = ctypes.create_string_buffer(64)
+    ok = ref.lib.ref_surjection_make(ref.ctx, proof, ctypes.byref(plen), tin, tout, ctypes.c_size_t(n_in), ctypes.c_size_t(n_use), ctypes.c_size_t(real), bytes(seed32))
+    return (proof.raw[:plen.value], tin.raw, tout.raw) if ok else None
+
+
+def surjection_verify(ref, proof, tin, n_in, tout):
+    return ref.lib.ref_surjection_verify(ref.ctx, bytes(proof), ctypes.c_size_t(len(proof)), bytes(tin), ctypes.c_size_t(n_in), bytes(tout))

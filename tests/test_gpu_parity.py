@@ -515,3 +515,94 @@ def test_bppp_4096_batch_properties(engine):
     ok = engine.bppp_norm_verify(bp, np.full(n, 324, dtype=np.uint32), tr, rho, fb["gens"], 16, cv, 8, cm)
     exp = np.ones(n, dtype=np.uint8); exp[bad] = 0
     assert np.array_equal(ok, exp)
+
+
+def test_rangeproof_header_fuzz_vs_reference(engine, ref):
+    """Every value of each of the first 11 proof bytes (header: flags/exp, mantissa, min_value, first sign byte) and
+    truncated / extended lengths: accept bit AND min/max outputs must match the reference (SURVEY 8b edge semantics:
+    exp > 18, mantissa > 64, max overflow, sign-bit padding, plen < 65, outputs written before the proof fails)."""
+    gen = ref.generator_h()
+    rnd = random.Random(99)
+    for (mv, ex, mb, val) in [(0, 0, 64, 12345678901234567), (13, 1, 8, 13 + 70), (5, 18, 1, 5), (0, 0, 3, 5)]:
+        blind = b32(rnd.getrandbits(256) % N or 1)
+        proofs, plen, commits = ref.rangeproof_make(blind, [val], gen, min_value=mv, exp=ex, min_bits=mb)
+        L = int(plen[0])
+        base = proofs[0, :L].copy()
+        variants, lens = [], []
+        for pos in range(11):
+            for v in range(256):
+                p = base.copy(); p[pos] = v
+                variants.append(p); lens.append(L)
+        for cut in (0, 1, 32, 64, 65, 66, L - 33, L - 32, L - 1):
+            if 0 <= cut <= L:
+                variants.append(base.copy()); lens.append(cut)
+        stride = L + 40
+        batch = np.zeros((len(variants), stride), dtype=np.uint8)
+        for i, p in enumerate(variants):
+            batch[i, :L] = p
+        lens += [L + 1, L + 32]
+        batch = np.concatenate([batch, np.zeros((2, stride), dtype=np.uint8)]); batch[-2, :L] = base; batch[-1, :L] = base
+        cm = np.repeat(commits[:1], batch.shape[0], axis=0)
+        er = ref.rangeproof_verify(cm.tobytes(), batch, lens, gen)
+        eg = engine.rangeproof_verify(cm, batch, lens, gen)
+        for a, b_ in zip(er, eg):
+            assert np.array_equal(a, b_), (mv, ex, mb, np.nonzero(a != b_)[0][:5])
+        assert er[0].sum() >= 1
+
+
+# ---- surjection proofs / tallies (SURVEY 8f rank 1) ----------------------------------------------------------
+def test_surjectionproof_verify_batch_vs_reference(engine, ref):
+    from tests.refshim import surjection_make, surjection_verify
+    rnd = random.Random(77)
+    proofs, tags, offs, outs, exp = [], [], [0], [], []
+    for k in range(160):
+        n_in = rnd.choice([1, 2, 3, 3, 5, 8, 13])
+        n_use = rnd.randint(1, min(3, n_in))
+        made = surjection_make(ref, n_in, n_use, rnd.randrange(n_in), hashlib.sha256(b"gsj%d" % k).digest())
+        assert made is not None
+        pr, tin, tout = made
+        pr = bytearray(pr)
+        if k % 4 == 1:
+            pr[rnd.randrange(len(pr))] ^= 1 << rnd.randrange(8)
+        if k % 9 == 2:
+            tin = tin[64:] + tin[:64]                  # rotate the input tags
+        if k % 11 == 3:
+            tout = tin[:64]
+        n_tags = n_in
+        if k % 13 == 4 and n_in > 1:
+            tin = tin[:-64]; n_tags = n_in - 1         # wrong number of tags
+        exp.append(surjection_verify(ref, bytes(pr), tin, n_tags, tout))
+        proofs.append(bytes(pr)); tags.append(tin); offs.append(offs[-1] + n_tags); outs.append(tout)
+    stride = max(len(p) for p in proofs) + 7
+    P = np.zeros((len(proofs), stride), dtype=np.uint8)
+    for i, p in enumerate(proofs):
+        P[i, :len(p)] = np.frombuffer(p, dtype=np.uint8)
+    got = engine.surjectionproof_verify(P, [len(p) for p in proofs], b"".join(tags), offs, b"".join(outs))
+    assert list(got) == exp
+    assert 60 < sum(exp) < 150
+
+
+def test_pedersen_verify_tally_batch_vs_reference(engine, ref):
+    rnd = random.Random(88)
+    gen = ref.generator_h()
+    pos, neg, po, no, exp = [], [], [0], [0], []
+    for k in range(200):
+        nn, np_ = rnd.randint(1, 4), rnd.randint(1, 4)
+        vals_n = [rnd.getrandbits(40) for _ in range(nn)]
+        bl_n = [rnd.getrandbits(256) % N for _ in range(nn)]
+        vals_p = [rnd.getrandbits(30) for _ in range(np_ - 1)]
+        bl_p = [rnd.getrandbits(256) % N for _ in range(np_ - 1)]
+        last = sum(vals_n) - sum(vals_p)
+        if last < 0:
+            vals_p = [0] * (np_ - 1); last = sum(vals_n)
+        vals_p.append(last); bl_p.append((sum(bl_n) - sum(bl_p)) % N)
+        cp = bytearray(ref.pedersen_commit(b"".join(b32(x) for x in bl_p), vals_p, gen)[1].tobytes())
+        cn = bytearray(ref.pedersen_commit(b"".join(b32(x) for x in bl_n), vals_n, gen)[1].tobytes())
+        if k % 3 == 1:
+            cp[1 + rnd.randrange(32)] ^= 1
+        if k % 7 == 2:
+            cn[0] ^= 1                                   # flip the sign of one commitment
+        exp.append(ref.lib.ref_pedersen_verify_tally(ref.ctx, bytes(cp), ctypes.c_size_t(np_), bytes(cn), ctypes.c_size_t(nn)))
+        pos.append(bytes(cp)); neg.append(bytes(cn)); po.append(po[-1] + np_); no.append(no[-1] + nn)
+    got = engine.pedersen_verify_tally(b"".join(pos), po, b"".join(neg), no)
+    assert list(got) == exp and 80 < sum(exp) < 160

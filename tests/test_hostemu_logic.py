@@ -275,3 +275,43 @@ def test_bppp_norm_verify_logic(emu, ref):
             p2 = bytes(p2)
             e = L.ref_bppp_norm_verify(ref.ctx, p2, ctypes.c_size_t(len(p2)), cm.raw, rho, gs, ctypes.c_size_t(g), cv, ctypes.c_size_t(h))
             assert e == emu.emu_bppp_norm_verify(p2, ctypes.c_size_t(len(p2)), cm.raw, rho, gxy.raw, g, cv, h, 1), (g, h, mut)
+
+
+def test_rangeproof_header_fuzz_logic(emu, ref):
+    gen = ref.generator_h()
+    blind = b32(0x1234567)
+    proofs, plen, commits = ref.rangeproof_make(blind, [13 + 70], gen, min_value=13, exp=1, min_bits=8)
+    L = int(plen[0]); base = bytes(proofs[0][:L]); c = bytes(commits[0])
+    cases = [(bytes(base[:pos]) + bytes([v]) + bytes(base[pos + 1:]), L) for pos in range(11) for v in range(0, 256, 5)]
+    cases += [(base, cut) for cut in (0, 1, 64, 65, 66, L - 32, L - 1)] + [(base + bytes(32), L + 1), (base + bytes(32), L + 32)]
+    for p, ln in cases:
+        e = ref.rangeproof_verify_one(c, p[:ln], gen)
+        assert e == _emu_rp(emu, c, p[:ln], gen), (ln, p[:12].hex())
+
+
+def test_surjection_and_tally_logic(emu, ref):
+    from tests.refshim import surjection_make, surjection_verify
+    rnd = random.Random(12)
+    for (n_in, n_use) in [(1, 1), (3, 1), (3, 3), (5, 2), (8, 3), (17, 3)]:
+        made = surjection_make(ref, n_in, n_use, rnd.randrange(n_in), hashlib.sha256(b"sj%d-%d" % (n_in, n_use)).digest())
+        assert made is not None
+        pr, tin, tout = made
+        for mu in [None] + [rnd.randrange(len(pr)) for _ in range(6)] + [0, 1, 2, len(pr) - 1]:
+            p2 = bytearray(pr)
+            if mu is not None: p2[mu] ^= 1 << rnd.randrange(8)
+            p2 = bytes(p2)
+            e = surjection_verify(ref, p2, tin, n_in, tout)
+            assert e == emu.emu_surjection_verify(p2, ctypes.c_size_t(len(p2)), tin, n_in, tout), (n_in, n_use, mu)
+            if mu is None: assert e == 1
+        for (pp, tt, nn, oo) in [(pr, tin[::-1], n_in, tout), (pr[:-1], tin, n_in, tout), (pr, tin, n_in, tin[:64])]:
+            assert surjection_verify(ref, pp, tt, nn, oo) == emu.emu_surjection_verify(pp, ctypes.c_size_t(len(pp)), tt, nn, oo)
+    gen = ref.generator_h()
+    vals_n, bl_n = [1000, 234], [rnd.getrandbits(256) % N for _ in range(2)]
+    vals_p, bl_p = [1200, 34], [rnd.getrandbits(256) % N]
+    bl_p.append((sum(bl_n) - sum(bl_p)) % N)
+    cp = ref.pedersen_commit(b"".join(b32(x) for x in bl_p), vals_p, gen)[1].tobytes()
+    cn = ref.pedersen_commit(b"".join(b32(x) for x in bl_n), vals_n, gen)[1].tobytes()
+    assert ref.lib.ref_pedersen_verify_tally(ref.ctx, cp, ctypes.c_size_t(2), cn, ctypes.c_size_t(2)) == emu.emu_pedersen_tally(cp, 2, cn, 2) == 1
+    bad = bytearray(cp); bad[40] ^= 1
+    assert ref.lib.ref_pedersen_verify_tally(ref.ctx, bytes(bad), ctypes.c_size_t(2), cn, ctypes.c_size_t(2)) == emu.emu_pedersen_tally(bytes(bad), 2, cn, 2) == 0
+    assert emu.emu_pedersen_tally(cp, 1, cn, 2) == ref.lib.ref_pedersen_verify_tally(ref.ctx, cp, ctypes.c_size_t(1), cn, ctypes.c_size_t(2)) == 0

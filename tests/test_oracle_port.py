@@ -169,3 +169,21 @@ def test_port_bppp_vectors_and_roundtrip(port, ref):
             p2 = bytes(p2)
             e = L.ref_bppp_norm_verify(ref.ctx, p2, ctypes.c_size_t(len(p2)), cm.raw, rho, gs, ctypes.c_size_t(g), cv, ctypes.c_size_t(h))
             assert e == port.lib.orc_bppp_norm_verify(p2, ctypes.c_size_t(len(p2)), cm.raw, rho, gxy.raw, ctypes.c_size_t(g), cv, ctypes.c_size_t(h))
+
+
+def test_port_surjection_and_tally(port, ref):
+    from tests.refshim import surjection_make, surjection_verify
+    rnd = random.Random(21)
+    for (n_in, n_use) in [(1, 1), (4, 2), (9, 3)]:
+        pr, tin, tout = surjection_make(ref, n_in, n_use, rnd.randrange(n_in), hashlib.sha256(b"psj%d" % n_in).digest())
+        for mu in (None, 0, 2, len(pr) // 2, len(pr) - 1):
+            p2 = bytearray(pr)
+            if mu is not None: p2[mu] ^= 4
+            p2 = bytes(p2)
+            assert surjection_verify(ref, p2, tin, n_in, tout) == port.lib.orc_surjectionproof_verify(p2, ctypes.c_size_t(len(p2)), tin, ctypes.c_size_t(n_in), tout)
+    gen = ref.generator_h()
+    bl = [rnd.getrandbits(256) % N for _ in range(3)]
+    cn = ref.pedersen_commit(b32(bl[0]) + b32(bl[1]), [70, 30], gen)[1].tobytes()
+    cp = ref.pedersen_commit(b32(bl[2]) + b32((bl[0] + bl[1] - bl[2]) % N), [55, 45], gen)[1].tobytes()
+    assert port.lib.orc_pedersen_verify_tally(cp, ctypes.c_size_t(2), cn, ctypes.c_size_t(2)) == 1
+    assert port.lib.orc_pedersen_verify_tally(cp, ctypes.c_size_t(2), cn, ctypes.c_size_t(1)) == 0
