@@ -77,6 +77,23 @@ SECP256K1_B200_API int secp256k1_rangeproof_verify(const secp256k1_context *ctx,
 SECP256K1_B200_API int secp256k1_rangeproof_info(const secp256k1_context *ctx, int *exp, int *mantissa, uint64_t *min_value, uint64_t *max_value,
         const unsigned char *proof, size_t plen);
 
+/* include/secp256k1_surjectionproof.h:42-55, :71-95, :113-138, verify (src/modules/surjection/main_impl.h:360);
+ * include/secp256k1_generator.h secp256k1_pedersen_verify_tally (src/modules/generator/main_impl.h:371) */
+typedef struct secp256k1_surjectionproof {
+    size_t n_inputs;
+    unsigned char used_inputs[256 / 8];
+    unsigned char data[32 * (1 + 256)];
+} secp256k1_surjectionproof;
+SECP256K1_B200_API int secp256k1_surjectionproof_parse(const secp256k1_context *ctx, secp256k1_surjectionproof *proof, const unsigned char *input, size_t inputlen);
+SECP256K1_B200_API int secp256k1_surjectionproof_serialize(const secp256k1_context *ctx, unsigned char *output, size_t *outputlen, const secp256k1_surjectionproof *proof);
+SECP256K1_B200_API size_t secp256k1_surjectionproof_n_total_inputs(const secp256k1_context *ctx, const secp256k1_surjectionproof *proof);
+SECP256K1_B200_API size_t secp256k1_surjectionproof_n_used_inputs(const secp256k1_context *ctx, const secp256k1_surjectionproof *proof);
+SECP256K1_B200_API size_t secp256k1_surjectionproof_serialized_size(const secp256k1_context *ctx, const secp256k1_surjectionproof *proof);
+SECP256K1_B200_API int secp256k1_surjectionproof_verify(const secp256k1_context *ctx, const secp256k1_surjectionproof *proof,
+        const secp256k1_generator *ephemeral_input_tags, size_t n_ephemeral_input_tags, const secp256k1_generator *ephemeral_output_tag);
+SECP256K1_B200_API int secp256k1_pedersen_verify_tally(const secp256k1_context *ctx, const secp256k1_pedersen_commitment * const *commits, size_t pcnt,
+        const secp256k1_pedersen_commitment * const *ncommits, size_t ncnt);
+
 /* the process-wide engine behind the calls above (created on first use); exposed so that a host application can
  * pick the device / share the engine with the batch API */
 SECP256K1_B200_API secp256k1_b200_engine *secp256k1_b200_global_engine(void);

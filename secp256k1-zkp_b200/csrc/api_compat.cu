@@ -345,4 +345,83 @@ int secp256k1_rangeproof_verify(const secp256k1_context* ctx, uint64_t* min_valu
     return ok;
 }
 
+// ---- surjection proofs (modules/surjection/main_impl.h) and commitment tallies ------------------------------------------
+static size_t count_bits(const unsigned char* p, size_t n) { size_t c = 0; for (size_t i = 0; i < n; i++) for (int k = 0; k < 8; k++) c += (p[i] >> k) & 1; return c; }
+int secp256k1_surjectionproof_parse(const secp256k1_context* ctx, secp256k1_surjectionproof* proof, const unsigned char* input, size_t inputlen) {
+    ARG_CHECK(proof != NULL);
+    ARG_CHECK(input != NULL);
+    if (inputlen < 2) return 0;
+    size_t n_inputs = ((size_t)input[1] << 8) + input[0];
+    if (n_inputs > 256) return 0;
+    size_t bm = (n_inputs + 7) / 8;
+    if (inputlen < 2 + bm) return 0;
+    if (n_inputs % 8 != 0 && (input[2 + bm - 1] & (unsigned char)(0xFFu << (n_inputs % 8))) != 0) return 0;   // padding bits
+    size_t siglen = 32 * (1 + count_bits(input + 2, bm));
+    if (inputlen != 2 + bm + siglen) return 0;
+    proof->n_inputs = n_inputs;
+    memcpy(proof->used_inputs, input + 2, bm);
+    memcpy(proof->data, input + 2 + bm, siglen);
+    return 1;
+}
+size_t secp256k1_surjectionproof_n_total_inputs(const secp256k1_context* ctx, const secp256k1_surjectionproof* proof) {
+    ARG_CHECK(proof != NULL);
+    return proof->n_inputs;
+}
+size_t secp256k1_surjectionproof_n_used_inputs(const secp256k1_context* ctx, const secp256k1_surjectionproof* proof) {
+    ARG_CHECK(proof != NULL);
+    return count_bits(proof->used_inputs, (proof->n_inputs + 7) / 8);
+}
+size_t secp256k1_surjectionproof_serialized_size(const secp256k1_context* ctx, const secp256k1_surjectionproof* proof) {
+    ARG_CHECK(proof != NULL);
+    return 2 + (proof->n_inputs + 7) / 8 + 32 * (1 + count_bits(proof->used_inputs, (proof->n_inputs + 7) / 8));
+}
+int secp256k1_surjectionproof_serialize(const secp256k1_context* ctx, unsigned char* output, size_t* outputlen, const secp256k1_surjectionproof* proof) {
+    ARG_CHECK(output != NULL);
+    ARG_CHECK(outputlen != NULL);
+    ARG_CHECK(proof != NULL);
+    size_t bm = (proof->n_inputs + 7) / 8, siglen = 32 * (1 + count_bits(proof->used_inputs, bm)), total = 2 + bm + siglen;
+    if (*outputlen < total) return 0;
+    output[0] = (unsigned char)(proof->n_inputs % 0x100);
+    output[1] = (unsigned char)(proof->n_inputs / 0x100);
+    memcpy(output + 2, proof->used_inputs, bm);
+    memcpy(output + 2 + bm, proof->data, siglen);
+    *outputlen = total;
+    return 1;
+}
+int secp256k1_surjectionproof_verify(const secp256k1_context* ctx, const secp256k1_surjectionproof* proof, const secp256k1_generator* ephemeral_input_tags,
+                                     size_t n_ephemeral_input_tags, const secp256k1_generator* ephemeral_output_tag) {
+    ARG_CHECK(proof != NULL);
+    ARG_CHECK(ephemeral_input_tags != NULL);
+    ARG_CHECK(ephemeral_output_tag != NULL);
+    if (proof->n_inputs > 256 || n_ephemeral_input_tags > 256) return 0;
+    unsigned char ser[2 + 32 + 32 * 257];
+    size_t slen = sizeof(ser);
+    if (!secp256k1_surjectionproof_serialize(ctx, ser, &slen, proof)) return 0;
+    ENGINE_OR_FAIL(e);
+    unsigned char ok = 0;
+    uint32_t pl = (uint32_t)slen, off[2] = {0, (uint32_t)n_ephemeral_input_tags};
+    // secp256k1_generator objects are 64 contiguous bytes each: the array is already the flat tag buffer
+    GPU_CALL(secp256k1_b200_surjectionproof_verify_batch(e, &ok, ser, slen, &pl, ephemeral_input_tags[0].data, off, ephemeral_output_tag->data, 1));
+    return ok;
+}
+int secp256k1_pedersen_verify_tally(const secp256k1_context* ctx, const secp256k1_pedersen_commitment* const* commits, size_t pcnt,
+                                    const secp256k1_pedersen_commitment* const* ncommits, size_t ncnt) {
+    ARG_CHECK(!pcnt || (commits != NULL));
+    ARG_CHECK(!ncnt || (ncommits != NULL));
+    for (size_t i = 0; i < pcnt; i++) ARG_CHECK(commits[i] != NULL);
+    for (size_t i = 0; i < ncnt; i++) ARG_CHECK(ncommits[i] != NULL);
+    if (pcnt > 0xFFFFFFu || ncnt > 0xFFFFFFu) return 0;
+    unsigned char* buf = (unsigned char*)malloc(33 * (pcnt + ncnt) + 1);
+    if (!buf) { callback_call(ctx->error_callback, "Out of memory"); return 0; }
+    for (size_t i = 0; i < pcnt; i++) memcpy(buf + 33 * i, commits[i]->data, 33);
+    for (size_t i = 0; i < ncnt; i++) memcpy(buf + 33 * (pcnt + i), ncommits[i]->data, 33);
+    secp256k1_b200_engine* e = engine_or_error(ctx);
+    unsigned char ok = 0;
+    uint32_t po[2] = {0, (uint32_t)pcnt}, no[2] = {0, (uint32_t)ncnt};
+    int rc = e ? secp256k1_b200_pedersen_verify_tally_batch(e, &ok, buf, po, buf + 33 * pcnt, no, 1) : 0;
+    free(buf);
+    if (e && !rc) callback_call(ctx->error_callback, secp256k1_b200_last_error());
+    return rc ? ok : 0;
+}
+
 }  // extern "C"

@@ -187,3 +187,48 @@ def test_illegal_callback_semantics(apis):
         # an all-zero (never parsed) pubkey object is API misuse: callback + 0 (src/secp256k1.c:282)
         assert api.lib.secp256k1_schnorrsig_verify(api.ctx, bytes(64), b"", ctypes.c_size_t(0), bytes(64)) == 0
         assert api.illegal == before + 3
+
+
+def test_surjection_and_tally_compat(apis, ref):
+    """secp256k1_surjectionproof_parse/serialize/verify and secp256k1_pedersen_verify_tally through both libraries"""
+    from tests.refshim import surjection_make
+    mine, theirs = apis
+    rnd = random.Random(5)
+
+    class SJ(ctypes.Structure):
+        _fields_ = [("n_inputs", ctypes.c_size_t), ("used_inputs", ctypes.c_ubyte * 32), ("data", ctypes.c_ubyte * (32 * 257))]
+    for (n_in, n_use) in [(1, 1), (3, 2), (6, 3)]:
+        pr, tin, tout = surjection_make(ref, n_in, n_use, rnd.randrange(n_in), hashlib.sha256(b"csj%d" % n_in).digest())
+        for mu in (None, len(pr) - 3, 1):
+            p2 = bytearray(pr)
+            if mu is not None:
+                p2[mu] ^= 2
+            res = []
+            for api in (mine, theirs):
+                sj = SJ()
+                ok = api.lib.secp256k1_surjectionproof_parse(api.ctx, ctypes.byref(sj), bytes(p2), ctypes.c_size_t(len(p2)))
+                v = api.lib.secp256k1_surjectionproof_verify(api.ctx, ctypes.byref(sj), tin, ctypes.c_size_t(n_in), tout) if ok else -1
+                out = ctypes.create_string_buffer(len(p2) + 8); ln = ctypes.c_size_t(len(p2) + 8)
+                s = api.lib.secp256k1_surjectionproof_serialize(api.ctx, out, ctypes.byref(ln), ctypes.byref(sj)) if ok else 0
+                res.append((ok, v, s, out.raw[:ln.value] if s else b""))
+            assert res[0] == res[1], (n_in, mu)
+            if mu is None:
+                assert res[0][1] == 1 and res[0][3] == bytes(pr)
+    gen = theirs.gen_h
+    bl = [rnd.getrandbits(256) % N for _ in range(3)]
+    cs = []
+    for b, v in ((bl[0], 70), (bl[1], 30), (bl[2], 55), ((bl[0] + bl[1] - bl[2]) % N, 45)):
+        r, c33 = theirs.pedersen_commit(b.to_bytes(32, "big"), v, gen)
+        assert r == 1
+        cs.append(c33)
+    for api in (mine, theirs):
+        objs = []
+        for c33 in cs:
+            r, o = api.commitment_parse(c33)
+            assert r == 1
+            objs.append(ctypes.create_string_buffer(o, 64))
+        arr_t = ctypes.c_void_p * 2
+        neg = arr_t(ctypes.addressof(objs[0]), ctypes.addressof(objs[1]))
+        pos = arr_t(ctypes.addressof(objs[2]), ctypes.addressof(objs[3]))
+        assert api.lib.secp256k1_pedersen_verify_tally(api.ctx, pos, ctypes.c_size_t(2), neg, ctypes.c_size_t(2)) == 1
+        assert api.lib.secp256k1_pedersen_verify_tally(api.ctx, pos, ctypes.c_size_t(1), neg, ctypes.c_size_t(2)) == 0
