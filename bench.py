@@ -272,6 +272,11 @@ def run_extra_workloads(eng, b200, torch, dist, D, dev, stream, rank, world, ima
 
 
 # ------------------------------------------------------------------------------------------------
+# measured once with ncu on the 2^20 launch (profiles/r1e_*): DRAM bytes per launch, IMAD.WIDE.U32(.X) executed per verify
+NCU_DRAM_BYTES_2P20 = 784147712 + 539369728
+IMAD_WIDE_EXECUTED_PER_VERIFY = 136155
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -444,8 +449,13 @@ def main():
                     "api": "secp256k1_b200_schnorrsig_verify_batch (host buffers, pinned)"},
             "gpu_launches": launches,
             "roofline": {"bound": "int32 multiply pipe (IMAD.WIDE.U32); not hbm, not tensor", "achieved": achieved, "peak": imad_peak_tmacs, "unit": "TMAC/s",
-                         "frac": achieved / imad_peak_tmacs, "traffic": None,
-                         "how": "algorithmic 1.81e5 MAC per verify (SURVEY 8d, reference algorithm) x %d verifies / %.3f ms kernel (CUDA events); peak = live IMAD.WIDE.U32 register-saturation probe" % (n, kms),
+                         "frac": achieved / imad_peak_tmacs, "traffic": NCU_DRAM_BYTES_2P20 if args.log2n == 20 else None,
+                         "how": "algorithmic 1.81e5 MAC per verify (SURVEY 8d, reference algorithm) x %d verifies / %.3f ms kernel (CUDA events); peak = live IMAD.WIDE.U32 probe "
+                                "(16 independent accumulators, distinct multiplicands); traffic = dram read+write bytes of one 2^20 launch (ncu, profiles/r1e_ncu_schnorr_2p20_metrics.csv): "
+                                "inputs 135 MB + generator-table misses + local-memory write-back, 50 GB/s, not a bound" % (n, kms),
+                         "executed": {"imad_wide_per_verify": IMAD_WIDE_EXECUTED_PER_VERIFY, "tmac_s": n * IMAD_WIDE_EXECUTED_PER_VERIFY / (kms / 1e3) / 1e12,
+                                      "frac_of_peak": n * IMAD_WIDE_EXECUTED_PER_VERIFY / (kms / 1e3) / 1e12 / imad_peak_tmacs,
+                                      "source": "ncu SourceCounters, IMAD.WIDE.U32(.X) thread instructions per verify (profiles/r1e_ncu_summary.md)"},
                          "kernel": "k_schnorr_verify", "kernel_ms": kms,
                          "hbm": {"achieved_gbs": n * BYTES_PER_VERIFY / (kms / 1e3) / 1e9, "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback",
                                  "frac": n * BYTES_PER_VERIFY / (kms / 1e3) / 1e9 / hbm_peak}},
