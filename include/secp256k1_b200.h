@@ -16,6 +16,7 @@
  *                                       include/secp256k1_extrakeys.h:47 when pkfmt = XONLY32]
  *   secp256k1_b200_ecdsa_verify_batch   secp256k1_ecdsa_verify (include/secp256k1.h:622, src/secp256k1.c:498)
  *                                       [+ secp256k1_ec_pubkey_parse / secp256k1_ecdsa_signature_parse_compact]
+ *   secp256k1_b200_ecdsa_recover_batch  secp256k1_ecdsa_recover (include/secp256k1_recovery.h:105, src/modules/recovery/main_impl.h:137)
  *   secp256k1_b200_pedersen_commit_batch     secp256k1_pedersen_commit (include/secp256k1_generator.h:114,
  *                                       src/modules/generator/main_impl.h:309) + _commitment_serialize (:281)
  *   secp256k1_b200_rangeproof_verify_batch   secp256k1_rangeproof_verify (include/secp256k1_rangeproof.h:70,
@@ -114,6 +115,14 @@ SECP256K1_B200_API int secp256k1_b200_ecdsa_verify_batch(secp256k1_b200_engine *
         const unsigned char *sig64, int sigfmt, const unsigned char *msghash32, const unsigned char *pk, int pkfmt, size_t n);
 SECP256K1_B200_API int secp256k1_b200_ecdsa_verify_batch_dev(secp256k1_b200_engine *e, unsigned char *d_ok,
         const unsigned char *d_sig64, int sigfmt, const unsigned char *d_msghash32, const unsigned char *d_pk, int pkfmt, size_t n, void *stream);
+
+/* Public-key recovery: secp256k1_ecdsa_recoverable_signature_parse_compact + secp256k1_ecdsa_recover
+ * (include/secp256k1_recovery.h:40,105; src/modules/recovery/main_impl.h:38,87,137).  sig64 = r||s big-endian, recid[i] in 0..3
+ * (anything else: ok = 0).  pubkey64[i] = affine x||y big-endian, zeros when ok[i] == 0. */
+SECP256K1_B200_API int secp256k1_b200_ecdsa_recover_batch(secp256k1_b200_engine *e, unsigned char *ok, unsigned char *pubkey64,
+        const unsigned char *sig64, const unsigned char *recid, const unsigned char *msghash32, size_t n);
+SECP256K1_B200_API int secp256k1_b200_ecdsa_recover_batch_dev(secp256k1_b200_engine *e, unsigned char *d_ok, unsigned char *d_pubkey64,
+        const unsigned char *d_sig64, const unsigned char *d_recid, const unsigned char *d_msghash32, size_t n, void *stream);
 
 /* ---- multi-scalar multiplication: out = g_scalar*G + sum_i scalars[i]*points[i] ----------------------------- */
 /* Pippenger bucket method on the GPU (replaces static secp256k1_ecmult_multi_var, src/ecmult.h:62; the callback

@@ -77,6 +77,17 @@ SECP256K1_B200_API int secp256k1_rangeproof_verify(const secp256k1_context *ctx,
 SECP256K1_B200_API int secp256k1_rangeproof_info(const secp256k1_context *ctx, int *exp, int *mantissa, uint64_t *min_value, uint64_t *max_value,
         const unsigned char *proof, size_t plen);
 
+/* include/secp256k1_recovery.h:27-29 (opaque 65 bytes), :40 parse_compact, :52 convert, :65 serialize_compact, :105 recover */
+typedef struct secp256k1_ecdsa_recoverable_signature { unsigned char data[65]; } secp256k1_ecdsa_recoverable_signature;
+SECP256K1_B200_API int secp256k1_ecdsa_recoverable_signature_parse_compact(const secp256k1_context *ctx, secp256k1_ecdsa_recoverable_signature *sig,
+        const unsigned char *input64, int recid);
+SECP256K1_B200_API int secp256k1_ecdsa_recoverable_signature_convert(const secp256k1_context *ctx, secp256k1_ecdsa_signature *sig,
+        const secp256k1_ecdsa_recoverable_signature *sigin);
+SECP256K1_B200_API int secp256k1_ecdsa_recoverable_signature_serialize_compact(const secp256k1_context *ctx, unsigned char *output64, int *recid,
+        const secp256k1_ecdsa_recoverable_signature *sig);
+SECP256K1_B200_API int secp256k1_ecdsa_recover(const secp256k1_context *ctx, secp256k1_pubkey *pubkey, const secp256k1_ecdsa_recoverable_signature *sig,
+        const unsigned char *msghash32);
+
 /* include/secp256k1_surjectionproof.h:42-55, :71-95, :113-138, verify (src/modules/surjection/main_impl.h:360);
  * include/secp256k1_generator.h secp256k1_pedersen_verify_tally (src/modules/generator/main_impl.h:371) */
 typedef struct secp256k1_surjectionproof {

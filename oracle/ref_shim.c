@@ -278,6 +278,52 @@ REF_EXPORT int ref_ecdsa_make_batch(const secp256k1_context *ctx, unsigned char 
     }
     return 1;
 }
+/* recoverable signatures (modules/recovery/main_impl.h:123-159): sign -> compact sig + recid; recover -> uncompressed key x||y */
+REF_EXPORT int ref_ecdsa_sign_recoverable_batch(const secp256k1_context *ctx, unsigned char *sig64, unsigned char *recid,
+        const unsigned char *sk32, const unsigned char *msg32, size_t n) {
+    size_t i;
+    for (i = 0; i < n; i++) {
+        secp256k1_ecdsa_recoverable_signature sig; int rid;
+        if (!secp256k1_ecdsa_sign_recoverable(ctx, &sig, msg32 + 32 * i, sk32 + 32 * i, NULL, NULL)) return 0;
+        secp256k1_ecdsa_recoverable_signature_serialize_compact(ctx, sig64 + 64 * i, &rid, &sig);
+        recid[i] = (unsigned char)rid;
+    }
+    return 1;
+}
+REF_EXPORT void ref_ecdsa_recover_batch(const secp256k1_context *ctx, unsigned char *ok, unsigned char *pubkey64,
+        const unsigned char *sig64, const unsigned char *recid, const unsigned char *msg32, size_t n) {
+    size_t i;
+    for (i = 0; i < n; i++) {
+        secp256k1_ecdsa_recoverable_signature sig; secp256k1_pubkey pk; unsigned char ser[65]; size_t l = 65;
+        ok[i] = 0; memset(pubkey64 + 64 * i, 0, 64);
+        if (recid[i] > 3) continue;   /* the API treats this as an illegal argument (ARG_CHECK) */
+        if (!secp256k1_ecdsa_recoverable_signature_parse_compact(ctx, &sig, sig64 + 64 * i, recid[i])) continue;
+        if (!secp256k1_ecdsa_recover(ctx, &pk, &sig, msg32 + 32 * i)) continue;
+        secp256k1_ec_pubkey_serialize(ctx, ser, &l, &pk, SECP256K1_EC_UNCOMPRESSED);
+        memcpy(pubkey64 + 64 * i, ser + 1, 64);
+        ok[i] = 1;
+    }
+}
+/* half-aggregation (modules/schnorrsig_halfagg/main_impl.h:99,:103): pubkeys as 32-byte x-only serializations */
+REF_EXPORT int ref_schnorrsig_aggregate(const secp256k1_context *ctx, unsigned char *aggsig, size_t *aggsig_len,
+        const unsigned char *pk32, const unsigned char *msgs32, const unsigned char *sigs64, size_t n) {
+    secp256k1_xonly_pubkey *pks = (secp256k1_xonly_pubkey*)malloc((n ? n : 1) * sizeof(*pks));
+    size_t i; int r = 1;
+    for (i = 0; i < n && r; i++) r = secp256k1_xonly_pubkey_parse(ctx, &pks[i], pk32 + 32 * i);
+    if (r) r = secp256k1_schnorrsig_aggregate(ctx, aggsig, aggsig_len, pks, msgs32, sigs64, n);
+    free(pks);
+    return r;
+}
+REF_EXPORT int ref_schnorrsig_aggverify(const secp256k1_context *ctx, const unsigned char *pk32, const unsigned char *msgs32, size_t n,
+        const unsigned char *aggsig, size_t aggsig_len) {
+    secp256k1_xonly_pubkey *pks = (secp256k1_xonly_pubkey*)malloc((n ? n : 1) * sizeof(*pks));
+    size_t i; int r = 1;
+    for (i = 0; i < n && r; i++) r = secp256k1_xonly_pubkey_parse(ctx, &pks[i], pk32 + 32 * i);
+    if (r) r = secp256k1_schnorrsig_aggverify(ctx, pks, msgs32, n, aggsig, aggsig_len);
+    else r = -1;   /* a key that does not parse never reaches aggverify in the reference API */
+    free(pks);
+    return r;
+}
 /* pedersen commit loop: out33 = serialized commitment (generator/main_impl.h:309,:281) */
 REF_EXPORT void ref_pedersen_commit_batch(const secp256k1_context *ctx, unsigned char *ok, unsigned char *out33,
         const unsigned char *blind32, const uint64_t *value, const secp256k1_generator *gen, size_t n) {

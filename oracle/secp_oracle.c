@@ -426,6 +426,30 @@ int orc_ecdsa_verify(const unsigned char *sig64, const unsigned char *msghash32,
     return u256_cmp(&xr, &r) == 0;
 }
 
+/* ---- ECDSA public-key recovery: modules/recovery/main_impl.h:38-59 (parse_compact), :87-121 (sig_recover), :137-159 ---- */
+int orc_ecdsa_recover(unsigned char *pubkey64, const unsigned char *sig64, int recid, const unsigned char *msghash32) {
+    sc r, s, m, rn, u1, u2; fe fx; ge X, Q; gej Xj, Qj;
+    memset(pubkey64, 0, 64);
+    if (recid < 0 || recid > 3) return 0;
+    if (sc_set_b32(&r, sig64) || sc_set_b32(&s, sig64 + 32)) return 0;
+    sc_set_b32(&m, msghash32);
+    if (u256_is_zero(&r) || u256_is_zero(&s)) return 0;
+    fx = r;
+    if (recid & 2) {
+        u256 pmn; u256_sub(&pmn, &FE_P, &SC_N);
+        if (u256_cmp(&fx, &pmn) >= 0) return 0;
+        u256_add(&fx, &fx, &SC_N);
+    }
+    if (!ge_set_xo(&X, &fx, recid & 1)) return 0;
+    sc_inv(&rn, &r); sc_mul(&u1, &rn, &m); sc_neg(&u1, &u1); sc_mul(&u2, &rn, &s);
+    gej_set_ge(&Xj, &X);
+    ecmult(&Qj, &Xj, &u2, &u1);
+    if (Qj.inf) return 0;
+    ge_set_gej(&Q, &Qj);
+    u256_to_be(pubkey64, &Q.x); u256_to_be(pubkey64 + 32, &Q.y);
+    return 1;
+}
+
 /* ---- generator / Pedersen: modules/generator/main_impl.h:40-49, :67-92, :266-335, pedersen_impl.h:20-49 --- */
 static void generator_load(ge *g, const unsigned char *gen64) { fe_set_b32_mod(&g->x, gen64); fe_set_b32_mod(&g->y, gen64 + 32); g->inf = 0; }
 int orc_generator_parse(unsigned char *gen64, const unsigned char *in33) {

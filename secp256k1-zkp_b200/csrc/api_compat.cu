@@ -218,6 +218,57 @@ int secp256k1_ecdsa_verify(const secp256k1_context* ctx, const secp256k1_ecdsa_s
     return ok;
 }
 
+// ---- ECDSA public-key recovery (modules/recovery/main_impl.h:38-85, :137-159) ---------------------------------------------
+int secp256k1_ecdsa_recoverable_signature_parse_compact(const secp256k1_context* ctx, secp256k1_ecdsa_recoverable_signature* sig,
+                                                        const unsigned char* input64, int recid) {
+    ARG_CHECK(sig != NULL);
+    ARG_CHECK(input64 != NULL);
+    ARG_CHECK(recid >= 0 && recid <= 3);
+    int ret = 1;
+    for (int half = 0; half < 2; half++)
+        if (memcmp(input64 + 32 * half, ORDER_BE, 32) >= 0) ret = 0;
+    if (ret) {
+        for (int half = 0; half < 2; half++)
+            for (int i = 0; i < 32; i++) sig->data[32 * half + i] = input64[32 * half + 31 - i];
+        sig->data[64] = (unsigned char)recid;
+    } else {
+        memset(sig, 0, sizeof(*sig));
+    }
+    return ret;
+}
+int secp256k1_ecdsa_recoverable_signature_serialize_compact(const secp256k1_context* ctx, unsigned char* output64, int* recid,
+                                                            const secp256k1_ecdsa_recoverable_signature* sig) {
+    ARG_CHECK(output64 != NULL);
+    ARG_CHECK(sig != NULL);
+    ARG_CHECK(recid != NULL);
+    for (int half = 0; half < 2; half++)
+        for (int i = 0; i < 32; i++) output64[32 * half + i] = sig->data[32 * half + 31 - i];
+    *recid = sig->data[64];
+    return 1;
+}
+int secp256k1_ecdsa_recoverable_signature_convert(const secp256k1_context* ctx, secp256k1_ecdsa_signature* sig, const secp256k1_ecdsa_recoverable_signature* sigin) {
+    ARG_CHECK(sig != NULL);
+    ARG_CHECK(sigin != NULL);
+    memcpy(sig->data, sigin->data, 64);
+    return 1;
+}
+int secp256k1_ecdsa_recover(const secp256k1_context* ctx, secp256k1_pubkey* pubkey, const secp256k1_ecdsa_recoverable_signature* sig, const unsigned char* msghash32) {
+    ARG_CHECK(msghash32 != NULL);
+    ARG_CHECK(sig != NULL);
+    ARG_CHECK(pubkey != NULL);
+    unsigned char sig64[64], recid, ok = 0, xy[64];
+    for (int half = 0; half < 2; half++)
+        for (int i = 0; i < 32; i++) sig64[32 * half + i] = sig->data[32 * half + 31 - i];
+    recid = sig->data[64];
+    ARG_CHECK(recid <= 3);   // signature_load: VERIFY-level in the reference; an out-of-range byte can only come from a corrupted object
+    memset(pubkey, 0, sizeof(*pubkey));
+    ENGINE_OR_FAIL(e);
+    GPU_CALL(secp256k1_b200_ecdsa_recover_batch(e, &ok, xy, sig64, &recid, msghash32, 1));
+    if (!ok) return 0;
+    for (int i = 0; i < 32; i++) { pubkey->data[i] = xy[31 - i]; pubkey->data[32 + i] = xy[63 - i]; }   // pubkey_save: x,y little-endian
+    return 1;
+}
+
 // ---- BIP-340 (modules/schnorrsig/main_impl.h:215-261) -------------------------------------------------------------
 int secp256k1_schnorrsig_verify(const secp256k1_context* ctx, const unsigned char* sig64, const unsigned char* msg, size_t msglen, const secp256k1_xonly_pubkey* pubkey) {
     ARG_CHECK(sig64 != NULL);

@@ -356,6 +356,32 @@ int secp256k1_b200_ecdsa_verify_batch(secp256k1_b200_engine* e, unsigned char* o
     return 1;
 }
 
+int secp256k1_b200_ecdsa_recover_batch_dev(secp256k1_b200_engine* e, unsigned char* d_ok, unsigned char* d_pubkey64, const unsigned char* d_sig64,
+                                           const unsigned char* d_recid, const unsigned char* d_msghash32, size_t n, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    device_guard guard(e->device);
+    CK(launch_ecdsa_recover(d_ok, d_pubkey64, d_sig64, d_recid, d_msghash32, n, e->gt(), (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_ecdsa_recover_batch(secp256k1_b200_engine* e, unsigned char* ok, unsigned char* pubkey64, const unsigned char* sig64,
+                                       const unsigned char* recid, const unsigned char* msghash32, size_t n) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (n == 0) return 1;
+    std::lock_guard<std::mutex> lock(e->mu);
+    device_guard guard(e->device);
+    carver c(e);
+    size_t os = c.add(64 * n), om = c.add(32 * n), orr = c.add(n), oo = c.add(n), op = c.add(64 * n);
+    if (!c.commit()) return 0;
+    CK(cudaMemcpyAsync(c.at(os), sig64, 64 * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(om), msghash32, 32 * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(orr), recid, n, cudaMemcpyHostToDevice, e->stream));
+    if (!secp256k1_b200_ecdsa_recover_batch_dev(e, c.at(oo), c.at(op), c.at(os), c.at(orr), c.at(om), n, e->stream)) return 0;
+    CK(cudaMemcpyAsync(ok, c.at(oo), n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(pubkey64, c.at(op), 64 * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
 /* ---- multi-scalar multiplication (Pippenger) ------------------------------------------------------------ */
 size_t secp256k1_b200_ecmult_multi_workspace_bytes(size_t n) { return msm_workspace_bytes(n); }
 int secp256k1_b200_ecmult_multi_dev(secp256k1_b200_engine* e, unsigned char* d_out64, const unsigned char* d_g_scalar32,

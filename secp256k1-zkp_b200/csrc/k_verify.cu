@@ -156,6 +156,44 @@ __global__ void __launch_bounds__(VERIFY_BLOCK, 3) k_ecdsa_verify(uint8_t* __res
     if (i < n) ok[i] = (uint8_t)(live && ecdsa_verify_finish(st, sn, gt, tab));
 }
 
+// out64[i] = recovered public key (affine x||y big-endian; zeros when ok[i] == 0)
+__global__ void __launch_bounds__(VERIFY_BLOCK, 3) k_ecdsa_recover(uint8_t* __restrict__ ok, uint8_t* __restrict__ out64, const uint8_t* __restrict__ sig64,
+        const uint8_t* __restrict__ recid, const uint8_t* __restrict__ msg32, size_t n, ecmult_gtable gt) {
+    extern __shared__ uint32_t smem[];
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    tab_shared tab = {smem + threadIdx.x, (int)blockDim.x};
+    ecdsa_recover_state st;
+    int live = 0;
+    if (i < n) {
+        __align__(16) uint8_t in[64 + 32];
+        load_bytes_global(in, sig64 + 64 * i, 64);
+        load_bytes_global(in + 64, msg32 + 32 * i, 32);
+        int rid = recid[i];
+        live = rid <= 3 && ecdsa_recover_parse(st, in, rid, in + 64);
+    }
+    sc x, rn;
+    if (live) x = st.r; else sc_set_int(x, 1);
+    sc_block_inverse(rn, x, reinterpret_cast<sc*>(smem));     // one inversion mod n per block
+    gej Q; gej_set_infinity(Q);
+    if (live) live = ecdsa_recover_finish(Q, st, rn, gt, tab);
+    fe z, zinv;
+    if (live) z = Q.z; else fe_set_int(z, 1);
+    fe_block_inverse(zinv, z, reinterpret_cast<fe*>(smem));   // one field inversion per block
+    if (i >= n) return;
+    __align__(16) uint8_t o[64];
+    if (!live) {
+        for (int k = 0; k < 64; k++) o[k] = 0;
+    } else {
+        ge Qa; ge_set_gej_zinv(Qa, Q, zinv);
+        fe_get_b32(o, Qa.x); fe_get_b32(o + 32, Qa.y);
+    }
+    ok[i] = (uint8_t)live;
+    uint4* q = reinterpret_cast<uint4*>(out64 + 64 * i);
+    const uint4* s4 = reinterpret_cast<const uint4*>(o);
+    if ((reinterpret_cast<uintptr_t>(out64) & 15) == 0) { q[0] = s4[0]; q[1] = s4[1]; q[2] = s4[2]; q[3] = s4[3]; }
+    else for (int k = 0; k < 64; k++) out64[64 * i + k] = o[k];
+}
+
 template <class K>
 static cudaError_t set_smem(K kernel) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VERIFY_SMEM);
@@ -188,6 +226,16 @@ cudaError_t launch_ecdsa_verify(uint8_t* ok, const uint8_t* sig64, int sigfmt, c
     cudaError_t err = set_smem(k_ecdsa_verify);
     if (err != cudaSuccess) return err;
     k_ecdsa_verify<<<(unsigned)((n + VERIFY_BLOCK - 1) / VERIFY_BLOCK), VERIFY_BLOCK, VERIFY_SMEM, s>>>(ok, sig64, sigfmt, msg32, pk, pkfmt, n, to_gt(gt));
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ecdsa_recover(uint8_t* ok, uint8_t* out64, const uint8_t* sig64, const uint8_t* recid, const uint8_t* msg32, size_t n,
+                                 const gtable_dev& gt, cudaStream_t s, uint64_t* launches) {
+    if (n == 0) return cudaSuccess;
+    cudaError_t err = set_smem(k_ecdsa_recover);
+    if (err != cudaSuccess) return err;
+    k_ecdsa_recover<<<(unsigned)((n + VERIFY_BLOCK - 1) / VERIFY_BLOCK), VERIFY_BLOCK, VERIFY_SMEM, s>>>(ok, out64, sig64, recid, msg32, n, to_gt(gt));
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

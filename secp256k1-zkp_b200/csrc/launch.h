@@ -25,6 +25,8 @@ cudaError_t launch_ecmult(uint8_t* out64, const uint8_t* a64, const uint8_t* na3
                           const gtable_dev& gt, cudaStream_t s, uint64_t* launches);
 cudaError_t launch_schnorr_verify(uint8_t* ok, const uint8_t* sig64, const uint8_t* msg, uint32_t msglen, const uint8_t* pk, int pkfmt,
                                   size_t n, const bip340_midstate_h& mid, const gtable_dev& gt, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_ecdsa_recover(uint8_t* ok, uint8_t* out64, const uint8_t* sig64, const uint8_t* recid, const uint8_t* msg32, size_t n,
+                                 const gtable_dev& gt, cudaStream_t s, uint64_t* launches);
 cudaError_t launch_ecdsa_verify(uint8_t* ok, const uint8_t* sig64, int sigfmt, const uint8_t* msg32, const uint8_t* pk, int pkfmt,
                                 size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches);
 

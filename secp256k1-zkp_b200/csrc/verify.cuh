@@ -143,6 +143,50 @@ HD int ecdsa_verify_finish(const ecdsa_state& st, const sc& sn /* s^-1 */, const
     bn_add8(xr.v, st.r.v, n);
     return gej_eq_x(xr, R);
 }
+// ECDSA public-key recovery (secp256k1_ecdsa_sig_recover, src/modules/recovery/main_impl.h:87-121), split around r^-1 mod n like
+// the verification above.  recid bit 0 = parity of R.y, bit 1 = "R.x is r + n".
+struct ecdsa_recover_state { sc r, s, m; ge X; };
+HD int ecdsa_recover_parse(ecdsa_recover_state& st, const uint8_t* sig64, int recid, const uint8_t* msghash32) {
+    // secp256k1_ecdsa_recoverable_signature_parse_compact: overflow in r or s => parse failure (:38-59); recid is range-checked by the caller
+    if (sc_set_b32(st.r, sig64)) return 0;
+    if (sc_set_b32(st.s, sig64 + 32)) return 0;
+    sc_set_b32(st.m, msghash32);
+    if (sc_is_zero(st.r) || sc_is_zero(st.s)) return 0;                    // (:96-98)
+    fe fx;
+#pragma unroll
+    for (int i = 0; i < 8; i++) fx.v[i] = st.r.v[i];                       // r < n < p
+    if (recid & 2) {
+        const uint32_t pmn[8] = {0x2FC9BAEEu, 0x402DA172u, 0x50B75FC4u, 0x45512319u, 1u, 0u, 0u, 0u};  // p - n
+        if (bn_gte8(st.r.v, pmn)) return 0;                                // (:104-107)
+        const uint32_t n[8] = SC_N_LIMBS;
+        bn_add8(fx.v, st.r.v, n);
+    }
+    return ge_set_xo(st.X, fx, recid & 1);                                 // (:110-112)
+}
+template <class Tab>
+HD int ecdsa_recover_finish(gej& Q, const ecdsa_recover_state& st, const sc& rn /* r^-1 */, const ecmult_gtable& gt, Tab& tab) {
+    sc u1, u2;
+    sc_mul(u1, rn, st.m);
+    sc_negate(u1, u1);
+    sc_mul(u2, rn, st.s);
+    gej Xj;
+    gej_set_ge(Xj, st.X);
+    ecmult(Q, Xj, u2, u1, gt, tab);                                        // Q = u2*X + u1*G   (:117)
+    return !Q.inf;
+}
+template <class Tab>
+HD int ecdsa_recover_item(uint8_t* out64, const uint8_t* sig64, int recid, const uint8_t* msghash32, const ecmult_gtable& gt, Tab& tab) {
+    ecdsa_recover_state st;
+    gej Q;
+    int ok = ecdsa_recover_parse(st, sig64, recid, msghash32);
+    if (ok) { sc rn; sc_inverse(rn, st.r); ok = ecdsa_recover_finish(Q, st, rn, gt, tab); }
+    if (!ok) { for (int k = 0; k < 64; k++) out64[k] = 0; return 0; }
+    fe zi; fe_inv(zi, Q.z);
+    ge Qa; ge_set_gej_zinv(Qa, Q, zi);
+    fe_get_b32(out64, Qa.x); fe_get_b32(out64 + 32, Qa.y);
+    return 1;
+}
+
 template <class Tab>
 HD int ecdsa_verify_item(const uint8_t* sig, int sigfmt, const uint8_t* msghash32, const uint8_t* pk, int pkfmt,
                          const ecmult_gtable& gt, Tab& tab) {

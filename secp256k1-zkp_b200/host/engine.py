@@ -87,6 +87,8 @@ def load_library():
     lib.secp256k1_b200_schnorrsig_verify_batch_dev.argtypes = [vp, u8p, u8p, u8p, sz, u8p, ci, sz, vp]
     lib.secp256k1_b200_ecdsa_verify_batch.argtypes = [vp, u8p, u8p, ci, u8p, u8p, ci, sz]
     lib.secp256k1_b200_ecdsa_verify_batch_dev.argtypes = [vp, u8p, u8p, ci, u8p, u8p, ci, sz, vp]
+    lib.secp256k1_b200_ecdsa_recover_batch.argtypes = [vp, u8p, u8p, u8p, u8p, u8p, sz]
+    lib.secp256k1_b200_ecdsa_recover_batch_dev.argtypes = [vp, u8p, u8p, u8p, u8p, u8p, sz, vp]
     _LIB = lib
     return lib
 
@@ -188,6 +190,17 @@ class Engine:
         ok = np.empty(n, dtype=np.uint8)
         self._ck(self._lib.secp256k1_b200_ecdsa_verify_batch(self._h, _p(ok), _p(sig), sigfmt, _p(m), _p(p), pkfmt, n))
         return ok
+
+    def ecdsa_recover(self, sig64, recid, msghash32):
+        """(ok[n], pubkey64[n,64]) -- secp256k1_ecdsa_recover on compact signatures + recovery ids"""
+        sig = _u8(sig64, len(sig64) if not hasattr(sig64, "size") else sig64.size, "sig64")
+        n = sig.size // 64
+        rid = _u8(recid, n, "recid")
+        m = _u8(msghash32, 32 * n, "msghash32")
+        ok = np.empty(n, dtype=np.uint8)
+        out = np.empty((n, 64), dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_ecdsa_recover_batch(self._h, _p(ok), _p(out), _p(sig), _p(rid), _p(m), n))
+        return ok, out
 
     def ecmult_multi(self, scalars32, points64, g_scalar32=None):
         """sum_i scalars[i]*points[i] (+ g_scalar*G); returns 64 bytes x||y (zeros = infinity)"""
@@ -341,6 +354,9 @@ class Engine:
 
     def schnorrsig_verify_dev(self, d_ok, d_sig64, d_msg, msglen, d_pk, pkfmt, n, stream=0):
         self._ck(self._lib.secp256k1_b200_schnorrsig_verify_batch_dev(self._h, d_ok, d_sig64, d_msg, msglen, d_pk, pkfmt, n, stream))
+
+    def ecdsa_recover_dev(self, d_ok, d_pubkey64, d_sig64, d_recid, d_msg32, n, stream=0):
+        self._ck(self._lib.secp256k1_b200_ecdsa_recover_batch_dev(self._h, d_ok, d_pubkey64, d_sig64, d_recid, d_msg32, n, stream))
 
     def ecdsa_verify_dev(self, d_ok, d_sig64, sigfmt, d_msg32, d_pk, pkfmt, n, stream=0):
         self._ck(self._lib.secp256k1_b200_ecdsa_verify_batch_dev(self._h, d_ok, d_sig64, sigfmt, d_msg32, d_pk, pkfmt, n, stream))

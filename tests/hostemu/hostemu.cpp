@@ -205,6 +205,10 @@ int emu_surjection_verify(const uint8_t* proof, size_t plen, const uint8_t* in_t
     tab_local tab; return surjection_verify_item(proof, plen, in_tags64, n_tags, out_tag64, g_gt, tab);
 }
 int emu_pedersen_tally(const uint8_t* pos33, uint32_t pcnt, const uint8_t* neg33, uint32_t ncnt) { return pedersen_tally_item(pos33, pcnt, neg33, ncnt); }
+int emu_ecdsa_recover(uint8_t* out64, const uint8_t* sig64, int recid, const uint8_t* msg32) {
+    if (recid < 0 || recid > 3) { memset(out64, 0, 64); return 0; }
+    tab_local tab; return ecdsa_recover_item(out64, sig64, recid, msg32, g_gt, tab);
+}
 int emu_ecdsa_verify(const uint8_t* sig, int sigfmt, const uint8_t* msg32, const uint8_t* pk, int pkfmt) {
     tab_local tab; return ecdsa_verify_item(sig, sigfmt, msg32, pk, pkfmt, g_gt, tab);
 }

@@ -135,6 +135,33 @@ class RefLib:
         assert self.lib.ref_ecdsa_make_batch(self.ctx, sig, pk, sk32, _buf(msg32), ctypes.c_size_t(n))
         return np.frombuffer(sig.raw, dtype=np.uint8).copy(), np.frombuffer(pk.raw, dtype=np.uint8).copy()
 
+    def ecdsa_sign_recoverable(self, sk32, msg32):
+        sk32 = _buf(sk32)
+        n = len(sk32) // 32
+        sig = ctypes.create_string_buffer(64 * n)
+        rid = ctypes.create_string_buffer(n)
+        assert self.lib.ref_ecdsa_sign_recoverable_batch(self.ctx, sig, rid, sk32, _buf(msg32), ctypes.c_size_t(n))
+        return np.frombuffer(sig.raw, dtype=np.uint8).copy(), np.frombuffer(rid.raw, dtype=np.uint8).copy()
+
+    def ecdsa_recover(self, sig64, recid, msg32):
+        sig64 = _buf(sig64)
+        n = len(sig64) // 64
+        ok = ctypes.create_string_buffer(n)
+        out = ctypes.create_string_buffer(64 * n)
+        self.lib.ref_ecdsa_recover_batch(self.ctx, ok, out, sig64, _buf(recid), _buf(msg32), ctypes.c_size_t(n))
+        return np.frombuffer(ok.raw, dtype=np.uint8).copy(), np.frombuffer(out.raw, dtype=np.uint8).reshape(n, 64).copy()
+
+    def aggregate(self, pk32, msgs32, sigs64):
+        n = len(_buf(pk32)) // 32
+        agg = ctypes.create_string_buffer(32 * (n + 1))
+        ln = ctypes.c_size_t(32 * (n + 1))
+        assert self.lib.ref_schnorrsig_aggregate(self.ctx, agg, ctypes.byref(ln), _buf(pk32), _buf(msgs32), _buf(sigs64), ctypes.c_size_t(n))
+        return agg.raw[:ln.value]
+
+    def aggverify(self, pk32, msgs32, aggsig):
+        n = len(_buf(pk32)) // 32
+        return self.lib.ref_schnorrsig_aggverify(self.ctx, _buf(pk32), _buf(msgs32), ctypes.c_size_t(n), _buf(aggsig), ctypes.c_size_t(len(_buf(aggsig))))
+
     def ecdsa_verify(self, sig64, msg32, pk33):
         sig64 = _buf(sig64)
         n = len(sig64) // 64

@@ -232,3 +232,35 @@ def test_surjection_and_tally_compat(apis, ref):
         pos = arr_t(ctypes.addressof(objs[2]), ctypes.addressof(objs[3]))
         assert api.lib.secp256k1_pedersen_verify_tally(api.ctx, pos, ctypes.c_size_t(2), neg, ctypes.c_size_t(2)) == 1
         assert api.lib.secp256k1_pedersen_verify_tally(api.ctx, pos, ctypes.c_size_t(1), neg, ctypes.c_size_t(2)) == 0
+
+
+def test_ecdsa_recover_compat(apis, ref):
+    """secp256k1_ecdsa_recoverable_signature_{parse,serialize}_compact / _convert / secp256k1_ecdsa_recover through both libraries"""
+    from tests.test_hostemu_logic import _recover_cases
+    mine, theirs = apis
+    gold = json.load(open(os.path.join(GOLD, "recovery.json")))["vectors"]
+    cases = [(bytes.fromhex(v["sig64"]), rid, bytes.fromhex(v["msg32"])) for v in gold for rid in range(4)]
+    sig, rid, msg = _recover_cases(ref, 60, b"compat")
+    cases += [(sig[64 * i:64 * i + 64], rid[i], msg[32 * i:32 * i + 32]) for i in range(60) if rid[i] <= 3]
+    n_ok = 0
+    for s64, r, m32 in cases:
+        res = []
+        for api in (mine, theirs):
+            obj = ctypes.create_string_buffer(65)
+            p = api.lib.secp256k1_ecdsa_recoverable_signature_parse_compact(api.ctx, obj, s64, r)
+            pk = ctypes.create_string_buffer(64)
+            rec = api.lib.secp256k1_ecdsa_recover(api.ctx, pk, obj, m32) if p else -1
+            out = ctypes.create_string_buffer(64); rr = ctypes.c_int(-1)
+            api.lib.secp256k1_ecdsa_recoverable_signature_serialize_compact(api.ctx, out, ctypes.byref(rr), obj)
+            plain = ctypes.create_string_buffer(64)
+            api.lib.secp256k1_ecdsa_recoverable_signature_convert(api.ctx, plain, obj)
+            ser = api.ec_serialize(pk.raw, False)[1] if rec == 1 else b""
+            res.append((p, rec, obj.raw, pk.raw, out.raw, rr.value, plain.raw, ser))
+        assert res[0] == res[1], (s64.hex(), r)
+        n_ok += res[0][1] == 1
+    assert n_ok > 20
+    assert mine.illegal == theirs.illegal == 0
+    obj = ctypes.create_string_buffer(65)
+    for api in (mine, theirs):
+        assert api.lib.secp256k1_ecdsa_recoverable_signature_parse_compact(api.ctx, obj, cases[0][0], 4) == 0
+    assert mine.illegal == theirs.illegal == 1

@@ -145,6 +145,35 @@ def test_ecdsa_verify_batch_vs_reference(engine, ref):
     assert 0.2 < exp.mean() < 0.7
 
 
+def test_ecdsa_recover_batch_vs_reference(engine, ref):
+    """secp256k1_b200_ecdsa_recover_batch: bit-exact recovered keys and accept set vs the reference, incl. the reference's edge-case vectors"""
+    from tests.test_hostemu_logic import _recover_cases
+    gold = json.load(open(os.path.join(GOLD, "recovery.json")))["vectors"]
+    sig = b"".join(bytes.fromhex(v["sig64"]) * 4 for v in gold)
+    msg = b"".join(bytes.fromhex(v["msg32"]) * 4 for v in gold)
+    rid = bytes([0, 1, 2, 3] * len(gold))
+    ok, _ = engine.ecdsa_recover(sig, rid, msg)
+    assert ok.tolist() == [x for v in gold for x in v["recover_ok"]]
+    n = 6000
+    sig, rid, msg = _recover_cases(ref, n, b"gpu")
+    eok, epk = ref.ecdsa_recover(sig, rid, msg)
+    ok, pk = engine.ecdsa_recover(sig, rid, msg)
+    assert np.array_equal(ok, eok)
+    assert np.array_equal(pk, epk)
+    assert 0.2 < eok.mean() < 0.9
+    # round trip at scale: every recovered key verifies its signature (normalised to low-s as secp256k1_ecdsa_verify demands)
+    import secp256k1_zkp_b200 as b200
+    good = np.nonzero(ok)[0]
+    s_arr = np.frombuffer(sig, dtype=np.uint8).reshape(n, 64)[good].copy()
+    for j in range(len(good)):
+        sv = int.from_bytes(bytes(s_arr[j, 32:]), "big")
+        if sv > N // 2:
+            s_arr[j, 32:] = np.frombuffer(b32(N - sv), dtype=np.uint8)
+    comp = np.concatenate([(2 + (pk[good, 63] & 1))[:, None].astype(np.uint8), pk[good, :32]], axis=1)
+    m_arr = np.frombuffer(msg, dtype=np.uint8).reshape(n, 32)[good]
+    assert engine.ecdsa_verify(s_arr, m_arr, comp, b200.SIG_COMPACT64, b200.PK_COMPRESSED33).all()
+
+
 # ---- the reference's own golden vectors through the C ABI ------------------------------------------
 import ctypes
 import json

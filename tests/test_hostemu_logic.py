@@ -315,3 +315,37 @@ def test_surjection_and_tally_logic(emu, ref):
     bad = bytearray(cp); bad[40] ^= 1
     assert ref.lib.ref_pedersen_verify_tally(ref.ctx, bytes(bad), ctypes.c_size_t(2), cn, ctypes.c_size_t(2)) == emu.emu_pedersen_tally(bytes(bad), 2, cn, 2) == 0
     assert emu.emu_pedersen_tally(cp, 1, cn, 2) == ref.lib.ref_pedersen_verify_tally(ref.ctx, cp, ctypes.c_size_t(1), cn, ctypes.c_size_t(2)) == 0
+
+
+# ---- ECDSA public-key recovery --------------------------------------------------------------------------
+def _recover_cases(ref, n, tag):
+    """compact signatures + recids from the reference signer, then tampered: wrong recid, flipped bits, r/s = 0, r + n variants"""
+    sk = b"".join(hashlib.sha256(b"%ssk%d" % (tag, i)).digest() for i in range(n))
+    msg = bytearray(b"".join(hashlib.sha256(b"%sm%d" % (tag, i)).digest() for i in range(n)))
+    sig, rid = ref.ecdsa_sign_recoverable(sk, bytes(msg))
+    sig, rid = bytearray(sig.tobytes()), bytearray(rid.tobytes())
+    for i in range(n):
+        if i % 3 == 1: rid[i] = (rid[i] + 1 + i % 3) & 3
+        if i % 5 == 2: sig[64 * i + (i * 7) % 64] ^= 1 << (i % 8)
+        if i % 7 == 3: msg[32 * i + i % 32] ^= 0x10
+        if i % 23 == 4: sig[64 * i:64 * i + 32] = bytes(32)
+        if i % 29 == 5: sig[64 * i + 32:64 * i + 64] = bytes(32)
+        if i % 31 == 6: sig[64 * i:64 * i + 32] = b32(N + 5 - (i % 7))                 # r overflows: parse failure
+        if i % 37 == 7: sig[64 * i:64 * i + 32] = b32(1 + (i % 5)); rid[i] = 2 + (i & 1)  # tiny r with the "r + n" bit
+        if i % 41 == 8: rid[i] = 4 + (i % 200)                                         # out-of-range recid
+    return bytes(sig), bytes(rid), bytes(msg)
+
+
+def test_ecdsa_recover_vs_reference_and_golden(emu, ref):
+    out = ctypes.create_string_buffer(64)
+    for v in json.load(open(os.path.join(GOLD, "recovery.json")))["vectors"]:
+        for rid in range(4):
+            assert emu.emu_ecdsa_recover(out, bytes.fromhex(v["sig64"]), rid, bytes.fromhex(v["msg32"])) == v["recover_ok"][rid]
+    n = 150
+    sig, rid, msg = _recover_cases(ref, n, b"emu")
+    eok, epk = ref.ecdsa_recover(sig, rid, msg)
+    assert 0.2 < eok.mean() < 0.9
+    for i in range(n):
+        ok = emu.emu_ecdsa_recover(out, sig[64 * i:64 * i + 64], rid[i], msg[32 * i:32 * i + 32])
+        assert ok == eok[i], i
+        assert out.raw == epk[i].tobytes(), i

@@ -187,3 +187,20 @@ def test_port_surjection_and_tally(port, ref):
     cp = ref.pedersen_commit(b32(bl[2]) + b32((bl[0] + bl[1] - bl[2]) % N), [55, 45], gen)[1].tobytes()
     assert port.lib.orc_pedersen_verify_tally(cp, ctypes.c_size_t(2), cn, ctypes.c_size_t(2)) == 1
     assert port.lib.orc_pedersen_verify_tally(cp, ctypes.c_size_t(2), cn, ctypes.c_size_t(1)) == 0
+
+
+def test_port_ecdsa_recover(port):
+    """oracle port of secp256k1_ecdsa_recover vs the reference's edge-case vectors and vs _ref on tampered signer output"""
+    from tests.refshim import RefLib
+    from tests.test_hostemu_logic import _recover_cases
+    out = ctypes.create_string_buffer(64)
+    for v in json.load(open(os.path.join(GOLD, "recovery.json")))["vectors"]:
+        for rid in range(4):
+            assert port.lib.orc_ecdsa_recover(out, bytes.fromhex(v["sig64"]), rid, bytes.fromhex(v["msg32"])) == v["recover_ok"][rid]
+    ref = RefLib()
+    n = 120
+    sig, rid, msg = _recover_cases(ref, n, b"port")
+    eok, epk = ref.ecdsa_recover(sig, rid, msg)
+    for i in range(n):
+        ok = port.lib.orc_ecdsa_recover(out, sig[64 * i:64 * i + 64], rid[i], msg[32 * i:32 * i + 32])
+        assert ok == eok[i] and out.raw == epk[i].tobytes(), i

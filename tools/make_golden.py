@@ -13,6 +13,8 @@ Sources (paths relative to /root/reference):
   src/modules/rangeproof/tests_impl.h:589-812, :883-1349  rangeproof vectors
   src/modules/generator/tests_impl.h             pedersen / generator fixed vectors
   src/modules/bppp/test_vectors/verify.h         BP++ norm-argument verify vectors
+  src/modules/recovery/tests_impl.h:156-249      ECDSA recovery edge cases
+  src/modules/schnorrsig_halfagg/tests_impl.h:72-167   half-aggregation spec vectors
 """
 import ctypes
 import hashlib
@@ -195,12 +197,47 @@ def bppp_vectors(ref):
             "gens33": gens33.hex(), "gens_xy": gens_xy.hex(), "vectors": out}
 
 
+def recovery_vectors():
+    """src/modules/recovery/tests_impl.h:156-199 (test_ecdsa_recovery_edge_cases): which recids recover a key."""
+    text = read("src/modules/recovery/tests_impl.h")
+    body = re.sub(r"/\*.*?\*/", "", func_body(text, "test_ecdsa_recovery_edge_cases"), flags=re.S)
+    body = re.sub(r"'(.)'", lambda m: "0x%02x" % ord(m.group(1)), body)      # msg32 is spelled with character literals
+    arr = {n: b for n, b, _ in parse_arrays(body)}
+    assert arr["msg32"] == b"This is a very secret message..." and len(arr["sig64"]) == 64 and len(arr["sigb64"]) == 64
+    vec = [{"msg32": arr["msg32"].hex(), "sig64": arr["sig64"].hex(), "recover_ok": [0, 1, 0, 0],
+            "note": "CHECK(!recover) for recid 0, 2, 3 and CHECK(recover) for recid 1 (:192-199)"},
+           {"msg32": arr["msg32"].hex(), "sig64": arr["sigb64"].hex(), "recover_ok": [1, 1, 1, 1],
+            "note": "(r,s) = (4,4) recovers with all four recids (:176,:247-249)"}]
+    return {"source": "src/modules/recovery/tests_impl.h:156-249", "vectors": vec}
+
+
+def halfagg_vectors():
+    """src/modules/schnorrsig_halfagg/tests_impl.h:72-167: the three half-aggregation spec vectors (all must verify)."""
+    text = read("src/modules/schnorrsig_halfagg/tests_impl.h")
+    body = func_body(text, "test_schnorrsig_aggverify_spec_vectors")
+    arrs = parse_arrays(body)
+    vec, cur = [], {}
+    for name, b, _ in arrs:
+        if name in cur:
+            vec.append(cur); cur = {}
+        cur[name] = b.hex()
+        if name == "aggsig":
+            vec.append(cur); cur = {}
+    out = []
+    for v in vec:
+        out.append({"pubkeys": v.get("pubkeys_ser", ""), "msgs32": v.get("msgs32", ""), "aggsig": v["aggsig"], "expected": 1})
+    assert [len(v["aggsig"]) // 64 - 1 for v in out] == [0, 1, 2]
+    return {"source": "src/modules/schnorrsig_halfagg/tests_impl.h:72-167", "vectors": out}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     from tests.refshim import RefLib
     ref = RefLib()
     jobs = {"bip340.json": bip340, "ecmult.json": ecmult_golden, "wycheproof_ecdsa.json": lambda: wycheproof(ref)}
     jobs["bppp_verify.json"] = lambda: bppp_vectors(ref)
+    jobs["recovery.json"] = recovery_vectors
+    jobs["halfagg.json"] = halfagg_vectors
     if hasattr(ref, "rangeproof_verify_one"):
         jobs["rangeproof.json"] = lambda: rangeproof(ref)
     for name, fn in jobs.items():
