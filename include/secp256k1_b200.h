@@ -17,6 +17,7 @@
  *   secp256k1_b200_ecdsa_verify_batch   secp256k1_ecdsa_verify (include/secp256k1.h:622, src/secp256k1.c:498)
  *                                       [+ secp256k1_ec_pubkey_parse / secp256k1_ecdsa_signature_parse_compact]
  *   secp256k1_b200_ecdsa_recover_batch  secp256k1_ecdsa_recover (include/secp256k1_recovery.h:105, src/modules/recovery/main_impl.h:137)
+ *   secp256k1_b200_schnorrsig_aggverify secp256k1_schnorrsig_aggverify (include/secp256k1_schnorrsig_halfagg.h:103)
  *   secp256k1_b200_pedersen_commit_batch     secp256k1_pedersen_commit (include/secp256k1_generator.h:114,
  *                                       src/modules/generator/main_impl.h:309) + _commitment_serialize (:281)
  *   secp256k1_b200_rangeproof_verify_batch   secp256k1_rangeproof_verify (include/secp256k1_rangeproof.h:70,
@@ -123,6 +124,18 @@ SECP256K1_B200_API int secp256k1_b200_ecdsa_recover_batch(secp256k1_b200_engine 
         const unsigned char *sig64, const unsigned char *recid, const unsigned char *msghash32, size_t n);
 SECP256K1_B200_API int secp256k1_b200_ecdsa_recover_batch_dev(secp256k1_b200_engine *e, unsigned char *d_ok, unsigned char *d_pubkey64,
         const unsigned char *d_sig64, const unsigned char *d_recid, const unsigned char *d_msghash32, size_t n, void *stream);
+
+/* BIP-340 half-aggregation: secp256k1_schnorrsig_aggverify (include/secp256k1_schnorrsig_halfagg.h:103,
+ * src/modules/schnorrsig_halfagg/main_impl.h:108).  pubkeys32 = n x 32-byte x-only serializations (the reference takes parsed
+ * secp256k1_xonly_pubkey objects; a key that does not parse gives *ok = 0 here), msgs32 = n x 32, aggsig = 32*(n+1) bytes
+ * (r_0..r_{n-1}, s).  *ok = verdict; the return value reports engine errors only.  Evaluated as ONE multi-scalar
+ * multiplication over 2n+1 terms (sum z_i*R_i + z_i*e_i*P_i - s*G == infinity).  The randomizers z_i are a running hash over all
+ * signatures (serial): walked on the host for the host-buffer call, by a single GPU thread for the _dev call. */
+SECP256K1_B200_API int secp256k1_b200_schnorrsig_aggverify(secp256k1_b200_engine *e, int *ok, const unsigned char *pubkeys32,
+        const unsigned char *msgs32, size_t n, const unsigned char *aggsig, size_t aggsig_len);
+SECP256K1_B200_API size_t secp256k1_b200_schnorrsig_aggverify_workspace_bytes(size_t n);
+SECP256K1_B200_API int secp256k1_b200_schnorrsig_aggverify_dev(secp256k1_b200_engine *e, unsigned char *d_ok, const unsigned char *d_pubkeys32,
+        const unsigned char *d_msgs32, size_t n, const unsigned char *d_aggsig, void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* ---- multi-scalar multiplication: out = g_scalar*G + sum_i scalars[i]*points[i] ----------------------------- */
 /* Pippenger bucket method on the GPU (replaces static secp256k1_ecmult_multi_var, src/ecmult.h:62; the callback

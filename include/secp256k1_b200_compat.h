@@ -77,6 +77,10 @@ SECP256K1_B200_API int secp256k1_rangeproof_verify(const secp256k1_context *ctx,
 SECP256K1_B200_API int secp256k1_rangeproof_info(const secp256k1_context *ctx, int *exp, int *mantissa, uint64_t *min_value, uint64_t *max_value,
         const unsigned char *proof, size_t plen);
 
+/* include/secp256k1_schnorrsig_halfagg.h:103 */
+SECP256K1_B200_API int secp256k1_schnorrsig_aggverify(const secp256k1_context *ctx, const secp256k1_xonly_pubkey *pubkeys, const unsigned char *msgs32,
+        size_t n, const unsigned char *aggsig, size_t aggsig_len);
+
 /* include/secp256k1_recovery.h:27-29 (opaque 65 bytes), :40 parse_compact, :52 convert, :65 serialize_compact, :105 recover */
 typedef struct secp256k1_ecdsa_recoverable_signature { unsigned char data[65]; } secp256k1_ecdsa_recoverable_signature;
 SECP256K1_B200_API int secp256k1_ecdsa_recoverable_signature_parse_compact(const secp256k1_context *ctx, secp256k1_ecdsa_recoverable_signature *sig,

@@ -407,6 +407,37 @@ void orc_schnorrsig_verify_batch(unsigned char *ok, const unsigned char *sig64, 
     for (i = 0; i < n; i++) ok[i] = (unsigned char)orc_schnorrsig_verify(sig64 + 64 * i, msg32 + 32 * i, 32, pk32 + 32 * i);
 }
 
+/* ---- BIP-340 half-aggregation verify: modules/schnorrsig_halfagg/main_impl.h:108-196 (pubkeys as x-only serializations) --- */
+int orc_schnorrsig_aggverify(const unsigned char *pk32, const unsigned char *msgs32, size_t n, const unsigned char *aggsig, size_t aggsig_len) {
+    sha256_t hz; gej rhs, lhs, gj; sc s; size_t i;
+    if (aggsig_len / 32 == 0 || aggsig_len / 32 - 1 != n || aggsig_len % 32 != 0) return 0;
+    rhs.inf = 1;
+    sha_init_tagged(&hz, "HalfAgg/randomizer");
+    for (i = 0; i < n; i++) {
+        fe rx; ge rp, pp; sc ei, zi; gej ppj, ti, t2; sha256_t hc, he; unsigned char buf[32], pk_ser[32];
+        if (!xonly_parse(&pp, pk32 + 32 * i)) return 0;
+        u256_to_be(pk_ser, &pp.x);
+        sha_write(&hz, aggsig + 32 * i, 32); sha_write(&hz, pk_ser, 32); sha_write(&hz, msgs32 + 32 * i, 32);
+        hc = hz; sha_final(&hc, buf); sc_set_b32(&zi, buf);
+        if (!fe_set_b32_limit(&rx, aggsig + 32 * i)) return 0;
+        if (!ge_set_xo(&rp, &rx, 0)) return 0;
+        sha_init_tagged(&he, "BIP0340/challenge");
+        sha_write(&he, aggsig + 32 * i, 32); sha_write(&he, pk_ser, 32); sha_write(&he, msgs32 + 32 * i, 32);
+        sha_final(&he, buf); sc_set_b32(&ei, buf);
+        gej_set_ge(&ppj, &pp);
+        ecmult(&ti, &ppj, &ei, NULL);
+        gej_add_ge(&t2, &ti, &rp); ti = t2;
+        if (i != 0) { ecmult(&t2, &ti, &zi, NULL); ti = t2; }
+        gej_add(&t2, &rhs, &ti); rhs = t2;
+    }
+    if (sc_set_b32(&s, aggsig + 32 * n)) return 0;
+    gej_set_ge(&gj, &GEN_G);
+    gej_mul(&lhs, &gj, &s);
+    gej_neg(&lhs, &lhs);
+    gej_add(&gj, &lhs, &rhs);
+    return gj.inf;
+}
+
 /* ---- ECDSA verify: secp256k1.c:498-512 + ecdsa_impl.h:195-272 (compact sig: secp256k1.c:372-391) -------- */
 int orc_ecdsa_verify(const unsigned char *sig64, const unsigned char *msghash32, const unsigned char *pk, size_t pklen) {
     sc r, s, m, sn, u1, u2; ge P, R; gej Pj, Rj; sc xr;

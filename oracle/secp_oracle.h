@@ -34,6 +34,7 @@ ORC_API int  orc_xonly_pubkey_parse(unsigned char *xy64, const unsigned char *pk
 ORC_API int  orc_ec_pubkey_parse(unsigned char *xy64, const unsigned char *pk, size_t len);
 ORC_API int  orc_schnorrsig_verify(const unsigned char *sig64, const unsigned char *msg, size_t msglen, const unsigned char *pk32);
 ORC_API void orc_schnorrsig_verify_batch(unsigned char *ok, const unsigned char *sig64, const unsigned char *msg32, const unsigned char *pk32, size_t n);
+ORC_API int  orc_schnorrsig_aggverify(const unsigned char *pk32, const unsigned char *msgs32, size_t n, const unsigned char *aggsig, size_t aggsig_len);
 ORC_API int  orc_ecdsa_recover(unsigned char *pubkey64, const unsigned char *sig64, int recid, const unsigned char *msghash32);
 ORC_API int  orc_ecdsa_verify(const unsigned char *sig64_compact, const unsigned char *msghash32, const unsigned char *pk, size_t pklen);
 

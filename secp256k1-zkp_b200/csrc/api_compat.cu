@@ -218,6 +218,32 @@ int secp256k1_ecdsa_verify(const secp256k1_context* ctx, const secp256k1_ecdsa_s
     return ok;
 }
 
+// ---- half-aggregation (modules/schnorrsig_halfagg/main_impl.h:108-196) ---------------------------------------------------------
+int secp256k1_schnorrsig_aggverify(const secp256k1_context* ctx, const secp256k1_xonly_pubkey* pubkeys, const unsigned char* msgs32, size_t n,
+                                   const unsigned char* aggsig, size_t aggsig_len) {
+    ARG_CHECK(pubkeys != NULL || n == 0);
+    ARG_CHECK(msgs32 != NULL || n == 0);
+    ARG_CHECK(aggsig != NULL);
+    ARG_CHECK(ctx->proper);                       // ecmult_gen context built (:119)
+    if ((aggsig_len / 32) <= 0 || ((aggsig_len / 32) - 1) != n || (aggsig_len % 32) != 0) return 0;
+    unsigned char* pk32 = (unsigned char*)malloc(32 * n + 1);
+    if (!pk32) { callback_call(ctx->error_callback, "Out of memory"); return 0; }
+    for (size_t i = 0; i < n; i++) {
+        if (all_zero(pubkeys[i].data, 32)) {      // secp256k1_xonly_pubkey_load -> pubkey_load ARG_CHECK (src/secp256k1.c:282)
+            free(pk32);
+            callback_call(ctx->illegal_callback, "!secp256k1_fe_is_zero(&ge->x)");
+            return 0;
+        }
+        for (int k = 0; k < 32; k++) pk32[32 * i + k] = pubkeys[i].data[31 - k];
+    }
+    secp256k1_b200_engine* e = engine_or_error(ctx);
+    int ok = 0;
+    int rc = e ? secp256k1_b200_schnorrsig_aggverify(e, &ok, pk32, msgs32, n, aggsig, aggsig_len) : 0;
+    free(pk32);
+    if (e && !rc) callback_call(ctx->error_callback, secp256k1_b200_last_error());
+    return rc ? ok : 0;
+}
+
 // ---- ECDSA public-key recovery (modules/recovery/main_impl.h:38-85, :137-159) ---------------------------------------------
 int secp256k1_ecdsa_recoverable_signature_parse_compact(const secp256k1_context* ctx, secp256k1_ecdsa_recoverable_signature* sig,
                                                         const unsigned char* input64, int recid) {

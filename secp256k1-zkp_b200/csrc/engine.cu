@@ -2,6 +2,7 @@
 // in include/secp256k1_b200.h.  No CPU compute path exists here: every entry point launches kernels
 // on the B200 or fails.
 #include "../../include/secp256k1_b200.h"
+#include "halfagg.cuh"
 #include "launch.h"
 #include "sha256.cuh"
 
@@ -36,6 +37,7 @@ struct secp256k1_b200_engine {
     uint32_t* d_bases;
     size_t gtab_bytes;
     bip340_midstate_h mid;
+    uint32_t mid_halfagg[8];   // tagged-hash prefix state of "HalfAgg/randomizer" (schnorrsig_halfagg/main_impl.h:9-17)
     sign_consts_h sign;
     cudaStream_t stream;       // engine-owned stream for host-buffer calls
     cudaStream_t stream2;      // second stream: chunked host-buffer calls overlap H2D of chunk k+1 with the kernel of chunk k
@@ -125,6 +127,8 @@ int secp256k1_b200_engine_create(secp256k1_b200_engine** out, int device, int ge
         sha256 h;
         sha256_init_tagged(h, (const uint8_t*)"BIP0340/challenge", 17);
         for (int i = 0; i < 8; i++) { e->mid.s[i] = h.s[i]; e->sign.mid_challenge[i] = h.s[i]; }
+        sha256_init_tagged(h, (const uint8_t*)"HalfAgg/randomizer", 18);
+        for (int i = 0; i < 8; i++) e->mid_halfagg[i] = h.s[i];
         sha256_init_tagged(h, (const uint8_t*)"BIP0340/nonce", 13);
         for (int i = 0; i < 8; i++) e->sign.mid_nonce[i] = h.s[i];
         const uint8_t zeros[32] = {0};
@@ -410,6 +414,51 @@ int secp256k1_b200_ecmult_multi(secp256k1_b200_engine* e, unsigned char* out64, 
     if (!secp256k1_b200_ecmult_multi_dev(e, c.at(oo), g_scalar32 ? c.at(og) : nullptr, c.at(os), c.at(op), n, c.at(ow), wsb, e->stream)) return 0;
     CK(cudaMemcpyAsync(out64, c.at(oo), 64, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
+/* ---- BIP-340 half-aggregation ------------------------------------------------------------ */
+size_t secp256k1_b200_schnorrsig_aggverify_workspace_bytes(size_t n) { return halfagg_workspace_bytes(n); }
+int secp256k1_b200_schnorrsig_aggverify_dev(secp256k1_b200_engine* e, unsigned char* d_ok, const unsigned char* d_pubkeys32, const unsigned char* d_msgs32,
+                                            size_t n, const unsigned char* d_aggsig, void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (workspace_bytes < halfagg_workspace_bytes(n)) { set_error("schnorrsig_aggverify: workspace too small (see secp256k1_b200_schnorrsig_aggverify_workspace_bytes)"); return 0; }
+    device_guard guard(e->device);
+    CK(launch_halfagg_verify(d_ok, d_pubkeys32, d_msgs32, n, d_aggsig, nullptr, e->mid_halfagg, e->mid, (uint8_t*)d_workspace, workspace_bytes,
+                             (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_schnorrsig_aggverify(secp256k1_b200_engine* e, int* ok, const unsigned char* pubkeys32, const unsigned char* msgs32, size_t n,
+                                        const unsigned char* aggsig, size_t aggsig_len) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (!ok || !aggsig || (n && (!pubkeys32 || !msgs32))) { set_error("schnorrsig_aggverify: NULL argument"); return 0; }
+    *ok = 0;
+    if (aggsig_len / 32 == 0 || aggsig_len / 32 - 1 != n || aggsig_len % 32 != 0) return 1;      // wrong length: a verdict, not an error (:124-126)
+    std::lock_guard<std::mutex> lock(e->mu);
+    device_guard guard(e->device);
+    carver c(e);
+    size_t wsb = halfagg_workspace_bytes(n);
+    size_t opk = c.add(32 * n + 32), om = c.add(32 * n + 32), oa = c.add(32 * (n + 1)), oz = c.add(32 * n + 32), oo = c.add(16), ow = c.add(wsb);
+    if (!c.commit()) return 0;
+    if (n) {
+        CK(cudaMemcpyAsync(c.at(opk), pubkeys32, 32 * n, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(c.at(om), msgs32, 32 * n, cudaMemcpyHostToDevice, e->stream));
+    }
+    CK(cudaMemcpyAsync(c.at(oa), aggsig, 32 * (n + 1), cudaMemcpyHostToDevice, e->stream));
+    // The randomizer chain is one running SHA-256 over all signatures: serial by construction.  With host buffers it is
+    // walked here on the host (while the uploads above are in flight); the _dev entry point walks it in a one-thread kernel.
+    std::vector<uint8_t> z(32 * n + 32);
+    {
+        halfagg_midstate hm;
+        for (int i = 0; i < 8; i++) hm.s[i] = e->mid_halfagg[i];
+        halfagg_z_chain(z.data(), hm, aggsig, pubkeys32, msgs32, n);
+    }
+    if (n) CK(cudaMemcpyAsync(c.at(oz), z.data(), 32 * n, cudaMemcpyHostToDevice, e->stream));
+    CK(launch_halfagg_verify(c.at(oo), c.at(opk), c.at(om), n, c.at(oa), n ? c.at(oz) : nullptr, e->mid_halfagg, e->mid, c.at(ow), wsb, e->stream, &e->launches));
+    unsigned char r = 0;
+    CK(cudaMemcpyAsync(&r, c.at(oo), 1, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    *ok = r;
     return 1;
 }
 

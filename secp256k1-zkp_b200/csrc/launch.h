@@ -49,6 +49,10 @@ cudaError_t launch_surjection_verify(uint8_t* ok, const uint8_t* proofs, size_t 
                                      const uint32_t* tag_off, const uint8_t* out_tags64, size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches);
 cudaError_t launch_pedersen_tally(uint8_t* ok, const uint8_t* pos33, const uint32_t* pos_off, const uint8_t* neg33, const uint32_t* neg_off, size_t n,
                                   cudaStream_t s, uint64_t* launches);
+size_t halfagg_workspace_bytes(size_t n);
+cudaError_t launch_halfagg_verify(uint8_t* d_ok, const uint8_t* d_pk32, const uint8_t* d_msgs32, size_t n, const uint8_t* d_aggsig,
+                                  const uint8_t* d_z32_in, const uint32_t* hmid, const bip340_midstate_h& mid, uint8_t* ws, size_t ws_bytes,
+                                  cudaStream_t s, uint64_t* launches);
 size_t msm_workspace_bytes(size_t n_terms);
 cudaError_t launch_msm(uint8_t* out64, const uint8_t* g_scalar32, const uint8_t* scalars32, const uint8_t* points64, size_t n,
                        uint8_t* workspace, size_t workspace_bytes, cudaStream_t s, uint64_t* launches);

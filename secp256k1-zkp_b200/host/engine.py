@@ -87,6 +87,10 @@ def load_library():
     lib.secp256k1_b200_schnorrsig_verify_batch_dev.argtypes = [vp, u8p, u8p, u8p, sz, u8p, ci, sz, vp]
     lib.secp256k1_b200_ecdsa_verify_batch.argtypes = [vp, u8p, u8p, ci, u8p, u8p, ci, sz]
     lib.secp256k1_b200_ecdsa_verify_batch_dev.argtypes = [vp, u8p, u8p, ci, u8p, u8p, ci, sz, vp]
+    lib.secp256k1_b200_schnorrsig_aggverify.argtypes = [vp, ctypes.POINTER(ci), u8p, u8p, sz, u8p, sz]
+    lib.secp256k1_b200_schnorrsig_aggverify_workspace_bytes.argtypes = [sz]
+    lib.secp256k1_b200_schnorrsig_aggverify_workspace_bytes.restype = sz
+    lib.secp256k1_b200_schnorrsig_aggverify_dev.argtypes = [vp, u8p, u8p, u8p, sz, u8p, vp, sz, vp]
     lib.secp256k1_b200_ecdsa_recover_batch.argtypes = [vp, u8p, u8p, u8p, u8p, u8p, sz]
     lib.secp256k1_b200_ecdsa_recover_batch_dev.argtypes = [vp, u8p, u8p, u8p, u8p, u8p, sz, vp]
     _LIB = lib
@@ -190,6 +194,24 @@ class Engine:
         ok = np.empty(n, dtype=np.uint8)
         self._ck(self._lib.secp256k1_b200_ecdsa_verify_batch(self._h, _p(ok), _p(sig), sigfmt, _p(m), _p(p), pkfmt, n))
         return ok
+
+    def schnorrsig_aggverify(self, pubkeys32, msgs32, aggsig):
+        """secp256k1_schnorrsig_aggverify: one half-aggregate signature over n (key, message) pairs -> 0/1"""
+        agg = _u8(aggsig, len(aggsig) if not hasattr(aggsig, "size") else aggsig.size, "aggsig")
+        pk = np.ascontiguousarray(np.frombuffer(pubkeys32, dtype=np.uint8) if isinstance(pubkeys32, (bytes, bytearray)) else pubkeys32, dtype=np.uint8).reshape(-1)
+        n = pk.size // 32
+        m = _u8(msgs32, 32 * n, "msgs32") if n else np.zeros(1, dtype=np.uint8)
+        if n == 0:
+            pk = np.zeros(1, dtype=np.uint8)
+        ok = ctypes.c_int(0)
+        self._ck(self._lib.secp256k1_b200_schnorrsig_aggverify(self._h, ctypes.byref(ok), _p(pk), _p(m), n, _p(agg), agg.size))
+        return ok.value
+
+    def schnorrsig_aggverify_workspace_bytes(self, n):
+        return int(self._lib.secp256k1_b200_schnorrsig_aggverify_workspace_bytes(n))
+
+    def schnorrsig_aggverify_dev(self, d_ok, d_pk32, d_msgs32, n, d_aggsig, d_ws, ws_bytes, stream=0):
+        self._ck(self._lib.secp256k1_b200_schnorrsig_aggverify_dev(self._h, d_ok, d_pk32, d_msgs32, n, d_aggsig, d_ws, ws_bytes, stream))
 
     def ecdsa_recover(self, sig64, recid, msghash32):
         """(ok[n], pubkey64[n,64]) -- secp256k1_ecdsa_recover on compact signatures + recovery ids"""

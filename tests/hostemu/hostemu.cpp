@@ -25,6 +25,7 @@ int emu_fe_is_zero(const uint8_t* a) { fe x; fe_set_b32(x, a); return fe_is_zero
 #include "../../secp256k1-zkp_b200/csrc/msm.cuh"
 #include "../../secp256k1-zkp_b200/csrc/bppp.cuh"
 #include "../../secp256k1-zkp_b200/csrc/surjection.cuh"
+#include "../../secp256k1-zkp_b200/csrc/halfagg.cuh"
 #include <vector>
 #include <string.h>
 static std::vector<uint32_t> g_tab;
@@ -205,6 +206,15 @@ int emu_surjection_verify(const uint8_t* proof, size_t plen, const uint8_t* in_t
     tab_local tab; return surjection_verify_item(proof, plen, in_tags64, n_tags, out_tag64, g_gt, tab);
 }
 int emu_pedersen_tally(const uint8_t* pos33, uint32_t pcnt, const uint8_t* neg33, uint32_t ncnt) { return pedersen_tally_item(pos33, pcnt, neg33, ncnt); }
+int emu_halfagg_verify(const uint8_t* pk32, const uint8_t* msgs32, size_t n, const uint8_t* aggsig, size_t aggsig_len) {
+    halfagg_midstate hm; bip340_midstate bm; sha256 h;
+    sha256_init_tagged(h, (const uint8_t*)"HalfAgg/randomizer", 18);
+    for (int i = 0; i < 8; i++) hm.s[i] = h.s[i];
+    sha256_init_tagged(h, (const uint8_t*)"BIP0340/challenge", 17);
+    for (int i = 0; i < 8; i++) bm.s[i] = h.s[i];
+    std::vector<uint8_t> z(32 * n + 32);
+    tab_local tab; return halfagg_verify_serial(hm, bm, pk32, msgs32, n, aggsig, aggsig_len, z.data(), g_gt, tab);
+}
 int emu_ecdsa_recover(uint8_t* out64, const uint8_t* sig64, int recid, const uint8_t* msg32) {
     if (recid < 0 || recid > 3) { memset(out64, 0, 64); return 0; }
     tab_local tab; return ecdsa_recover_item(out64, sig64, recid, msg32, g_gt, tab);

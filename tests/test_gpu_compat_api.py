@@ -264,3 +264,20 @@ def test_ecdsa_recover_compat(apis, ref):
     for api in (mine, theirs):
         assert api.lib.secp256k1_ecdsa_recoverable_signature_parse_compact(api.ctx, obj, cases[0][0], 4) == 0
     assert mine.illegal == theirs.illegal == 1
+
+
+def test_halfagg_compat(apis, ref):
+    """secp256k1_schnorrsig_aggverify with parsed secp256k1_xonly_pubkey objects through both libraries"""
+    from tests.test_hostemu_logic import _halfagg_cases
+    mine, theirs = apis
+    for n in (0, 1, 4):
+        for pk, msg, agg, label in _halfagg_cases(ref, n, b"cagg%d" % n):
+            res = []
+            for api in (mine, theirs):
+                objs = ctypes.create_string_buffer(64 * max(n, 1))
+                parsed = all(api.lib.secp256k1_xonly_pubkey_parse(api.ctx, ctypes.byref(objs, 64 * i), pk[32 * i:32 * i + 32]) for i in range(n))
+                r = api.lib.secp256k1_schnorrsig_aggverify(api.ctx, objs if n else None, msg if n else None, ctypes.c_size_t(n), agg, ctypes.c_size_t(len(agg))) if parsed else -1
+                res.append((parsed, r))
+            assert res[0] == res[1], (n, label)
+            assert (label == "valid") == (res[0][1] == 1) or label.startswith("key tampered")
+    assert mine.illegal == theirs.illegal == 0

@@ -174,6 +174,54 @@ def test_ecdsa_recover_batch_vs_reference(engine, ref):
     assert engine.ecdsa_verify(s_arr, m_arr, comp, b200.SIG_COMPACT64, b200.PK_COMPRESSED33).all()
 
 
+def test_halfagg_verify_vs_reference(engine, ref):
+    """secp256k1_b200_schnorrsig_aggverify (host chain + MSM) and the _dev entry point (device chain) vs the reference: spec vectors,
+    valid aggregates of several sizes, every tampering of _halfagg_cases"""
+    import torch
+    from tests.test_hostemu_logic import _halfagg_cases
+
+    def dev_verify(pk, msg, agg):
+        n = len(pk) // 32
+        if len(agg) != 32 * (n + 1):
+            return None                      # the _dev call has no length argument: the caller guarantees 32*(n+1) bytes
+        t = lambda b: torch.frombuffer(bytearray(b if len(b) else b"\0"), dtype=torch.uint8).cuda()
+        d_pk, d_msg, d_agg = t(pk), t(msg), t(agg)
+        wsb = engine.schnorrsig_aggverify_workspace_bytes(n)
+        ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+        ok = torch.zeros(1, dtype=torch.uint8, device="cuda")
+        engine.schnorrsig_aggverify_dev(ok.data_ptr(), d_pk.data_ptr(), d_msg.data_ptr(), n, d_agg.data_ptr(), ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        return int(ok[0])
+    for v in json.load(open(os.path.join(GOLD, "halfagg.json")))["vectors"]:
+        pk, msg, agg = bytes.fromhex(v["pubkeys"]), bytes.fromhex(v["msgs32"]), bytes.fromhex(v["aggsig"])
+        assert engine.schnorrsig_aggverify(pk, msg, agg) == v["expected"]
+        assert dev_verify(pk, msg, agg) == v["expected"]
+    seen = set()
+    for n in (0, 1, 2, 33, 300):
+        for pk, msg, agg, label in _halfagg_cases(ref, n, b"gpu%d" % n):
+            exp = ref.aggverify(pk, msg, agg)
+            want = 1 if exp == 1 else 0
+            assert engine.schnorrsig_aggverify(pk, msg, agg) == want, (n, label)
+            d = dev_verify(pk, msg, agg)
+            assert d is None or d == want, (n, label)
+            seen.add(exp)
+    assert seen >= {0, 1}
+
+
+def test_halfagg_verify_large(engine, ref):
+    """one aggregate over 20000 signatures (reference-signed, device-side randomizer chain skipped: host chain + 40001-term MSM)"""
+    n = 20000
+    sk = b"".join(hashlib.sha256(b"bigagg%d" % i).digest() for i in range(n))
+    msg = b"".join(hashlib.sha256(b"bigaggm%d" % i).digest() for i in range(n))
+    sig, pk = ref.schnorr_make(sk, msg)
+    agg = ref.aggregate(pk.tobytes(), msg, sig.tobytes())
+    assert engine.schnorrsig_aggverify(pk.tobytes(), msg, agg) == 1
+    bad = bytearray(agg); bad[32 * 12345 + 7] ^= 0x20
+    assert engine.schnorrsig_aggverify(pk.tobytes(), msg, bytes(bad)) == 0
+    bad = bytearray(msg); bad[32 * 19999] ^= 1
+    assert engine.schnorrsig_aggverify(pk.tobytes(), bytes(bad), agg) == 0
+
+
 # ---- the reference's own golden vectors through the C ABI ------------------------------------------
 import ctypes
 import json

@@ -349,3 +349,49 @@ def test_ecdsa_recover_vs_reference_and_golden(emu, ref):
         ok = emu.emu_ecdsa_recover(out, sig[64 * i:64 * i + 64], rid[i], msg[32 * i:32 * i + 32])
         assert ok == eok[i], i
         assert out.raw == epk[i].tobytes(), i
+
+
+# ---- BIP-340 half-aggregation -----------------------------------------------------------------------------
+def _halfagg_cases(ref, n, tag):
+    """(pk32, msgs32, aggsig, label) list: a valid aggregate of n reference signatures plus tampered variants"""
+    sk = b"".join(hashlib.sha256(b"%shsk%d" % (tag, i)).digest() for i in range(n))
+    msg = b"".join(hashlib.sha256(b"%shm%d" % (tag, i)).digest() for i in range(n))
+    sig, pk = ref.schnorr_make(sk, msg)
+    sig, pk = sig.tobytes(), pk.tobytes()
+    agg = ref.aggregate(pk, msg, sig)
+    assert len(agg) == 32 * (n + 1)
+    out = [(pk, msg, agg, "valid")]
+
+    def flip(b, pos, bit=1):
+        b = bytearray(b); b[pos] ^= bit; return bytes(b)
+    if n:
+        out.append((pk, msg, flip(agg, 32 * n + 31), "s+-1"))
+        out.append((pk, msg, flip(agg, 5, 4), "r_0 tampered"))
+        out.append((pk, flip(msg, 32 * (n - 1) + 3), agg, "last msg tampered"))
+        out.append((flip(pk, 32 * (n // 2) + 31), msg, agg, "key tampered (may stop parsing)"))
+        out.append((pk, msg, agg[:32 * (n // 2)] + b"\xff" * 32 + agg[32 * (n // 2) + 32:], "r >= p"))
+        out.append((pk, msg, agg[:32 * n] + b32(N), "s = n (overflow)"))
+        out.append((pk, msg, agg[:-32], "aggsig one block short"))
+        out.append((pk, msg, agg + bytes(32), "aggsig one block long"))
+        out.append((pk, msg, agg + b"\x00", "aggsig_len not a multiple of 32"))
+        if n > 1:   # swap two (key, msg, r) triples: the randomizers depend on the order
+            i, j = 0, n - 1
+            def sw(b, w):
+                b = bytearray(b); b[w * i:w * i + w], b[w * j:w * j + w] = b[w * j:w * j + w], b[w * i:w * i + w]; return bytes(b)
+            out.append((sw(pk, 32), sw(msg, 32), sw(agg[:32 * n], 32) + agg[32 * n:], "order swapped"))
+    return out
+
+
+def test_halfagg_vs_reference_and_golden(emu, ref):
+    for v in json.load(open(os.path.join(GOLD, "halfagg.json")))["vectors"]:
+        pk, msg, agg = bytes.fromhex(v["pubkeys"]), bytes.fromhex(v["msgs32"]), bytes.fromhex(v["aggsig"])
+        assert emu.emu_halfagg_verify(pk, msg, ctypes.c_size_t(len(pk) // 32), agg, ctypes.c_size_t(len(agg))) == v["expected"]
+    seen = set()
+    for n in (0, 1, 2, 5, 17):
+        for pk, msg, agg, label in _halfagg_cases(ref, n, b"emu%d" % n):
+            exp = ref.aggverify(pk, msg, agg)
+            got = emu.emu_halfagg_verify(pk, msg, ctypes.c_size_t(n), agg, ctypes.c_size_t(len(agg)))
+            assert got == (1 if exp == 1 else 0), (n, label)     # exp == -1: a key the reference cannot even parse
+            assert (label == "valid") == (exp == 1) or label.startswith("key tampered"), (n, label, exp)
+            seen.add(exp)
+    assert seen >= {0, 1}

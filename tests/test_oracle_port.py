@@ -204,3 +204,17 @@ def test_port_ecdsa_recover(port):
     for i in range(n):
         ok = port.lib.orc_ecdsa_recover(out, sig[64 * i:64 * i + 64], rid[i], msg[32 * i:32 * i + 32])
         assert ok == eok[i] and out.raw == epk[i].tobytes(), i
+
+
+def test_port_halfagg(port):
+    """oracle port of secp256k1_schnorrsig_aggverify vs the three spec vectors of the reference tests and vs _ref on tampered aggregates"""
+    from tests.refshim import RefLib
+    from tests.test_hostemu_logic import _halfagg_cases
+    for v in json.load(open(os.path.join(GOLD, "halfagg.json")))["vectors"]:
+        pk, msg, agg = bytes.fromhex(v["pubkeys"]), bytes.fromhex(v["msgs32"]), bytes.fromhex(v["aggsig"])
+        assert port.lib.orc_schnorrsig_aggverify(pk, msg, ctypes.c_size_t(len(pk) // 32), agg, ctypes.c_size_t(len(agg))) == v["expected"]
+    ref = RefLib()
+    for n in (0, 1, 3, 9):
+        for pk, msg, agg, label in _halfagg_cases(ref, n, b"port%d" % n):
+            exp = ref.aggverify(pk, msg, agg)
+            assert port.lib.orc_schnorrsig_aggverify(pk, msg, ctypes.c_size_t(n), agg, ctypes.c_size_t(len(agg))) == (1 if exp == 1 else 0), (n, label)
