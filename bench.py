@@ -192,7 +192,7 @@ def run_extra_workloads(eng, b200, torch, dist, D, dev, stream, rank, world, ima
     m = hi - lo
     gen = torch.Generator(device=dev); gen.manual_seed(777 + rank)
     sk = torch.randint(0, 256, (m, 32), dtype=torch.uint8, device=dev, generator=gen); sk[:, 0] &= 0x7F
-    sc = torch.randint(0, 256, (m, 32), dtype=torch.uint8, device=dev, generator=gen); sc[:, 0] &= 0x7F
+    sc = torch.randint(0, 256, (m, 32), dtype=torch.uint8, device=dev, generator=gen)
     pts = torch.empty((m, 64), dtype=torch.uint8, device=dev)
     z64, z32 = torch.zeros((m, 64), dtype=torch.uint8, device=dev), torch.zeros((m, 32), dtype=torch.uint8, device=dev)
     eng.ecmult_dev(pts.data_ptr(), z64.data_ptr(), z32.data_ptr(), sk.data_ptr(), m, stream)     # P_i = sk_i * G

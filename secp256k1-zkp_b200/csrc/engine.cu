@@ -6,6 +6,7 @@
 #include "launch.h"
 #include "sha256.cuh"
 
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -448,16 +449,24 @@ int secp256k1_b200_schnorrsig_aggverify(secp256k1_b200_engine* e, int* ok, const
     // The randomizer chain is one running SHA-256 over all signatures: serial by construction.  With host buffers it is
     // walked here on the host (while the uploads above are in flight); the _dev entry point walks it in a one-thread kernel.
     std::vector<uint8_t> z(32 * n + 32);
+    const bool timing = getenv("SECP256K1_B200_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
     {
         halfagg_midstate hm;
         for (int i = 0; i < 8; i++) hm.s[i] = e->mid_halfagg[i];
         halfagg_z_chain(z.data(), hm, aggsig, pubkeys32, msgs32, n);
     }
+    auto t1 = std::chrono::steady_clock::now();
     if (n) CK(cudaMemcpyAsync(c.at(oz), z.data(), 32 * n, cudaMemcpyHostToDevice, e->stream));
     CK(launch_halfagg_verify(c.at(oo), c.at(opk), c.at(om), n, c.at(oa), n ? c.at(oz) : nullptr, e->mid_halfagg, e->mid, c.at(ow), wsb, e->stream, &e->launches));
     unsigned char r = 0;
     CK(cudaMemcpyAsync(&r, c.at(oo), 1, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    if (timing) {
+        auto t2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[b200 timing] aggverify n=%zu: randomizer chain %.2f ms, device part (terms + MSM + copies) %.2f ms\n", n,
+                std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
+    }
     *ok = r;
     return 1;
 }

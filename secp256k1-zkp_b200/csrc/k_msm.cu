@@ -8,14 +8,14 @@ namespace b200 {
 struct msm_ws {
     uint32_t* scalars;     // [N][8]   reduced scalars, LE limbs
     uint32_t* points;      // [N][16]  affine LE storage, zero = infinity
-    uint32_t* hist;        // [17][32768]
-    uint32_t* offsets;     // [17][32768]
-    uint32_t* cursor;      // [17][32768]
-    uint32_t* entries;     // [17][N]
-    gej_store* buckets;    // [17][32768]
-    gej_store* chunks;     // [17][1024]
-    gej_store* groups;     // [17][32]
-    gej_store* windows;    // [17]
+    uint32_t* hist;        // [16][32768]
+    uint32_t* offsets;     // [16][32768]
+    uint32_t* cursor;      // [16][32768]
+    uint32_t* entries;     // [16][N]
+    gej_store* buckets;    // [16][32768]
+    gej_store* chunks;     // [16][1024]
+    gej_store* groups;     // [16][32]
+    gej_store* windows;    // [16]
 };
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }

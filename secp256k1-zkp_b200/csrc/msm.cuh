@@ -4,12 +4,13 @@
 // -> secp256k1_ecmult_pippenger_wnaf (:516-591) compute, re-designed for a GPU:
 //   reference: per window, clear buckets, add every point into its bucket one after the other (:545-566), then the
 //              running-sum reduction (:581-588); one thread, scratch space sized by the bucket window (:597-621).
-//   here:      c = 16-bit signed windows (17 windows, 2^15 buckets each).  (1) every term emits its 17 signed digits and
+//   here:      c = 16-bit signed windows (16 windows, 2^15 buckets each; a scalar above n/2 is replaced by its negative and the
+//              digit signs flipped, so the recoding never carries out of the top window).  (1) every term emits its 16 signed digits and
 //              bumps a (window,bucket) histogram; (2) exclusive scan; (3) counting-sort scatter of term indices, so each
 //              bucket's points are contiguous; (4) ONE THREAD PER BUCKET sums its points with mixed adds (557 056
 //              independent threads at 2^20 terms, ~32 points each); (5) the running-sum reduction is cut into chunks of
 //              32 buckets: chunk value = L + b0*A with L = sum j*S_{b0+j}, A = sum S_{b0+j} (b0*A by a 15-bit
-//              double-and-add); (6) tree-sum of the chunks per window, Horner over the 17 windows.
+//              double-and-add); (6) tree-sum of the chunks per window, Horner over the 16 windows.
 // No GLV split (it halves the windows but doubles the points: same number of bucket additions on a GPU).
 // Only the final point has to match the reference; it does because the group element is unique.
 #pragma once
@@ -19,21 +20,27 @@
 namespace B200_NS {
 
 #define MSM_C 16
-#define MSM_WINDOWS 17
+#define MSM_WINDOWS 16
 #define MSM_BUCKETS 32768            // per window: |digit| in 1..32768
 #define MSM_CHUNK 32                 // buckets per reduction chunk
 #define MSM_CHUNKS (MSM_BUCKETS / MSM_CHUNK)
 
-// signed 16-bit window recoding of a 256-bit scalar: k = sum d_w 2^(16w), d_w in [-32767, 32768], w = 0..16
-HD void msm_digits(int32_t* d /*[17]*/, const sc& k) {
+// signed 16-bit window recoding of a scalar: k = sum d_w 2^(16w) (mod n), d_w in [-32768, 32768], w = 0..15.
+// k > n/2 is recoded as -(n - k): then the top window holds < 2^15 and nothing carries out of it.  (Without this every scalar with
+// bit 255 set put a digit 1 into a 17th window and ONE bucket thread summed half of all points serially: 256 ms at 131 072 terms.)
+HD void msm_digits(int32_t* d /*[16]*/, const sc& k0) {
+    int neg = sc_is_high(k0);
+    sc k;
+    if (neg) sc_negate(k, k0); else k = k0;
     uint32_t carry = 0;
 #pragma unroll
     for (int w = 0; w < 16; w++) {
         uint32_t v = ((k.v[w >> 1] >> ((w & 1) * 16)) & 0xFFFFu) + carry;
-        if (v > 32768u) { d[w] = (int32_t)v - 65536; carry = 1; }
-        else { d[w] = (int32_t)v; carry = 0; }
+        int32_t dw;
+        if (v > 32768u) { dw = (int32_t)v - 65536; carry = 1; }
+        else { dw = (int32_t)v; carry = 0; }
+        d[w] = neg ? -dw : dw;
     }
-    d[16] = (int32_t)carry;
 }
 
 // affine point storage used by the MSM kernels: 16 words x[8] y[8] (LE limbs), all-zero = infinity

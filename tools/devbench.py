@@ -93,7 +93,7 @@ def bench_msm_and_rangeproof():
         pts = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
         eng.ecmult_dev(pts.data_ptr(), torch.zeros((n, 64), dtype=torch.uint8, device="cuda").data_ptr(),
                        torch.zeros((n, 32), dtype=torch.uint8, device="cuda").data_ptr(), ng.data_ptr(), n, stream)
-        sc = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda"); sc[:, 0] &= 0x7F
+        sc = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda")
         wsb = eng.ecmult_multi_workspace_bytes(n)
         ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
         out = torch.empty(64, dtype=torch.uint8, device="cuda")

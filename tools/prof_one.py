@@ -40,7 +40,7 @@ okr = torch.zeros(per, dtype=torch.uint8, device="cuda"); mn = torch.zeros(per, 
 for _ in range(2):
     eng.rangeproof_verify_dev(okr.data_ptr(), mn.data_ptr(), mx.data_ptr(), commits.data_ptr(), proofs.data_ptr(), 5126, plen.data_ptr(), g64.data_ptr(), 0, per, st)
 m = 1 << 18
-sc = torch.randint(0, 256, (m, 32), dtype=torch.uint8, device="cuda", generator=g); sc[:, 0] &= 0x7F
+sc = torch.randint(0, 256, (m, 32), dtype=torch.uint8, device="cuda", generator=g)
 pts = torch.empty((m, 64), dtype=torch.uint8, device="cuda")
 eng.ecmult_dev(pts.data_ptr(), torch.zeros((m, 64), dtype=torch.uint8, device="cuda").data_ptr(), torch.zeros((m, 32), dtype=torch.uint8, device="cuda").data_ptr(), sc.data_ptr(), m, st)
 wsb = eng.ecmult_multi_workspace_bytes(m); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda"); out = torch.empty(64, dtype=torch.uint8, device="cuda")
