@@ -134,6 +134,11 @@ SECP256K1_B200_API int secp256k1_b200_ecdsa_recover_batch_dev(secp256k1_b200_eng
 SECP256K1_B200_API int secp256k1_b200_schnorrsig_aggverify(secp256k1_b200_engine *e, int *ok, const unsigned char *pubkeys32,
         const unsigned char *msgs32, size_t n, const unsigned char *aggsig, size_t aggsig_len);
 SECP256K1_B200_API size_t secp256k1_b200_schnorrsig_aggverify_workspace_bytes(size_t n);
+/* host-only helper (no GPU): the randomizers z_0..z_{n-1} of an aggregate as 32-byte hash outputs (z_0 = 1), the serial part of the
+ * verification above (main_impl.h:144-155).  Returns 1 if the CPU's SHA extensions were used, 0 for the portable code;
+ * force_portable != 0 selects the portable code (tests compare the two). */
+SECP256K1_B200_API int secp256k1_b200_halfagg_randomizers(unsigned char *z32, const unsigned char *pubkeys32, const unsigned char *msgs32, size_t n,
+        const unsigned char *aggsig, int force_portable);
 SECP256K1_B200_API int secp256k1_b200_schnorrsig_aggverify_dev(secp256k1_b200_engine *e, unsigned char *d_ok, const unsigned char *d_pubkeys32,
         const unsigned char *d_msgs32, size_t n, const unsigned char *d_aggsig, void *d_workspace, size_t workspace_bytes, void *stream);
 

@@ -38,13 +38,19 @@ def _newest_header():
     return t
 
 
+CXX = os.environ.get("CXX", "g++")
+
+
 def _compile(unit, flags, force, hdr_time):
     src = os.path.join(CSRC, unit)
-    obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
+    obj = os.path.join(OBJ, unit.replace(".cu", ".o").replace(".cpp", ".o"))
     if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
             and os.path.getmtime(obj) > hdr_time):
         return obj, ""
-    cmd = [NVCC] + ARCH + COMMON + EXTRA + flags + ["-c", "-o", obj, src]
+    if unit.endswith(".cpp"):      # plain host C++ (no CUDA front end: x86 intrinsics headers stay out of cudafe's way)
+        cmd = [CXX, "-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden"] + flags + ["-c", "-o", obj, src]
+    else:
+        cmd = [NVCC] + ARCH + COMMON + EXTRA + flags + ["-c", "-o", obj, src]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (unit, p.stdout, p.stderr))
@@ -55,7 +61,7 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     units = dict(UNITS)
     for f in sorted(os.listdir(CSRC)):
-        if f.endswith(".cu") and f not in units:
+        if f.endswith((".cu", ".cpp")) and f not in units:
             units[f] = []
     hdr_time = _newest_header()
     objs = []

@@ -418,8 +418,16 @@ int secp256k1_b200_ecmult_multi(secp256k1_b200_engine* e, unsigned char* out64, 
     return 1;
 }
 
+extern "C" int b200_host_halfagg_z_chain(uint8_t* z32, const uint32_t* mid, const uint8_t* aggsig, const uint8_t* pk32, const uint8_t* msgs32, size_t n,
+                                         int force_portable);
 /* ---- BIP-340 half-aggregation ------------------------------------------------------------ */
 size_t secp256k1_b200_schnorrsig_aggverify_workspace_bytes(size_t n) { return halfagg_workspace_bytes(n); }
+int secp256k1_b200_halfagg_randomizers(unsigned char* z32, const unsigned char* pubkeys32, const unsigned char* msgs32, size_t n, const unsigned char* aggsig,
+                                       int force_portable) {
+    sha256 h;
+    sha256_init_tagged(h, (const uint8_t*)"HalfAgg/randomizer", 18);
+    return b200_host_halfagg_z_chain(z32, h.s, aggsig, pubkeys32, msgs32, n, force_portable);
+}
 int secp256k1_b200_schnorrsig_aggverify_dev(secp256k1_b200_engine* e, unsigned char* d_ok, const unsigned char* d_pubkeys32, const unsigned char* d_msgs32,
                                             size_t n, const unsigned char* d_aggsig, void* d_workspace, size_t workspace_bytes, void* stream) {
     if (!e) { set_error("engine is NULL"); return 0; }
@@ -451,11 +459,7 @@ int secp256k1_b200_schnorrsig_aggverify(secp256k1_b200_engine* e, int* ok, const
     std::vector<uint8_t> z(32 * n + 32);
     const bool timing = getenv("SECP256K1_B200_TIMING") != nullptr;
     auto t0 = std::chrono::steady_clock::now();
-    {
-        halfagg_midstate hm;
-        for (int i = 0; i < 8; i++) hm.s[i] = e->mid_halfagg[i];
-        halfagg_z_chain(z.data(), hm, aggsig, pubkeys32, msgs32, n);
-    }
+    b200_host_halfagg_z_chain(z.data(), e->mid_halfagg, aggsig, pubkeys32, msgs32, n, 0);     // host_sha256.cpp (SHA extensions when present)
     auto t1 = std::chrono::steady_clock::now();
     if (n) CK(cudaMemcpyAsync(c.at(oz), z.data(), 32 * n, cudaMemcpyHostToDevice, e->stream));
     CK(launch_halfagg_verify(c.at(oo), c.at(opk), c.at(om), n, c.at(oa), n ? c.at(oz) : nullptr, e->mid_halfagg, e->mid, c.at(ow), wsb, e->stream, &e->launches));

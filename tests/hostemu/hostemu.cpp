@@ -206,6 +206,12 @@ int emu_surjection_verify(const uint8_t* proof, size_t plen, const uint8_t* in_t
     tab_local tab; return surjection_verify_item(proof, plen, in_tags64, n_tags, out_tag64, g_gt, tab);
 }
 int emu_pedersen_tally(const uint8_t* pos33, uint32_t pcnt, const uint8_t* neg33, uint32_t ncnt) { return pedersen_tally_item(pos33, pcnt, neg33, ncnt); }
+void emu_halfagg_z_chain(uint8_t* z32, const uint8_t* pk32, const uint8_t* msgs32, size_t n, const uint8_t* aggsig) {
+    halfagg_midstate hm; sha256 h;
+    sha256_init_tagged(h, (const uint8_t*)"HalfAgg/randomizer", 18);
+    for (int i = 0; i < 8; i++) hm.s[i] = h.s[i];
+    halfagg_z_chain(z32, hm, aggsig, pk32, msgs32, n);
+}
 int emu_halfagg_verify(const uint8_t* pk32, const uint8_t* msgs32, size_t n, const uint8_t* aggsig, size_t aggsig_len) {
     halfagg_midstate hm; bip340_midstate bm; sha256 h;
     sha256_init_tagged(h, (const uint8_t*)"HalfAgg/randomizer", 18);

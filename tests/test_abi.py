@@ -37,3 +37,28 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(b200.B200Error):
         b200.Engine()
+
+
+def test_halfagg_randomizer_chain_host_paths():
+    """the host walker of the half-aggregation randomizer chain (SHA-extension and portable paths, no GPU needed) against the
+    device-header implementation compiled for the host, and z_1 against hashlib"""
+    import hashlib
+    import numpy as np
+    from tests import hostemu_lib
+    import secp256k1_zkp_b200 as b200
+    lib = ctypes.CDLL(b200.library_path())
+    emu = hostemu_lib.load()
+    rng = np.random.default_rng(11)
+    for n in (0, 1, 2, 3, 64, 1001):
+        pk, msg, agg = rng.integers(0, 256, 32 * n + 1, dtype=np.uint8).tobytes(), rng.integers(0, 256, 32 * n + 1, dtype=np.uint8).tobytes(), rng.integers(0, 256, 32 * (n + 1), dtype=np.uint8).tobytes()
+        want = ctypes.create_string_buffer(32 * n + 32)
+        emu.emu_halfagg_z_chain(want, pk, msg, ctypes.c_size_t(n), agg)
+        for force in (0, 1):
+            got = ctypes.create_string_buffer(32 * n + 32)
+            used = lib.secp256k1_b200_halfagg_randomizers(got, pk, msg, ctypes.c_size_t(n), agg, force)
+            assert got.raw[:32 * n] == want.raw[:32 * n], (n, force)
+            assert not (force and used)
+        if n >= 2:
+            th = hashlib.sha256(b"HalfAgg/randomizer").digest()
+            h = hashlib.sha256(th + th + b"".join(agg[32 * i:32 * i + 32] + pk[32 * i:32 * i + 32] + msg[32 * i:32 * i + 32] for i in range(2)))
+            assert want.raw[32:64] == h.digest() and want.raw[:32] == (1).to_bytes(32, "big")
