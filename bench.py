@@ -182,7 +182,7 @@ def _time_dev(torch, dist, world, fn, warm=2, reps=5):
     return float(t[0])
 
 
-def run_extra_workloads(eng, b200, torch, dist, D, dev, stream, rank, world, imad_peak):
+def run_extra_workloads(eng, b200_mod, torch, dist, D, dev, stream, rank, world, imad_peak):
     import numpy as np
     out = {}
     gold = os.path.join(ROOT, "tests", "golden")
@@ -268,6 +268,44 @@ def run_extra_workloads(eng, b200, torch, dist, D, dev, stream, rank, world, ima
     out["bppp_norm_verify_16g8h"] = {"proofs": per * world, "per_gpu": per, "ms": ms, "verify_per_s": per * world / ms * 1e3, "scaling": "weak",
                                      "accept_pattern_ok": bool(np.array_equal(okb.cpu().numpy(), expb)),
                                      "note": "norm-product argument only: this reference snapshot has no full BP++ range proof (SURVEY fact 3)"}
+    del d
+    # ---- ECDSA public-key recovery, 2^18 per GPU: r = x of a BIP-340 nonce point (always liftable), s random
+    per = 1 << 18
+    gen = torch.Generator(device=dev); gen.manual_seed(4242 + rank)
+    sk = torch.randint(0, 256, (per, 32), dtype=torch.uint8, device=dev, generator=gen); sk[:, 0] &= 0x7F; sk[:, 31] |= 1
+    msg = torch.randint(0, 256, (per, 32), dtype=torch.uint8, device=dev, generator=gen)
+    sig = torch.empty((per, 64), dtype=torch.uint8, device=dev); pk = torch.empty((per, 32), dtype=torch.uint8, device=dev)
+    eng.testdata_schnorrsig_sign_dev(sig.data_ptr(), pk.data_ptr(), sk.data_ptr(), msg.data_ptr(), 32, per, stream)
+    rsig = sig.clone(); rsig[:, 32] &= 0x7F
+    rid = torch.randint(0, 2, (per,), dtype=torch.uint8, device=dev, generator=gen)
+    okc = torch.empty(per, dtype=torch.uint8, device=dev); rec = torch.empty((per, 64), dtype=torch.uint8, device=dev)
+
+    def rec_step():
+        eng.ecdsa_recover_dev(okc.data_ptr(), rec.data_ptr(), rsig.data_ptr(), rid.data_ptr(), msg.data_ptr(), per, stream)
+    ms = _time_dev(torch, dist, world, rec_step, warm=1, reps=3)
+    # property check: a recovered key verifies the signature it was recovered from (low-s form, as secp256k1_ecdsa_verify demands)
+    chk = 4096
+    s_host = rsig[:chk].cpu().numpy().copy()
+    N_ORD = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+    for j in range(chk):
+        sv = int.from_bytes(s_host[j, 32:].tobytes(), "big")
+        if sv > N_ORD // 2:
+            s_host[j, 32:] = np.frombuffer((N_ORD - sv).to_bytes(32, "big"), dtype=np.uint8)
+    rk = rec[:chk].cpu().numpy()
+    comp = np.concatenate([(2 + (rk[:, 63] & 1))[:, None].astype(np.uint8), rk[:, :32]], axis=1)
+    vok = eng.ecdsa_verify(s_host, msg[:chk].cpu().numpy(), comp, b200_mod.SIG_COMPACT64, b200_mod.PK_COMPRESSED33)
+    out["ecdsa_recover"] = {"signatures": per * world, "per_gpu": per, "ms": ms, "recover_per_s": per * world / ms * 1e3, "scaling": "weak",
+                            "all_recovered": bool(okc.all()), "recovered_keys_verify": bool(vok.all())}
+    # ---- one half-aggregate signature over the same 2^18 (key, message, r) triples per GPU, device part only
+    # (terms + 2n+1-term MSM; the serial randomizer hash is host work and is reported by tools/devbench2.py)
+    agg = torch.cat([sig[:, :32].reshape(-1), torch.zeros(32, dtype=torch.uint8, device=dev)]).contiguous()
+    wsb = eng.schnorrsig_aggverify_workspace_bytes(per)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev); okb1 = torch.zeros(1, dtype=torch.uint8, device=dev)
+    h_ok = eng.schnorrsig_aggverify(pk.cpu().numpy(), msg.cpu().numpy(), agg.cpu().numpy())       # s = 0: must be rejected
+    t0 = time.perf_counter()
+    eng.schnorrsig_aggverify(pk.cpu().numpy(), msg.cpu().numpy(), agg.cpu().numpy())
+    out["schnorrsig_aggverify"] = {"signatures_per_aggregate": per, "host_call_ms": (time.perf_counter() - t0) * 1e3, "rejects_wrong_s": h_ok == 0,
+                                   "note": "host-buffer call incl. the serial randomizer hash chain on the host; each rank verifies its own aggregate"}
     return out
 
 
