@@ -22,6 +22,7 @@
  *                                       src/modules/generator/main_impl.h:309) + _commitment_serialize (:281)
  *   secp256k1_b200_rangeproof_verify_batch   secp256k1_rangeproof_verify (include/secp256k1_rangeproof.h:70,
  *                                       src/modules/rangeproof/main_impl.h:54)
+ *   secp256k1_b200_rangeproof_rewind_batch   secp256k1_rangeproof_rewind (include/secp256k1_rangeproof.h:95, main_impl.h:31)
  *   secp256k1_b200_ecmult_multi         static secp256k1_ecmult_multi_var (src/ecmult.h:62, src/ecmult_impl.h:823)
  *   secp256k1_b200_bppp_norm_verify_batch    static secp256k1_bppp_rangeproof_norm_product_verify
  *                                       (src/modules/bppp/bppp_norm_product_impl.h:425)
@@ -225,6 +226,23 @@ SECP256K1_B200_API int secp256k1_b200_rangeproof_verify_batch_dev(secp256k1_b200
         const unsigned char *d_commit33, const unsigned char *d_proofs, size_t proof_stride, const uint32_t *d_plen,
         const unsigned char *d_gen64, size_t gen_stride, const unsigned char *d_extra, size_t extra_stride, const uint32_t *d_extra_len,
         size_t n, void *stream);
+
+/* Rewinding: secp256k1_rangeproof_rewind (include/secp256k1_rangeproof.h:95, src/modules/rangeproof/main_impl.h:31; rangeproof_impl.h:61-112,
+ * :354-471, :653-681).  Verifies like the call above and, with the 32-byte nonce the prover used, recovers per proof the blinding factor
+ * (blind32), the proven value, and the embedded message (up to message_stride bytes per proof into message + i*message_stride,
+ * message_len[i] = bytes recovered; message may be NULL).  ok[i] = 1 only if the proof verifies AND the recovered (value, blind)
+ * rebuild the commitment; otherwise blind/value/message_len are zero.  The _dev form needs a device workspace of
+ * secp256k1_b200_rangeproof_rewind_workspace_bytes(n) bytes (the ring challenges, 4096 per proof). */
+SECP256K1_B200_API size_t secp256k1_b200_rangeproof_rewind_workspace_bytes(size_t n);
+SECP256K1_B200_API int secp256k1_b200_rangeproof_rewind_batch(secp256k1_b200_engine *e, unsigned char *ok, unsigned char *blind32, uint64_t *value,
+        unsigned char *message, size_t message_stride, uint32_t *message_len, uint64_t *min_value, uint64_t *max_value,
+        const unsigned char *nonce32, const unsigned char *commit33, const unsigned char *proofs, size_t proof_stride, const uint32_t *plen,
+        const unsigned char *gen64, size_t gen_stride, const unsigned char *extra, size_t extra_stride, const uint32_t *extra_len, size_t n);
+SECP256K1_B200_API int secp256k1_b200_rangeproof_rewind_batch_dev(secp256k1_b200_engine *e, unsigned char *d_ok, unsigned char *d_blind32, uint64_t *d_value,
+        unsigned char *d_message, size_t message_stride, uint32_t *d_message_len, uint64_t *d_min_value, uint64_t *d_max_value,
+        const unsigned char *d_nonce32, const unsigned char *d_commit33, const unsigned char *d_proofs, size_t proof_stride, const uint32_t *d_plen,
+        const unsigned char *d_gen64, size_t gen_stride, const unsigned char *d_extra, size_t extra_stride, const uint32_t *d_extra_len, size_t n,
+        void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* ---- synthetic inputs for tests and benchmarks (NOT constant time; never use with real secrets) ---- */
 /* BIP-340 signatures exactly as secp256k1_schnorrsig_sign_custom(ctx, sig, msg, msglen, keypair, NULL) emits them

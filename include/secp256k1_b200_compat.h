@@ -77,6 +77,11 @@ SECP256K1_B200_API int secp256k1_rangeproof_verify(const secp256k1_context *ctx,
 SECP256K1_B200_API int secp256k1_rangeproof_info(const secp256k1_context *ctx, int *exp, int *mantissa, uint64_t *min_value, uint64_t *max_value,
         const unsigned char *proof, size_t plen);
 
+/* include/secp256k1_rangeproof.h:95 */
+SECP256K1_B200_API int secp256k1_rangeproof_rewind(const secp256k1_context *ctx, unsigned char *blind_out, uint64_t *value_out, unsigned char *message_out,
+        size_t *outlen, const unsigned char *nonce, uint64_t *min_value, uint64_t *max_value, const secp256k1_pedersen_commitment *commit,
+        const unsigned char *proof, size_t plen, const unsigned char *extra_commit, size_t extra_commit_len, const secp256k1_generator *gen);
+
 /* include/secp256k1_schnorrsig_halfagg.h:103 */
 SECP256K1_B200_API int secp256k1_schnorrsig_aggverify(const secp256k1_context *ctx, const secp256k1_xonly_pubkey *pubkeys, const unsigned char *msgs32,
         size_t n, const unsigned char *aggsig, size_t aggsig_len);

@@ -365,6 +365,41 @@ REF_EXPORT void ref_rangeproof_verify_batch(const secp256k1_context *ctx, unsign
     }
 }
 
+/* rangeproof with an embedded message and an explicit nonce (sign: main_impl.h:72), and the rewinding call (main_impl.h:31) */
+REF_EXPORT int ref_rangeproof_make_msg_batch(const secp256k1_context *ctx, unsigned char *proofs, size_t stride, size_t *plen,
+        unsigned char *commit33, const unsigned char *blind32, const uint64_t *value, const uint64_t *min_value,
+        const int *exp, const int *min_bits, const unsigned char *nonce32, const unsigned char *msg, size_t msg_stride, const size_t *msg_len,
+        const unsigned char *extra, size_t extra_len, const secp256k1_generator *gen, size_t n) {
+    size_t i;
+    for (i = 0; i < n; i++) {
+        secp256k1_pedersen_commitment c;
+        size_t l = stride;
+        if (!secp256k1_pedersen_commit(ctx, &c, blind32 + 32 * i, value[i], gen)) return 0;
+        if (!secp256k1_rangeproof_sign(ctx, proofs + stride * i, &l, min_value[i], &c, blind32 + 32 * i, nonce32 + 32 * i, exp[i], min_bits[i],
+                                       value[i], msg_len[i] ? msg + msg_stride * i : NULL, msg_len[i], extra_len ? extra : NULL, extra_len, gen)) return 0;
+        plen[i] = l;
+        secp256k1_pedersen_commitment_serialize(ctx, commit33 + 33 * i, &c);
+    }
+    return 1;
+}
+REF_EXPORT void ref_rangeproof_rewind_batch(const secp256k1_context *ctx, unsigned char *ok, unsigned char *blind_out32, uint64_t *value_out,
+        unsigned char *msg_out, size_t msg_cap, size_t *msg_len_out, uint64_t *min_value, uint64_t *max_value, const unsigned char *nonce32,
+        const unsigned char *commit33, const unsigned char *proofs, size_t stride, const size_t *plen,
+        const unsigned char *extra, size_t extra_len, const secp256k1_generator *gen, size_t n) {
+    size_t i;
+    for (i = 0; i < n; i++) {
+        secp256k1_pedersen_commitment c;
+        size_t ml = msg_cap;
+        ok[i] = 0; min_value[i] = 0; max_value[i] = 0; value_out[i] = 0; msg_len_out[i] = 0;
+        memset(blind_out32 + 32 * i, 0, 32);
+        if (!secp256k1_pedersen_commitment_parse(ctx, &c, commit33 + 33 * i)) continue;
+        ok[i] = (unsigned char)secp256k1_rangeproof_rewind(ctx, blind_out32 + 32 * i, &value_out[i], msg_cap ? msg_out + msg_cap * i : NULL, msg_cap ? &ml : NULL,
+                    nonce32 + 32 * i, &min_value[i], &max_value[i], &c, proofs + stride * i, plen[i], extra_len ? extra : NULL, extra_len, gen);
+        if (ok[i]) msg_len_out[i] = msg_cap ? ml : 0;
+        else { value_out[i] = 0; memset(blind_out32 + 32 * i, 0, 32); }
+    }
+}
+
 /* ---- BP++ norm-product argument (bppp_norm_product_impl.h:105,:223,:425) -- */
 /* The transcript is initialised exactly as the reference tests do
  * (modules/bppp/tests_impl.h:273-311): tagged "Bulletproofs_pp/v0/commitment"

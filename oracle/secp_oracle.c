@@ -522,9 +522,106 @@ static void borromean_hash(unsigned char *out, const unsigned char *m, size_t ml
     sha256_t h; unsigned char ring[4] = {ridx >> 24, ridx >> 16, ridx >> 8, ridx}, epos[4] = {eidx >> 24, eidx >> 16, eidx >> 8, eidx};
     sha_init(&h); sha_write(&h, e, elen); sha_write(&h, m, mlen); sha_write(&h, ring, 4); sha_write(&h, epos, 4); sha_final(&h, out);
 }
-int orc_rangeproof_verify(uint64_t *min_value, uint64_t *max_value, const unsigned char *commit33, const unsigned char *proof, size_t plen,
+/* ---- rewinding: hash_impl.h:211-314 (HMAC-SHA256, RFC 6979 generator), rangeproof_impl.h:61-112 (genrand), :334-350, :354-471 --- */
+typedef struct { sha256_t inner, outer; } hmac_t;
+static void hmac_init(hmac_t *h, const unsigned char *key, size_t keylen) {
+    unsigned char rkey[64]; size_t n;
+    memset(rkey, 0, 64); memcpy(rkey, key, keylen);            /* keylen <= 64 on this path */
+    for (n = 0; n < 64; n++) rkey[n] ^= 0x5c;
+    sha_init(&h->outer); sha_write(&h->outer, rkey, 64);
+    for (n = 0; n < 64; n++) rkey[n] ^= 0x5c ^ 0x36;
+    sha_init(&h->inner); sha_write(&h->inner, rkey, 64);
+}
+static void hmac_final(hmac_t *h, unsigned char *out32) {
+    unsigned char t[32];
+    sha_final(&h->inner, t); sha_write(&h->outer, t, 32); sha_final(&h->outer, out32);
+}
+typedef struct { unsigned char v[32], k[32]; int retry; } rfc6979_t;
+static void rfc6979_init(rfc6979_t *r, const unsigned char *key, size_t keylen) {
+    hmac_t h; unsigned char sep;
+    memset(r->v, 1, 32); memset(r->k, 0, 32);
+    for (sep = 0; sep < 2; sep++) {
+        hmac_init(&h, r->k, 32); sha_write(&h.inner, r->v, 32); sha_write(&h.inner, &sep, 1); sha_write(&h.inner, key, keylen); hmac_final(&h, r->k);
+        hmac_init(&h, r->k, 32); sha_write(&h.inner, r->v, 32); hmac_final(&h, r->v);
+    }
+    r->retry = 0;
+}
+static void rfc6979_gen32(rfc6979_t *r, unsigned char *out32) {
+    hmac_t h; unsigned char zero = 0;
+    if (r->retry) {
+        hmac_init(&h, r->k, 32); sha_write(&h.inner, r->v, 32); sha_write(&h.inner, &zero, 1); hmac_final(&h, r->k);
+        hmac_init(&h, r->k, 32); sha_write(&h.inner, r->v, 32); hmac_final(&h, r->v);
+    }
+    hmac_init(&h, r->k, 32); sha_write(&h.inner, r->v, 32); hmac_final(&h, r->v);
+    memcpy(out32, r->v, 32);
+    r->retry = 1;
+}
+static void rp_genrand(sc *sec, sc *s, unsigned char *message, const size_t *rsizes, size_t rings, const unsigned char *nonce,
+                       const ge *commit, const unsigned char *proof, size_t len, const ge *genp) {
+    unsigned char tmp[32], seed[32 + 33 + 33 + 10]; rfc6979_t rng; sc acc = {{0, 0, 0, 0}}; size_t i, j, npub = 0; int b, overflow;
+    memcpy(seed, nonce, 32); rp_serialize_point(seed + 32, commit); rp_serialize_point(seed + 65, genp); memcpy(seed + 98, proof, len);
+    rfc6979_init(&rng, seed, 98 + len);
+    for (i = 0; i < rings; i++) {
+        if (i < rings - 1) {
+            rfc6979_gen32(&rng, tmp);
+            do { rfc6979_gen32(&rng, tmp); overflow = sc_set_b32(&sec[i], tmp); } while (overflow || u256_is_zero(&sec[i]));
+            sc_add(&acc, &acc, &sec[i]);
+        } else sc_neg(&sec[i], &acc);
+        for (j = 0; j < rsizes[i]; j++) {
+            rfc6979_gen32(&rng, tmp);
+            for (b = 0; b < 32; b++) { tmp[b] ^= message[(i * 4 + j) * 32 + b]; message[(i * 4 + j) * 32 + b] = tmp[b]; }
+            sc_set_b32(&s[npub], tmp);
+            npub++;
+        }
+    }
+}
+static void rp_recover_x(sc *x, const sc *k, const sc *e, const sc *s) { sc t; sc_neg(x, s); sc_add(x, x, k); sc_inv(&t, e); sc_mul(x, x, &t); }
+static int rp_rewind_inner(sc *blind, uint64_t *v, unsigned char *m, size_t *mlen, const sc *ev, const sc *s, const size_t *rsizes, size_t rings,
+                           const unsigned char *nonce, const ge *commit, const unsigned char *proof, size_t len, const ge *genp) {
+    sc s_orig[128], sec[32], stmp; unsigned char prep[4096], tmp[32]; uint64_t value = 0; size_t offset, i, j, npub, skip1, skip2; int b;
+    memset(prep, 0, 4096);
+    rp_genrand(sec, s_orig, prep, rsizes, rings, nonce, commit, proof, len, genp);
+    *v = UINT64_MAX;
+    if (rings == 1 && rsizes[0] == 1) { rp_recover_x(blind, &s_orig[0], &ev[0], &s[0]); *v = 0; if (mlen) *mlen = 0; return 1; }
+    npub = (rings - 1) << 2;
+    for (j = 0; j < 2; j++) {
+        size_t idx = npub + rsizes[rings - 1] - 1 - j;
+        u256_to_be(tmp, &s[idx]);
+        for (b = 0; b < 32; b++) tmp[b] ^= prep[idx * 32 + b];
+        if ((tmp[0] & 128) && memcmp(tmp + 16, tmp + 24, 8) == 0 && memcmp(tmp + 8, tmp + 16, 8) == 0) {
+            for (i = 0; i < 8; i++) value = (value << 8) + tmp[24 + i];
+            *v = value; memcpy(prep + idx * 32, tmp, 32);
+            break;
+        }
+    }
+    if (j > 1) { if (mlen) *mlen = 0; return 0; }
+    skip1 = rsizes[rings - 1] - 1 - j; skip2 = (value >> ((rings - 1) << 1)) & 3;
+    if (skip1 == skip2) { if (mlen) *mlen = 0; return 0; }
+    skip1 += (rings - 1) << 2; skip2 += (rings - 1) << 2;
+    rp_recover_x(&stmp, &s_orig[skip2], &ev[skip2], &s[skip2]);
+    sc_neg(&sec[rings - 1], &sec[rings - 1]);
+    sc_add(blind, &stmp, &sec[rings - 1]);
+    if (!m || !mlen || *mlen == 0) { if (mlen) *mlen = 0; return 1; }
+    offset = 0; npub = 0;
+    for (i = 0; i < rings; i++) {
+        size_t idx = (value >> (i << 1)) & 3;
+        for (j = 0; j < rsizes[i]; j++) {
+            if (npub == skip1 || npub == skip2) { npub++; continue; }
+            if (idx == j) { sc t; sc_mul(&t, &sec[i], &ev[npub]); sc_add(&stmp, &s[npub], &t); } else stmp = s[npub];
+            u256_to_be(tmp, &stmp);
+            for (b = 0; b < 32; b++) tmp[b] ^= prep[npub * 32 + b];
+            for (b = 0; b < 32 && offset < *mlen; b++) m[offset++] = tmp[b];
+            npub++;
+        }
+    }
+    *mlen = offset;
+    return 1;
+}
+
+static int rangeproof_verify_impl(unsigned char *blind_out, uint64_t *value_out, unsigned char *message_out, size_t *outlen, const unsigned char *nonce,
+                          uint64_t *min_value, uint64_t *max_value, const unsigned char *commit33, const unsigned char *proof, size_t plen,
                           const unsigned char *extra, size_t extra_len, const unsigned char *gen64) {
-    ge commit, genp, c; gej accj, pubs[128], base; sc s[128]; sha256_t sha_m, sha_e0;
+    ge commit, genp, c; gej accj, pubs[128], base; sc s[128], evalues[128]; sha256_t sha_m, sha_e0; size_t offset_post_header;
     size_t rsizes[32], rings, npub, offset = 0, i, j, count; int exp, mantissa, has_nz, has_min; uint64_t scale;
     unsigned char signs[31], m[33], tmp[33]; const unsigned char *e0;
     if (!commitment_parse(&commit, commit33)) return 0;
@@ -549,6 +646,7 @@ int orc_rangeproof_verify(uint64_t *min_value, uint64_t *max_value, const unsign
     }
     if (*max_value > UINT64_MAX - *min_value) return 0;
     *max_value += *min_value;
+    offset_post_header = offset;
     /* ring layout (:566-586) */
     rings = 1; rsizes[0] = 1; npub = 1;
     if (mantissa != 0) {
@@ -604,6 +702,7 @@ int orc_rangeproof_verify(uint64_t *min_value, uint64_t *max_value, const unsign
         for (j = 0; j < rsizes[i]; j++) {
             gej rgej; ge rge;
             if (overflow || u256_is_zero(&s[count]) || u256_is_zero(&ens) || pubs[count].inf) return 0;
+            evalues[count] = ens;
             ecmult(&rgej, &pubs[count], &ens, &s[count]);
             if (rgej.inf) return 0;
             ge_set_gej(&rge, &rgej);
@@ -614,7 +713,32 @@ int orc_rangeproof_verify(uint64_t *min_value, uint64_t *max_value, const unsign
         }
     }
     sha_write(&sha_e0, m, 32); sha_final(&sha_e0, tmp);
-    return memcmp(e0, tmp, 32) == 0;
+    if (memcmp(e0, tmp, 32) != 0) return 0;
+    if (nonce) {                                               /* rewind (:653-681) */
+        sc blind, vs; uint64_t vv; gej bj, vj, gj;
+        memset(&blind, 0, sizeof(blind));
+        if (!rp_rewind_inner(&blind, &vv, message_out, outlen, evalues, s, rsizes, rings, nonce, &commit, proof, offset_post_header, &genp)) return 0;
+        vv = vv * scale + *min_value;
+        gej_set_ge(&gj, &GEN_G); gej_mul(&bj, &gj, &blind);
+        sc_set_u64(&vs, vv); gej_set_ge(&gj, &genp); gej_mul(&vj, &gj, &vs);
+        gej_add(&accj, &bj, &vj);
+        if (accj.inf) return 0;
+        gej_neg(&accj, &accj); gej_add_ge(&accj, &accj, &commit);
+        if (!accj.inf) return 0;
+        if (blind_out) u256_to_be(blind_out, &blind);
+        if (value_out) *value_out = vv;
+    }
+    return 1;
+}
+int orc_rangeproof_verify(uint64_t *min_value, uint64_t *max_value, const unsigned char *commit33, const unsigned char *proof, size_t plen,
+                          const unsigned char *extra, size_t extra_len, const unsigned char *gen64) {
+    return rangeproof_verify_impl(NULL, NULL, NULL, NULL, NULL, min_value, max_value, commit33, proof, plen, extra, extra_len, gen64);
+}
+/* secp256k1_rangeproof_rewind (main_impl.h:31-52): *outlen = capacity in, bytes recovered out */
+int orc_rangeproof_rewind(unsigned char *blind_out32, uint64_t *value_out, unsigned char *message_out, size_t *outlen, const unsigned char *nonce32,
+                          uint64_t *min_value, uint64_t *max_value, const unsigned char *commit33, const unsigned char *proof, size_t plen,
+                          const unsigned char *extra, size_t extra_len, const unsigned char *gen64) {
+    return rangeproof_verify_impl(blind_out32, value_out, message_out, outlen, nonce32, min_value, max_value, commit33, proof, plen, extra, extra_len, gen64);
 }
 
 /* ---- surjection proof verify: modules/surjection/main_impl.h:46-83 (parse), :360-402 (verify), surjection_impl.h:18-36, :66-92 */

@@ -44,6 +44,9 @@ ORC_API int  orc_generator_parse(unsigned char *gen64, const unsigned char *gen3
 ORC_API int  orc_rangeproof_verify(uint64_t *min_value, uint64_t *max_value, const unsigned char *commit33,
                                    const unsigned char *proof, size_t plen, const unsigned char *extra, size_t extra_len,
                                    const unsigned char *gen64);
+ORC_API int  orc_rangeproof_rewind(unsigned char *blind_out32, uint64_t *value_out, unsigned char *message_out, size_t *outlen, const unsigned char *nonce32,
+                          uint64_t *min_value, uint64_t *max_value, const unsigned char *commit33, const unsigned char *proof, size_t plen,
+                          const unsigned char *extra, size_t extra_len, const unsigned char *gen64);
 
 ORC_API int  orc_surjectionproof_verify(const unsigned char *proof, size_t plen, const unsigned char *in_tags64, size_t n_tags, const unsigned char *out_tag64);
 ORC_API int  orc_pedersen_verify_tally(const unsigned char *pos33, size_t pcnt, const unsigned char *neg33, size_t ncnt);

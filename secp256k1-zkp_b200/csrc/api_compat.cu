@@ -422,6 +422,36 @@ int secp256k1_rangeproof_verify(const secp256k1_context* ctx, uint64_t* min_valu
     return ok;
 }
 
+// secp256k1_rangeproof_rewind (modules/rangeproof/main_impl.h:31-52).  *outlen: capacity in, recovered bytes out (0 when nothing was recovered).
+int secp256k1_rangeproof_rewind(const secp256k1_context* ctx, unsigned char* blind_out, uint64_t* value_out, unsigned char* message_out, size_t* outlen,
+                                const unsigned char* nonce, uint64_t* min_value, uint64_t* max_value, const secp256k1_pedersen_commitment* commit,
+                                const unsigned char* proof, size_t plen, const unsigned char* extra_commit, size_t extra_commit_len, const secp256k1_generator* gen) {
+    ARG_CHECK(commit != NULL);
+    ARG_CHECK(proof != NULL);
+    ARG_CHECK(min_value != NULL);
+    ARG_CHECK(max_value != NULL);
+    ARG_CHECK(message_out != NULL || outlen == NULL);
+    ARG_CHECK(nonce != NULL);
+    ARG_CHECK(extra_commit != NULL || extra_commit_len == 0);
+    ARG_CHECK(gen != NULL);
+    ARG_CHECK(ctx->proper);                       // ecmult_gen context built (:47)
+    if (plen > 0xFFFFFFFFull || extra_commit_len > 0xFFFFFFFFull) return 0;
+    ENGINE_OR_FAIL(e);
+    unsigned char ok = 0, blind[32];
+    uint32_t pl = (uint32_t)plen, el = (uint32_t)extra_commit_len, ml = 0;
+    uint64_t mn = 0, mx = 0, value = 0;
+    size_t cap = (message_out && outlen) ? (*outlen > 4096 ? 4096 : *outlen) : 0;       // at most 4096 message bytes exist (rangeproof_impl.h:359)
+    GPU_CALL(secp256k1_b200_rangeproof_rewind_batch(e, &ok, blind, &value, cap ? message_out : NULL, cap, &ml, &mn, &mx, nonce, commit->data, proof,
+                                                    plen ? plen : 1, &pl, gen->data, 0, extra_commit_len ? extra_commit : NULL, extra_commit_len,
+                                                    extra_commit_len ? &el : NULL, 1));
+    if (plen >= 65 && (proof[0] & 128) == 0) { *min_value = mn; *max_value = mx; }
+    if (!ok) return 0;
+    if (blind_out) memcpy(blind_out, blind, 32);
+    if (value_out) *value_out = value;
+    if (outlen) *outlen = ml;
+    return 1;
+}
+
 // ---- surjection proofs (modules/surjection/main_impl.h) and commitment tallies ------------------------------------------
 static size_t count_bits(const unsigned char* p, size_t n) { size_t c = 0; for (size_t i = 0; i < n; i++) for (int k = 0; k < 8; k++) c += (p[i] >> k) & 1; return c; }
 int secp256k1_surjectionproof_parse(const secp256k1_context* ctx, secp256k1_surjectionproof* proof, const unsigned char* input, size_t inputlen) {

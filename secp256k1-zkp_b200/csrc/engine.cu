@@ -727,4 +727,74 @@ int secp256k1_b200_rangeproof_verify_batch(secp256k1_b200_engine* e, unsigned ch
     return 1;
 }
 
+/* ---- range-proof rewinding: verify (one warp per proof, challenges kept) + replay (one thread per proof) ---- */
+size_t secp256k1_b200_rangeproof_rewind_workspace_bytes(size_t n) { return 4096 * n + 256; }
+int secp256k1_b200_rangeproof_rewind_batch_dev(secp256k1_b200_engine* e, unsigned char* d_ok, unsigned char* d_blind32, uint64_t* d_value,
+                                               unsigned char* d_message, size_t message_stride, uint32_t* d_message_len,
+                                               uint64_t* d_min_value, uint64_t* d_max_value, const unsigned char* d_nonce32,
+                                               const unsigned char* d_commit33, const unsigned char* d_proofs, size_t proof_stride,
+                                               const uint32_t* d_plen, const unsigned char* d_gen64, size_t gen_stride, const unsigned char* d_extra,
+                                               size_t extra_stride, const uint32_t* d_extra_len, size_t n, void* d_workspace, size_t workspace_bytes,
+                                               void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (gen_stride != 0 && gen_stride < 64) { set_error("gen_stride must be 0 (shared generator) or >= 64"); return 0; }
+    if (workspace_bytes < secp256k1_b200_rangeproof_rewind_workspace_bytes(n)) { set_error("rangeproof_rewind: workspace too small (see secp256k1_b200_rangeproof_rewind_workspace_bytes)"); return 0; }
+    if (d_message && message_stride == 0) { set_error("rangeproof_rewind: message_stride is 0"); return 0; }
+    device_guard guard(e->device);
+    uint8_t* ev = (uint8_t*)d_workspace;
+    CK(launch_rangeproof_verify(d_ok, d_min_value, d_max_value, d_commit33, d_proofs, proof_stride, d_plen, d_gen64, gen_stride,
+                                d_extra, extra_stride, d_extra_len, n, e->gt(), (cudaStream_t)stream, &e->launches, ev));
+    CK(launch_rangeproof_rewind(d_ok, d_blind32, d_value, d_message, message_stride, d_message_len, d_nonce32, d_commit33, d_proofs, proof_stride,
+                                d_plen, d_gen64, gen_stride, ev, n, e->gt(), (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_rangeproof_rewind_batch(secp256k1_b200_engine* e, unsigned char* ok, unsigned char* blind32, uint64_t* value,
+                                           unsigned char* message, size_t message_stride, uint32_t* message_len, uint64_t* min_value, uint64_t* max_value,
+                                           const unsigned char* nonce32, const unsigned char* commit33, const unsigned char* proofs, size_t proof_stride,
+                                           const uint32_t* plen, const unsigned char* gen64, size_t gen_stride, const unsigned char* extra,
+                                           size_t extra_stride, const uint32_t* extra_len, size_t n) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (gen_stride != 0 && gen_stride < 64) { set_error("gen_stride must be 0 (shared generator) or >= 64"); return 0; }
+    if (message && message_stride == 0) { set_error("rangeproof_rewind: message_stride is 0"); return 0; }
+    if (n == 0) return 1;
+    for (size_t i = 0; i < n; i++) {
+        if (plen[i] > proof_stride) { set_error("rangeproof_rewind_batch: plen[i] > proof_stride"); return 0; }
+        if (extra && extra_len && extra_len[i] > extra_stride) { set_error("rangeproof_rewind_batch: extra_len[i] > extra_stride"); return 0; }
+    }
+    std::lock_guard<std::mutex> lock(e->mu);
+    device_guard guard(e->device);
+    carver c(e);
+    size_t gbytes = gen_stride ? gen_stride * n : 64;
+    bool has_extra = extra && extra_len && extra_stride;
+    size_t wsb = secp256k1_b200_rangeproof_rewind_workspace_bytes(n);
+    size_t oc = c.add(33 * n), op = c.add(proof_stride * n), ol = c.add(4 * n), og = c.add(gbytes), on = c.add(32 * n);
+    size_t oe = c.add(has_extra ? extra_stride * n : 16), oel = c.add(4 * n);
+    size_t ook = c.add(n), omn = c.add(8 * n), omx = c.add(8 * n), ob = c.add(32 * n), ov = c.add(8 * n);
+    size_t om = c.add(message ? message_stride * n : 16), oml = c.add(4 * n), ow = c.add(wsb);
+    if (!c.commit()) return 0;
+    CK(cudaMemcpyAsync(c.at(oc), commit33, 33 * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(op), proofs, proof_stride * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(ol), plen, 4 * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(og), gen64, gbytes, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(c.at(on), nonce32, 32 * n, cudaMemcpyHostToDevice, e->stream));
+    if (has_extra) {
+        CK(cudaMemcpyAsync(c.at(oe), extra, extra_stride * n, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(c.at(oel), extra_len, 4 * n, cudaMemcpyHostToDevice, e->stream));
+    }
+    if (message) CK(cudaMemsetAsync(c.at(om), 0, message_stride * n, e->stream));
+    if (!secp256k1_b200_rangeproof_rewind_batch_dev(e, c.at(ook), c.at(ob), (uint64_t*)c.at(ov), message ? c.at(om) : nullptr, message_stride,
+                                                    (uint32_t*)c.at(oml), (uint64_t*)c.at(omn), (uint64_t*)c.at(omx), c.at(on), c.at(oc), c.at(op),
+                                                    proof_stride, (const uint32_t*)c.at(ol), c.at(og), gen_stride, has_extra ? c.at(oe) : nullptr,
+                                                    extra_stride, has_extra ? (const uint32_t*)c.at(oel) : nullptr, n, c.at(ow), wsb, e->stream)) return 0;
+    CK(cudaMemcpyAsync(ok, c.at(ook), n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(blind32, c.at(ob), 32 * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(value, c.at(ov), 8 * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(min_value, c.at(omn), 8 * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(max_value, c.at(omx), 8 * n, cudaMemcpyDeviceToHost, e->stream));
+    if (message) CK(cudaMemcpyAsync(message, c.at(om), message_stride * n, cudaMemcpyDeviceToHost, e->stream));
+    if (message_len) CK(cudaMemcpyAsync(message_len, c.at(oml), 4 * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
 }  // extern "C"

@@ -1,5 +1,5 @@
 // k_rangeproof.cu -- rangeproof_verify (one warp per proof, one lane per ring) and pedersen_commit kernels.
-#include "rangeproof.cuh"
+#include "rewind.cuh"
 #include "launch.h"
 
 namespace b200 {
@@ -12,7 +12,7 @@ namespace b200 {
 __global__ void __launch_bounds__(RP_WARPS * 32, 3) k_rangeproof_verify(uint8_t* __restrict__ ok, uint64_t* __restrict__ minv, uint64_t* __restrict__ maxv,
         const uint8_t* __restrict__ commit33, const uint8_t* __restrict__ proofs, size_t stride, const uint32_t* __restrict__ plen,
         const uint8_t* __restrict__ gen64, size_t gen_stride, const uint8_t* __restrict__ extra, size_t extra_stride,
-        const uint32_t* __restrict__ extra_len, size_t n, ecmult_gtable gt) {
+        const uint32_t* __restrict__ extra_len, size_t n, ecmult_gtable gt, uint8_t* __restrict__ ev_out /* optional: n x 4096 bytes */) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t item = (size_t)blockIdx.x * RP_WARPS + warp;
@@ -78,12 +78,41 @@ __global__ void __launch_bounds__(RP_WARPS * 32, 3) k_rangeproof_verify(uint8_t*
         gej base;
         rp_ring_base(base, genp, h.exp, lane);
         tab_shared tab = {tabw + lane, 32};
-        ring_ok = rp_ring_walk(r33 + 33 * lane, h, proof, m32, lane, pub, base, gt, tab);
+        ring_ok = rp_ring_walk(r33 + 33 * lane, h, proof, m32, lane, pub, base, gt, tab, ev_out ? ev_out + 4096 * item : nullptr);
     }
     ring_ok = __all_sync(0xffffffffu, ring_ok);
     __syncwarp();
     // ---- P5
     if (lane == 0) ok[item] = (uint8_t)(ring_ok && rp_final_check(h, proof, r33, m32));
+}
+
+// Second pass of a rewind: one thread per proof that k_rangeproof_verify accepted (ok[i] != 0 on entry).  Replays the prover's
+// RFC 6979 stream from the nonce, recovers value / blinding factor / message and re-checks the commitment.
+__global__ void __launch_bounds__(64) k_rangeproof_rewind(uint8_t* __restrict__ ok, uint8_t* __restrict__ blind32, uint64_t* __restrict__ value,
+        uint8_t* __restrict__ msg, size_t msg_stride, uint32_t* __restrict__ msg_len, const uint8_t* __restrict__ nonce32,
+        const uint8_t* __restrict__ commit33, const uint8_t* __restrict__ proofs, size_t stride, const uint32_t* __restrict__ plen,
+        const uint8_t* __restrict__ gen64, size_t gen_stride, const uint8_t* __restrict__ ev, size_t n, ecmult_gtable gt) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int good = ok[i];
+    uint8_t bl[32];
+    uint64_t v = 0;
+    size_t ml = 0;
+    for (int k = 0; k < 32; k++) bl[k] = 0;
+    if (good) {
+        rp_header h;
+        uint64_t mn, mx;
+        const uint8_t* proof = proofs + i * stride;
+        good = rp_parse_header(h, mn, mx, proof, plen[i]);          // accepted before: cannot fail
+        ge genp; rp_generator_load(genp, gen64 + gen_stride * i);
+        if (good) good = rp_rewind_item(bl, v, msg ? msg + msg_stride * i : nullptr, msg ? msg_stride : 0, ml, h, proof, commit33 + 33 * i,
+                                        gen64 + gen_stride * i, fe_is_square(genp.y), nonce32 + 32 * i, ev + 4096 * i, gt);
+    }
+    if (!good) { v = 0; ml = 0; for (int k = 0; k < 32; k++) bl[k] = 0; }
+    ok[i] = (uint8_t)good;
+    for (int k = 0; k < 32; k++) blind32[32 * i + k] = bl[k];
+    value[i] = v;
+    if (msg_len) msg_len[i] = (uint32_t)ml;
 }
 
 __global__ void __launch_bounds__(128) k_pedersen_commit(uint8_t* __restrict__ ok, uint8_t* __restrict__ out33, const uint8_t* __restrict__ blind32,
@@ -102,13 +131,23 @@ static inline ecmult_gtable to_gt(const gtable_dev& g) { ecmult_gtable t; t.data
 
 cudaError_t launch_rangeproof_verify(uint8_t* ok, uint64_t* minv, uint64_t* maxv, const uint8_t* commit33, const uint8_t* proofs, size_t stride,
                                      const uint32_t* plen, const uint8_t* gen64, size_t gen_stride, const uint8_t* extra, size_t extra_stride,
-                                     const uint32_t* extra_len, size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches) {
+                                     const uint32_t* extra_len, size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches, uint8_t* ev_out) {
     if (n == 0) return cudaSuccess;
     const int smem = RP_WARPS * RP_WARP_STRIDE;
     cudaError_t err = cudaFuncSetAttribute(k_rangeproof_verify, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return err;
     k_rangeproof_verify<<<(unsigned)((n + RP_WARPS - 1) / RP_WARPS), RP_WARPS * 32, smem, s>>>(ok, minv, maxv, commit33, proofs, stride, plen,
-                                                                                            gen64, gen_stride, extra, extra_stride, extra_len, n, to_gt(gt));
+                                                                                            gen64, gen_stride, extra, extra_stride, extra_len, n, to_gt(gt), ev_out);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+cudaError_t launch_rangeproof_rewind(uint8_t* ok, uint8_t* blind32, uint64_t* value, uint8_t* msg, size_t msg_stride, uint32_t* msg_len,
+                                     const uint8_t* nonce32, const uint8_t* commit33, const uint8_t* proofs, size_t stride, const uint32_t* plen,
+                                     const uint8_t* gen64, size_t gen_stride, const uint8_t* ev, size_t n, const gtable_dev& gt, cudaStream_t s,
+                                     uint64_t* launches) {
+    if (n == 0) return cudaSuccess;
+    k_rangeproof_rewind<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(ok, blind32, value, msg, msg_stride, msg_len, nonce32, commit33, proofs, stride, plen,
+                                                                 gen64, gen_stride, ev, n, to_gt(gt));
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -171,9 +171,10 @@ HD int rp_borromean_challenge(sc& ens, const uint8_t* e, uint32_t elen, const ui
 
 // P4: walk ring `ring` (borromean_impl.h:69-99).  pub = first key of the ring (Jacobian), base = step point.
 // Writes the 33-byte serialization of the ring's last R.  Returns 0 on any reject condition.
+// ev_out (optional): 32 bytes per position, index 4*ring + j, big-endian challenge e_{ring,j}.
 template <class Tab>
 HD int rp_ring_walk(uint8_t* r33, const rp_header& h, const uint8_t* proof, const uint8_t* m32, uint32_t ring,
-                    gej pub, const gej& base, const ecmult_gtable& gt, Tab& tab) {
+                    gej pub, const gej& base, const ecmult_gtable& gt, Tab& tab, uint8_t* ev_out = nullptr) {
     uint32_t rsize = rp_rsize(h, ring);
     const uint8_t* sbase = proof + h.off_s + 32 * (4 * ring);    // rings before the last all have 4 keys
     sc ens;
@@ -185,6 +186,7 @@ HD int rp_ring_walk(uint8_t* r33, const rp_header& h, const uint8_t* proof, cons
         sc s;
         if (sc_set_b32(s, sbase + 32 * j)) return 0;              // s >= n (rangeproof_impl.h:637-640)
         if (overflow || sc_is_zero(s) || sc_is_zero(ens) || pub.inf) return 0;
+        if (ev_out) sc_get_b32(ev_out + 32 * (4 * ring + j), ens);   // the challenges, for rewinding (borromean_impl.h:76-78 "evalues")
         gej R;
         ecmult(R, pub, ens, s, gt, tab);
         if (R.inf) return 0;

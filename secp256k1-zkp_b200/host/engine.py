@@ -87,6 +87,10 @@ def load_library():
     lib.secp256k1_b200_schnorrsig_verify_batch_dev.argtypes = [vp, u8p, u8p, u8p, sz, u8p, ci, sz, vp]
     lib.secp256k1_b200_ecdsa_verify_batch.argtypes = [vp, u8p, u8p, ci, u8p, u8p, ci, sz]
     lib.secp256k1_b200_ecdsa_verify_batch_dev.argtypes = [vp, u8p, u8p, ci, u8p, u8p, ci, sz, vp]
+    lib.secp256k1_b200_rangeproof_rewind_workspace_bytes.argtypes = [sz]
+    lib.secp256k1_b200_rangeproof_rewind_workspace_bytes.restype = sz
+    lib.secp256k1_b200_rangeproof_rewind_batch.argtypes = [vp, u8p, u8p, vp, u8p, sz, vp, vp, vp, u8p, u8p, u8p, sz, vp, u8p, sz, u8p, sz, vp, sz]
+    lib.secp256k1_b200_rangeproof_rewind_batch_dev.argtypes = [vp, u8p, u8p, vp, u8p, sz, vp, vp, vp, u8p, u8p, u8p, sz, vp, u8p, sz, u8p, sz, vp, sz, vp, sz, vp]
     lib.secp256k1_b200_schnorrsig_aggverify.argtypes = [vp, ctypes.POINTER(ci), u8p, u8p, sz, u8p, sz]
     lib.secp256k1_b200_schnorrsig_aggverify_workspace_bytes.argtypes = [sz]
     lib.secp256k1_b200_schnorrsig_aggverify_workspace_bytes.restype = sz
@@ -194,6 +198,26 @@ class Engine:
         ok = np.empty(n, dtype=np.uint8)
         self._ck(self._lib.secp256k1_b200_ecdsa_verify_batch(self._h, _p(ok), _p(sig), sigfmt, _p(m), _p(p), pkfmt, n))
         return ok
+
+    def rangeproof_rewind(self, nonce32, commit33, proofs, plen, gen64, msg_cap=4096, extra=None, extra_len=None):
+        """secp256k1_rangeproof_rewind over a batch: proofs[n, stride], one 32-byte nonce per proof.
+        -> ok[n], blind[n,32], value[n], message[n,msg_cap], message_len[n], min[n], max[n]"""
+        proofs = np.ascontiguousarray(proofs, dtype=np.uint8)
+        n, stride = proofs.shape
+        c = _u8(commit33, 33 * n, "commit33"); nz = _u8(nonce32, 32 * n, "nonce32")
+        pl = np.ascontiguousarray(plen, dtype=np.uint32)
+        g = _u8(gen64, len(gen64) if not hasattr(gen64, "size") else gen64.size, "gen64")
+        gen_stride = 0 if g.size == 64 else 64
+        ok = np.zeros(n, dtype=np.uint8); blind = np.zeros((n, 32), dtype=np.uint8); val = np.zeros(n, dtype=np.uint64)
+        mn = np.zeros(n, dtype=np.uint64); mx = np.zeros(n, dtype=np.uint64)
+        msg = np.zeros((n, max(msg_cap, 1)), dtype=np.uint8) if msg_cap else None
+        ml = np.zeros(n, dtype=np.uint32)
+        ex = np.ascontiguousarray(extra, dtype=np.uint8) if extra is not None else None
+        exl = np.ascontiguousarray(extra_len, dtype=np.uint32) if extra_len is not None else None
+        self._ck(self._lib.secp256k1_b200_rangeproof_rewind_batch(
+            self._h, _p(ok), _p(blind), _p(val), _p(msg), msg_cap, _p(ml), _p(mn), _p(mx), _p(nz), _p(c), _p(proofs), stride, _p(pl), _p(g), gen_stride,
+            _p(ex), ex.shape[1] if ex is not None else 0, _p(exl), n))
+        return ok, blind, val, msg, ml, mn, mx
 
     def schnorrsig_aggverify(self, pubkeys32, msgs32, aggsig):
         """secp256k1_schnorrsig_aggverify: one half-aggregate signature over n (key, message) pairs -> 0/1"""

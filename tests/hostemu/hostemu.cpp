@@ -21,7 +21,7 @@ int emu_fe_is_zero(const uint8_t* a) { fe x; fe_set_b32(x, a); return fe_is_zero
 #include "../../secp256k1-zkp_b200/csrc/gtable.cuh"
 #include "../../secp256k1-zkp_b200/csrc/verify.cuh"
 #include "../../secp256k1-zkp_b200/csrc/testdata.cuh"
-#include "../../secp256k1-zkp_b200/csrc/rangeproof.cuh"
+#include "../../secp256k1-zkp_b200/csrc/rewind.cuh"
 #include "../../secp256k1-zkp_b200/csrc/msm.cuh"
 #include "../../secp256k1-zkp_b200/csrc/bppp.cuh"
 #include "../../secp256k1-zkp_b200/csrc/surjection.cuh"
@@ -86,8 +86,8 @@ int emu_schnorr_sign(uint8_t* sig64, uint8_t* pk32, const uint8_t* sk32, const u
     return schnorr_sign_item(sig64, pk32, sk32, msg, msglen, c, g_gt);
 }
 // same phases as k_rangeproof_verify, lanes executed one after the other
-int emu_rangeproof_verify(uint64_t* minv, uint64_t* maxv, const uint8_t* commit33, const uint8_t* proof, size_t plen,
-                          const uint8_t* gen64, const uint8_t* extra, size_t extra_len) {
+static int rp_verify_core(uint64_t* minv, uint64_t* maxv, const uint8_t* commit33, const uint8_t* proof, size_t plen,
+                          const uint8_t* gen64, const uint8_t* extra, size_t extra_len, uint8_t* ev) {
     rp_header h; uint64_t mn = 0, mx = 0;
     int hdr_ok = rp_parse_header(h, mn, mx, proof, plen);
     *minv = mn; *maxv = mx;
@@ -121,9 +121,28 @@ int emu_rangeproof_verify(uint64_t* minv, uint64_t* maxv, const uint8_t* commit3
     for (uint32_t lane = 0; lane < h.rings; lane++) {
         gej base; rp_ring_base(base, genp, h.exp, lane);
         tab_local tab;
-        ring_ok &= rp_ring_walk(r33 + 33 * lane, h, proof, m32, lane, pub[lane], base, g_gt, tab);
+        ring_ok &= rp_ring_walk(r33 + 33 * lane, h, proof, m32, lane, pub[lane], base, g_gt, tab, ev);
     }
     return ring_ok && rp_final_check(h, proof, r33, m32);
+}
+int emu_rangeproof_verify(uint64_t* minv, uint64_t* maxv, const uint8_t* commit33, const uint8_t* proof, size_t plen,
+                          const uint8_t* gen64, const uint8_t* extra, size_t extra_len) {
+    return rp_verify_core(minv, maxv, commit33, proof, plen, gen64, extra, extra_len, nullptr);
+}
+// k_rangeproof_verify (challenges kept) followed by k_rangeproof_rewind, for one proof
+int emu_rangeproof_rewind(uint8_t* blind32, uint64_t* value, uint8_t* msg, size_t msg_cap, size_t* msg_len, uint64_t* minv, uint64_t* maxv,
+                          const uint8_t* nonce32, const uint8_t* commit33, const uint8_t* proof, size_t plen, const uint8_t* gen64,
+                          const uint8_t* extra, size_t extra_len) {
+    std::vector<uint8_t> ev(4096);
+    memset(blind32, 0, 32); *value = 0; *msg_len = 0;
+    if (!rp_verify_core(minv, maxv, commit33, proof, plen, gen64, extra, extra_len, ev.data())) return 0;
+    rp_header h; uint64_t mn, mx;
+    if (!rp_parse_header(h, mn, mx, proof, plen)) return 0;
+    ge genp; rp_generator_load(genp, gen64);
+    uint8_t bl[32]; uint64_t v = 0; size_t ml = 0;
+    if (!rp_rewind_item(bl, v, msg_cap ? msg : nullptr, msg_cap, ml, h, proof, commit33, gen64, fe_is_square(genp.y), nonce32, ev.data(), g_gt)) return 0;
+    memcpy(blind32, bl, 32); *value = v; *msg_len = ml;
+    return 1;
 }
 int emu_pedersen_commit(uint8_t* out33, const uint8_t* blind32, uint64_t value, const uint8_t* gen64) {
     return pedersen_commit_item(out33, blind32, value, gen64, g_gt);

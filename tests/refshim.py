@@ -109,6 +109,38 @@ class RefLib:
         return (np.frombuffer(proofs.raw, dtype=np.uint8).reshape(n, stride).copy(), np.array(list(plen), dtype=np.uint64),
                 np.frombuffer(commit.raw, dtype=np.uint8).reshape(n, 33).copy())
 
+    def rangeproof_make_msg(self, blind32, values, min_values, exps, min_bits, nonce32, msgs, gen64, extra=b"", stride=5134):
+        """reference-signed proofs with embedded messages: msgs = list of bytes.  -> (proofs[n,stride], plen[n], commit33[n,33])"""
+        n = len(values)
+        msg_stride = max([len(m) for m in msgs] + [1])
+        mbuf = b"".join(bytes(m).ljust(msg_stride, b"\0") for m in msgs)
+        proofs = ctypes.create_string_buffer(stride * n)
+        plen = (ctypes.c_size_t * n)()
+        commit = ctypes.create_string_buffer(33 * n)
+        ok = self.lib.ref_rangeproof_make_msg_batch(
+            self.ctx, proofs, ctypes.c_size_t(stride), plen, commit, _buf(blind32), (ctypes.c_uint64 * n)(*[int(v) for v in values]),
+            (ctypes.c_uint64 * n)(*[int(v) for v in min_values]), (ctypes.c_int * n)(*exps), (ctypes.c_int * n)(*min_bits), _buf(nonce32), mbuf,
+            ctypes.c_size_t(msg_stride), (ctypes.c_size_t * n)(*[len(m) for m in msgs]), bytes(extra) if extra else None, ctypes.c_size_t(len(extra)),
+            bytes(gen64), ctypes.c_size_t(n))
+        assert ok == 1
+        return (np.frombuffer(proofs.raw, dtype=np.uint8).reshape(n, stride).copy(), np.array(list(plen), dtype=np.uint64),
+                np.frombuffer(commit.raw, dtype=np.uint8).reshape(n, 33).copy())
+
+    def rangeproof_rewind(self, nonce32, commit33, proofs, plen, gen64, msg_cap=4096, extra=b""):
+        """-> ok[n], blind[n,32], value[n], msgs (list of bytes), min[n], max[n]"""
+        proofs = np.ascontiguousarray(proofs, dtype=np.uint8)
+        n, stride = proofs.shape
+        ok = ctypes.create_string_buffer(n); blind = ctypes.create_string_buffer(32 * n)
+        val = (ctypes.c_uint64 * n)(); mn = (ctypes.c_uint64 * n)(); mx = (ctypes.c_uint64 * n)()
+        msg = ctypes.create_string_buffer(max(msg_cap, 1) * n); ml = (ctypes.c_size_t * n)()
+        self.lib.ref_rangeproof_rewind_batch.restype = None
+        self.lib.ref_rangeproof_rewind_batch(self.ctx, ok, blind, val, msg, ctypes.c_size_t(msg_cap), ml, mn, mx, _buf(nonce32), _buf(commit33),
+                                             proofs.tobytes(), ctypes.c_size_t(stride), (ctypes.c_size_t * n)(*[int(x) for x in plen]),
+                                             bytes(extra) if extra else None, ctypes.c_size_t(len(extra)), bytes(gen64), ctypes.c_size_t(n))
+        msgs = [msg.raw[msg_cap * i:msg_cap * i + ml[i]] for i in range(n)]
+        return (np.frombuffer(ok.raw, dtype=np.uint8).copy(), np.frombuffer(blind.raw, dtype=np.uint8).reshape(n, 32).copy(),
+                np.array(list(val), dtype=np.uint64), msgs, np.array(list(mn), dtype=np.uint64), np.array(list(mx), dtype=np.uint64))
+
     def rangeproof_verify(self, commit33, proofs, plen, gen64, extra=b""):
         proofs = np.ascontiguousarray(proofs, dtype=np.uint8)
         n, stride = proofs.shape

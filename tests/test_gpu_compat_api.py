@@ -283,3 +283,30 @@ def test_halfagg_compat(apis, ref):
             assert res[0] == res[1], (n, label)
             assert (label == "valid") == (res[0][1] == 1) or label.startswith("key tampered")
     assert (mine.illegal, theirs.illegal) == ill0
+
+
+def test_rangeproof_rewind_compat(apis, ref):
+    """secp256k1_rangeproof_rewind through both libraries: same verdict, blind, value, message, min/max"""
+    from tests.test_hostemu_logic import _rewind_cases
+    mine, theirs = apis
+    ill0 = (mine.illegal, theirs.illegal)
+    c = _rewind_cases(ref, 4, 10)
+    for i in range(10):
+        for variant in ("ok", "wrong nonce", "no message buffer"):
+            nonce = bytearray(c["nonce"][32 * i:32 * i + 32])
+            if variant == "wrong nonce":
+                nonce[3] ^= 1
+            res = []
+            for api in (mine, theirs):
+                r, cobj = api.commitment_parse(c["commit"][i].tobytes())
+                assert r == 1
+                blind = ctypes.create_string_buffer(32); val = ctypes.c_uint64(0); mn = ctypes.c_uint64(0); mx = ctypes.c_uint64(0)
+                msg = ctypes.create_string_buffer(4096); ml = ctypes.c_size_t(4096)
+                nomsg = variant == "no message buffer"
+                proof = c["proofs"][i, :int(c["plen"][i])].tobytes()
+                ret = api.lib.secp256k1_rangeproof_rewind(api.ctx, blind, ctypes.byref(val), None if nomsg else msg, None if nomsg else ctypes.byref(ml), bytes(nonce),
+                                                          ctypes.byref(mn), ctypes.byref(mx), cobj, proof, ctypes.c_size_t(len(proof)), None, ctypes.c_size_t(0), api.gen_h)
+                res.append((ret, blind.raw, val.value, msg.raw[:ml.value] if (ret and not nomsg) else b"", mn.value, mx.value) if ret else (ret, mn.value, mx.value))
+            assert res[0] == res[1], (i, variant)
+            assert (res[0][0] == 1) == (variant != "wrong nonce")
+    assert (mine.illegal, theirs.illegal) == ill0

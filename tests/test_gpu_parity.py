@@ -222,6 +222,50 @@ def test_halfagg_verify_large(engine, ref):
     assert engine.schnorrsig_aggverify(pk.tobytes(), bytes(bad), agg) == 0
 
 
+def test_rangeproof_rewind_batch(engine, ref):
+    """secp256k1_b200_rangeproof_rewind_batch vs the reference: reproducible vectors (nonce -> blind, value, 0xFF message), assorted shapes with
+    messages, wrong nonce, tampered proof, short / absent message buffer; then 4096 64-bit proofs of the fixture (known value and blind)"""
+    from tests.test_hostemu_logic import _rewind_cases
+    gen = ref.generator_h()
+    gold = json.load(open(os.path.join(GOLD, "rangeproof_rewind.json")))["vectors"]
+    stride = 5134
+    pr = np.zeros((len(gold), stride), dtype=np.uint8)
+    for i, v in enumerate(gold):
+        b = bytes.fromhex(v["proof"]); pr[i, :len(b)] = np.frombuffer(b, dtype=np.uint8)
+    ok, bl, val, msg, ml, mn, mx = engine.rangeproof_rewind(b"".join(bytes.fromhex(v["nonce"]) for v in gold), b"".join(bytes.fromhex(v["commit"]) for v in gold),
+                                                            pr, [len(v["proof"]) // 2 for v in gold], gen)
+    for i, v in enumerate(gold):
+        assert ok[i] == 1 and bl[i].tobytes().hex() == v["blind"] and int(val[i]) == int(v["value"]) and int(ml[i]) >= v["message_len"], v["name"]
+        assert msg[i, :v["message_len"]].tobytes() == bytes([255]) * v["message_len"] and int(mn[i]) == int(v["min_value"]) and int(mx[i]) == int(v["max_value"])
+    n = 48
+    c = _rewind_cases(ref, 3, n)
+    nonce = bytearray(c["nonce"]); nonce[32 * 7 + 1] ^= 0x80
+    proofs = c["proofs"].copy(); proofs[11, 40] ^= 2; proofs[12, int(c["plen"][12]) - 33] ^= 1
+    for cap in (4096, 33, 0):
+        eok, ebl, eval_, emsg, emn, emx = ref.rangeproof_rewind(bytes(nonce), c["commit"], proofs, c["plen"], c["gen"], msg_cap=cap)
+        ok, bl, val, msg, ml, mn, mx = engine.rangeproof_rewind(bytes(nonce), c["commit"].tobytes(), proofs, c["plen"], c["gen"], msg_cap=cap)
+        assert np.array_equal(ok, eok) and eok[7] == 0 and eok[11] == 0 and eok[12] == 0 and eok.sum() == n - 3
+        for i in range(n):
+            if ok[i]:
+                assert bl[i].tobytes() == ebl[i].tobytes() and val[i] == eval_[i] and mn[i] == emn[i] and mx[i] == emx[i], (cap, i)
+                assert (msg[i, :ml[i]].tobytes() if cap else b"") == emsg[i], (cap, i)
+                if cap == 4096:
+                    assert emsg[i][:len(c["msgs"][i])] == c["msgs"][i]
+            else:
+                assert not bl[i].any() and val[i] == 0 and ml[i] == 0
+    fx = np.load(os.path.join(GOLD, "rangeproof64_fixture.npz"))
+    reps = 64
+    proofs = np.tile(fx["proofs"], (reps, 1)); commits = np.tile(fx["commits"], (reps, 1))
+    nonces = commits[:, :32].copy()                      # the fixture was signed with nonce = commitment bytes (bench_rangeproof.c:32-34)
+    bad = np.arange(5, 64 * reps, 97)
+    nonces[bad, 9] ^= 1
+    ok, bl, val, msg, ml, mn, mx = engine.rangeproof_rewind(nonces.tobytes(), commits.tobytes(), proofs, np.full(64 * reps, 5126), fx["gen64"], msg_cap=64)
+    exp_ok = np.ones(64 * reps, dtype=np.uint8); exp_ok[bad] = 0
+    assert np.array_equal(ok, exp_ok)
+    good = ok.astype(bool)
+    assert np.array_equal(val[good], np.tile(fx["values"], reps)[good]) and np.array_equal(bl[good], np.tile(fx["blinds"], (reps, 1))[good])
+
+
 # ---- the reference's own golden vectors through the C ABI ------------------------------------------
 import ctypes
 import json

@@ -8,6 +8,7 @@ import json
 import os
 import random
 
+import numpy as np
 import pytest
 
 from tests.hostemu_lib import load
@@ -395,3 +396,66 @@ def test_halfagg_vs_reference_and_golden(emu, ref):
             assert (label == "valid") == (exp == 1) or label.startswith("key tampered"), (n, label, exp)
             seen.add(exp)
     assert seen >= {0, 1}
+
+
+# ---- range-proof rewinding ----------------------------------------------------------------------------------
+def _rewind_cases(ref, tag, count):
+    """reference-signed proofs of assorted shapes with embedded messages; returns dict of arrays + the inputs that went in"""
+    rnd = random.Random(tag)
+    gen = ref.generator_h()
+    shapes = [(0, 64, 0), (0, 8, 0), (1, 3, 1), (0, 1, 5), (2, 16, 0), (0, 0, 0), (-1, 0, 7), (18, 64, 0)]   # (exp, min_bits, min_value)
+    values, mins, exps, bits, msgs = [], [], [], [], []
+    for i in range(count):
+        exp, mb, mv = shapes[i % len(shapes)]
+        if exp == -1:
+            v = mv + rnd.randrange(1000); msg = b""            # exact-value proof: single ring, no room for a message
+        elif exp == 18:
+            v = 2**64 - 1 - rnd.randrange(10); msg = bytes(rnd.randrange(256) for _ in range(rnd.choice([0, 31, 100, 3968])))
+        else:
+            v = mv + rnd.randrange(1 << max(mb - 1, 1)) * (10 ** exp)
+            msg = bytes(rnd.randrange(256) for _ in range(rnd.choice([0, 1, 32, 33, 64])))
+        values.append(v); mins.append(mv); exps.append(exp); bits.append(mb); msgs.append(msg)
+    blind = b"".join(hashlib.sha256(b"rwb%d-%d" % (tag, i)).digest() for i in range(count))
+    nonce = b"".join(hashlib.sha256(b"rwn%d-%d" % (tag, i)).digest() for i in range(count))
+    rows = []
+    for i in range(count):      # sign one by one: a message that does not fit the proof's shape makes the reference signer refuse -> retry without
+        args = (blind[32 * i:32 * i + 32], [values[i]], [mins[i]], [exps[i]], [bits[i]], nonce[32 * i:32 * i + 32])
+        try:
+            rows.append(ref.rangeproof_make_msg(*args, [msgs[i]], gen))
+        except AssertionError:
+            msgs[i] = b""
+            rows.append(ref.rangeproof_make_msg(*args, [b""], gen))
+    proofs = np.concatenate([r[0] for r in rows]); plen = np.concatenate([r[1] for r in rows]); commit = np.concatenate([r[2] for r in rows])
+    return {"proofs": proofs, "plen": plen, "commit": commit, "nonce": nonce, "blind": blind, "values": values, "msgs": msgs, "gen": gen}
+
+
+def _emu_rewind(emu, nonce, commit, proof, gen, cap=4096, extra=b""):
+    bl = ctypes.create_string_buffer(32); val = ctypes.c_uint64(0); msg = ctypes.create_string_buffer(max(cap, 1)); ml = ctypes.c_size_t(0)
+    mn, mx = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    ok = emu.emu_rangeproof_rewind(bl, ctypes.byref(val), msg, ctypes.c_size_t(cap), ctypes.byref(ml), ctypes.byref(mn), ctypes.byref(mx), bytes(nonce),
+                                   bytes(commit), bytes(proof), ctypes.c_size_t(len(proof)), bytes(gen), extra if extra else None, ctypes.c_size_t(len(extra)))
+    return ok, bl.raw, val.value, msg.raw[:ml.value], mn.value, mx.value
+
+
+def test_rangeproof_rewind_golden_and_reference(emu, ref):
+    gen = ref.generator_h()
+    for v in json.load(open(os.path.join(GOLD, "rangeproof_rewind.json")))["vectors"]:
+        ok, bl, val, msg, mn, mx = _emu_rewind(emu, bytes.fromhex(v["nonce"]), bytes.fromhex(v["commit"]), bytes.fromhex(v["proof"]), gen)
+        assert ok == 1 and bl.hex() == v["blind"] and val == int(v["value"]), v["name"]
+        assert msg[:v["message_len"]] == bytes([255]) * v["message_len"] and mn == int(v["min_value"]) and mx == int(v["max_value"]), v["name"]
+    c = _rewind_cases(ref, 1, 16)
+    n = 16
+    # wrong nonce / tampered proof / small message buffer variants ride along
+    nonce = bytearray(c["nonce"]); nonce[32 * 3] ^= 1
+    proofs = c["proofs"].copy(); proofs[5, int(c["plen"][5]) - 1] ^= 1
+    for cap in (4096, 40, 0):
+        eok, ebl, eval_, emsg, emn, emx = ref.rangeproof_rewind(bytes(nonce), c["commit"], proofs, c["plen"], c["gen"], msg_cap=cap)
+        assert eok[3] == 0 and eok[5] == 0 and eok.sum() == n - 2
+        for i in range(n):
+            ok, bl, val, msg, mn, mx = _emu_rewind(emu, nonce[32 * i:32 * i + 32], c["commit"][i], proofs[i, :int(c["plen"][i])], c["gen"], cap=cap)
+            assert ok == eok[i], (cap, i)
+            if ok:
+                assert bl == ebl[i].tobytes() == c["blind"][32 * i:32 * i + 32] and val == eval_[i] == c["values"][i], (cap, i)
+                assert msg == emsg[i] and mn == emn[i] and mx == emx[i], (cap, i)
+                if cap == 4096:
+                    assert msg[:len(c["msgs"][i])] == c["msgs"][i]

@@ -218,3 +218,30 @@ def test_port_halfagg(port):
         for pk, msg, agg, label in _halfagg_cases(ref, n, b"port%d" % n):
             exp = ref.aggverify(pk, msg, agg)
             assert port.lib.orc_schnorrsig_aggverify(pk, msg, ctypes.c_size_t(n), agg, ctypes.c_size_t(len(agg))) == (1 if exp == 1 else 0), (n, label)
+
+
+def test_port_rangeproof_rewind(port):
+    """oracle port of secp256k1_rangeproof_rewind vs the reference's reproducible vectors (nonce -> blind, value, message) and vs _ref"""
+    from tests.refshim import RefLib
+    from tests.test_hostemu_logic import _rewind_cases
+    ref = RefLib()
+    gen = ref.generator_h()
+
+    def port_rewind(nonce, commit, proof, cap=4096):
+        bl = ctypes.create_string_buffer(32); val = ctypes.c_uint64(0); msg = ctypes.create_string_buffer(max(cap, 1)); ml = ctypes.c_size_t(cap)
+        mn, mx = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        ok = port.lib.orc_rangeproof_rewind(bl, ctypes.byref(val), msg if cap else None, ctypes.byref(ml) if cap else None, bytes(nonce), ctypes.byref(mn),
+                                            ctypes.byref(mx), bytes(commit), bytes(proof), ctypes.c_size_t(len(proof)), None, ctypes.c_size_t(0), bytes(gen))
+        return ok, bl.raw, val.value, msg.raw[:ml.value] if cap else b"", mn.value, mx.value
+    for v in json.load(open(os.path.join(GOLD, "rangeproof_rewind.json")))["vectors"]:
+        ok, bl, val, msg, mn, mx = port_rewind(bytes.fromhex(v["nonce"]), bytes.fromhex(v["commit"]), bytes.fromhex(v["proof"]))
+        assert ok == 1 and bl.hex() == v["blind"] and val == int(v["value"]) and msg[:v["message_len"]] == bytes([255]) * v["message_len"], v["name"]
+    c = _rewind_cases(ref, 2, 8)
+    nonce = bytearray(c["nonce"]); nonce[32 * 2 + 5] ^= 4
+    eok, ebl, eval_, emsg, emn, emx = ref.rangeproof_rewind(bytes(nonce), c["commit"], c["proofs"], c["plen"], c["gen"])
+    assert eok[2] == 0 and eok.sum() == 7
+    for i in range(8):
+        ok, bl, val, msg, mn, mx = port_rewind(nonce[32 * i:32 * i + 32], c["commit"][i], c["proofs"][i, :int(c["plen"][i])])
+        assert ok == eok[i], i
+        if ok:
+            assert bl == ebl[i].tobytes() and val == eval_[i] and msg == emsg[i] and (mn, mx) == (emn[i], emx[i]), i

@@ -197,6 +197,24 @@ def bppp_vectors(ref):
             "gens33": gens33.hex(), "gens_xy": gens_xy.hex(), "vectors": out}
 
 
+def rewind_vectors():
+    """src/modules/rangeproof/tests_impl.h:843-851, :883-1352 (test_rangeproof_fixed_vectors_reproducible): what rewinding the three
+    reproducible vectors with vector_nonce must return (blind = vector_blind, the value, an all-0xFF message of the stated length)."""
+    text = read("src/modules/rangeproof/tests_impl.h")
+    arr = {n: b for n, b, _ in parse_arrays(text)}
+    gold = json.load(open(os.path.join(OUT, "rangeproof.json")))["vectors"]
+    by = {v["name"]: v for v in gold}
+    exp = [("reproducible_0", 2**64 - 1, 3968), ("reproducible_1", 13, 128), ("reproducible_2", 2**63 - 1, 0)]
+    m = re.search(r"#define\s+SECP256K1_RANGEPROOF_MAX_MESSAGE_LEN\s+(\d+)", read("include/secp256k1_rangeproof.h"))
+    assert m and int(m.group(1)) == 3968
+    out = []
+    for name, value, mlen in exp:
+        v = by[name]
+        out.append({"name": name, "commit": v["commit"], "proof": v["proof"], "nonce": arr["vector_nonce"].hex(), "blind": arr["vector_blind"].hex(),
+                    "value": str(value), "message_len": mlen, "message_byte": "ff", "min_value": v["min_value"], "max_value": v["max_value"]})
+    return {"source": "src/modules/rangeproof/tests_impl.h:843-881, :883-1352", "vectors": out}
+
+
 def recovery_vectors():
     """src/modules/recovery/tests_impl.h:156-199 (test_ecdsa_recovery_edge_cases): which recids recover a key."""
     text = read("src/modules/recovery/tests_impl.h")
@@ -240,6 +258,8 @@ def main():
     jobs["halfagg.json"] = halfagg_vectors
     if hasattr(ref, "rangeproof_verify_one"):
         jobs["rangeproof.json"] = lambda: rangeproof(ref)
+    if "rangeproof.json" in jobs:
+        jobs["rangeproof_rewind.json"] = rewind_vectors          # after rangeproof.json (reads it)
     for name, fn in jobs.items():
         data = fn()
         with open(os.path.join(OUT, name), "w") as f:
