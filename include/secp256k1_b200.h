@@ -232,7 +232,7 @@ SECP256K1_B200_API int secp256k1_b200_rangeproof_verify_batch_dev(secp256k1_b200
  * (blind32), the proven value, and the embedded message (up to message_stride bytes per proof into message + i*message_stride,
  * message_len[i] = bytes recovered; message may be NULL).  ok[i] = 1 only if the proof verifies AND the recovered (value, blind)
  * rebuild the commitment; otherwise blind/value/message_len are zero.  The _dev form needs a device workspace of
- * secp256k1_b200_rangeproof_rewind_workspace_bytes(n) bytes (the ring challenges, 4096 per proof). */
+ * secp256k1_b200_rangeproof_rewind_workspace_bytes(n) bytes (ring challenges and the replayed random stream, 9216 per proof). */
 SECP256K1_B200_API size_t secp256k1_b200_rangeproof_rewind_workspace_bytes(size_t n);
 SECP256K1_B200_API int secp256k1_b200_rangeproof_rewind_batch(secp256k1_b200_engine *e, unsigned char *ok, unsigned char *blind32, uint64_t *value,
         unsigned char *message, size_t message_stride, uint32_t *message_len, uint64_t *min_value, uint64_t *max_value,

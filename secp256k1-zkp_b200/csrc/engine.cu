@@ -728,7 +728,7 @@ int secp256k1_b200_rangeproof_verify_batch(secp256k1_b200_engine* e, unsigned ch
 }
 
 /* ---- range-proof rewinding: verify (one warp per proof, challenges kept) + replay (one thread per proof) ---- */
-size_t secp256k1_b200_rangeproof_rewind_workspace_bytes(size_t n) { return 4096 * n + 256; }
+size_t secp256k1_b200_rangeproof_rewind_workspace_bytes(size_t n) { return (4096 + 5120) * n + 256; }   // challenges + replayed stream
 int secp256k1_b200_rangeproof_rewind_batch_dev(secp256k1_b200_engine* e, unsigned char* d_ok, unsigned char* d_blind32, uint64_t* d_value,
                                                unsigned char* d_message, size_t message_stride, uint32_t* d_message_len,
                                                uint64_t* d_min_value, uint64_t* d_max_value, const unsigned char* d_nonce32,
@@ -745,7 +745,7 @@ int secp256k1_b200_rangeproof_rewind_batch_dev(secp256k1_b200_engine* e, unsigne
     CK(launch_rangeproof_verify(d_ok, d_min_value, d_max_value, d_commit33, d_proofs, proof_stride, d_plen, d_gen64, gen_stride,
                                 d_extra, extra_stride, d_extra_len, n, e->gt(), (cudaStream_t)stream, &e->launches, ev));
     CK(launch_rangeproof_rewind(d_ok, d_blind32, d_value, d_message, message_stride, d_message_len, d_nonce32, d_commit33, d_proofs, proof_stride,
-                                d_plen, d_gen64, gen_stride, ev, n, e->gt(), (cudaStream_t)stream, &e->launches));
+                                d_plen, d_gen64, gen_stride, ev, ev + 4096 * n, n, e->gt(), (cudaStream_t)stream, &e->launches));
     return 1;
 }
 int secp256k1_b200_rangeproof_rewind_batch(secp256k1_b200_engine* e, unsigned char* ok, unsigned char* blind32, uint64_t* value,

@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(RP_WARPS * 32, 3) k_rangeproof_verify(uint8_t*
 __global__ void __launch_bounds__(64) k_rangeproof_rewind(uint8_t* __restrict__ ok, uint8_t* __restrict__ blind32, uint64_t* __restrict__ value,
         uint8_t* __restrict__ msg, size_t msg_stride, uint32_t* __restrict__ msg_len, const uint8_t* __restrict__ nonce32,
         const uint8_t* __restrict__ commit33, const uint8_t* __restrict__ proofs, size_t stride, const uint32_t* __restrict__ plen,
-        const uint8_t* __restrict__ gen64, size_t gen_stride, const uint8_t* __restrict__ ev, size_t n, ecmult_gtable gt) {
+        const uint8_t* __restrict__ gen64, size_t gen_stride, const uint8_t* __restrict__ ev, uint8_t* __restrict__ scratch /* n x 5120 */, size_t n,
+        ecmult_gtable gt) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int good = ok[i];
@@ -106,7 +107,8 @@ __global__ void __launch_bounds__(64) k_rangeproof_rewind(uint8_t* __restrict__ 
         good = rp_parse_header(h, mn, mx, proof, plen[i]);          // accepted before: cannot fail
         ge genp; rp_generator_load(genp, gen64 + gen_stride * i);
         if (good) good = rp_rewind_item(bl, v, msg ? msg + msg_stride * i : nullptr, msg ? msg_stride : 0, ml, h, proof, commit33 + 33 * i,
-                                        gen64 + gen_stride * i, fe_is_square(genp.y), nonce32 + 32 * i, ev + 4096 * i, gt);
+                                        gen64 + gen_stride * i, fe_is_square(genp.y), nonce32 + 32 * i, ev + 4096 * i, gt,
+                                        reinterpret_cast<sc*>(scratch + 5120 * i + 4096), scratch + 5120 * i);
     }
     if (!good) { v = 0; ml = 0; for (int k = 0; k < 32; k++) bl[k] = 0; }
     ok[i] = (uint8_t)good;
@@ -143,11 +145,11 @@ cudaError_t launch_rangeproof_verify(uint8_t* ok, uint64_t* minv, uint64_t* maxv
 }
 cudaError_t launch_rangeproof_rewind(uint8_t* ok, uint8_t* blind32, uint64_t* value, uint8_t* msg, size_t msg_stride, uint32_t* msg_len,
                                      const uint8_t* nonce32, const uint8_t* commit33, const uint8_t* proofs, size_t stride, const uint32_t* plen,
-                                     const uint8_t* gen64, size_t gen_stride, const uint8_t* ev, size_t n, const gtable_dev& gt, cudaStream_t s,
-                                     uint64_t* launches) {
+                                     const uint8_t* gen64, size_t gen_stride, const uint8_t* ev, uint8_t* scratch, size_t n, const gtable_dev& gt,
+                                     cudaStream_t s, uint64_t* launches) {
     if (n == 0) return cudaSuccess;
     k_rangeproof_rewind<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(ok, blind32, value, msg, msg_stride, msg_len, nonce32, commit33, proofs, stride, plen,
-                                                                 gen64, gen_stride, ev, n, to_gt(gt));
+                                                                 gen64, gen_stride, ev, scratch, n, to_gt(gt));
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

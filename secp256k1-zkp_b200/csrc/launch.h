@@ -38,8 +38,8 @@ cudaError_t launch_rangeproof_verify(uint8_t* ok, uint64_t* minv, uint64_t* maxv
                                      const uint32_t* extra_len, size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches, uint8_t* ev_out = nullptr);
 cudaError_t launch_rangeproof_rewind(uint8_t* ok, uint8_t* blind32, uint64_t* value, uint8_t* msg, size_t msg_stride, uint32_t* msg_len,
                                      const uint8_t* nonce32, const uint8_t* commit33, const uint8_t* proofs, size_t stride, const uint32_t* plen,
-                                     const uint8_t* gen64, size_t gen_stride, const uint8_t* ev, size_t n, const gtable_dev& gt, cudaStream_t s,
-                                     uint64_t* launches);
+                                     const uint8_t* gen64, size_t gen_stride, const uint8_t* ev, uint8_t* scratch, size_t n, const gtable_dev& gt,
+                                     cudaStream_t s, uint64_t* launches);
 cudaError_t launch_pedersen_commit(uint8_t* ok, uint8_t* out33, const uint8_t* blind32, const uint64_t* value, const uint8_t* gen64, size_t gen_stride,
                                    size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches);
 

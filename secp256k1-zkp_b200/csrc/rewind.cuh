@@ -94,11 +94,12 @@ HD void rp_recover_x(sc& x, const sc& k, const sc& e, const sc& s) {
 
 // One verified proof.  ev = the challenges of the ring walk, 32 bytes big-endian per position, index 4*ring + j.
 // msg_cap = capacity of msg_out (0 or msg_out == nullptr: no message wanted).  Returns 1 and fills blind32 / value / msg_len on success.
+// sec / prep: caller-provided scratch (32 scalars, 4096 bytes).  On the device they live in the global-memory workspace, not on the
+// thread's stack: with the 4 KB array as a local, two sm_100a builds of k_rangeproof_rewind overwrote its first 512 / 64 bytes with
+// the temporaries of the scalar inversion further down (wrong message bytes, correct blind and value; clean under the host build).
 HD int rp_rewind_item(uint8_t* blind32, uint64_t& value_out, uint8_t* msg_out, size_t msg_cap, size_t& msg_len, const rp_header& h,
                       const uint8_t* proof, const uint8_t* commit33, const uint8_t* gen64, int gen_y_is_square, const uint8_t* nonce32,
-                      const uint8_t* ev, const ecmult_gtable& gt) {
-    sc sec[RP_MAX_RINGS];
-    uint8_t prep[4096];
+                      const uint8_t* ev, const ecmult_gtable& gt, sc* sec, uint8_t* prep) {
     msg_len = 0;
     rp_genrand(sec, prep, h, nonce32, commit33, gen64, gen_y_is_square, proof);
     const uint8_t* sb = proof + h.off_s;

@@ -161,19 +161,43 @@ HD void sc_split_lambda(sc& r1, sc& r2, const sc& k) {
 // finding; inlining this function, or any unrelated change to the kernel, made it disappear -- A/B libraries on the GPU,
 // round 1).  Inlined, the table lives in the kernel's own frame like every other local array.
 HD void sc_inverse(sc& r, const sc& a) {
-    // n - 2, little-endian limbs
-    const uint32_t e[8] = {0xD036413Fu, 0xBFD25E8Cu, 0xAF48A03Bu, 0xBAAEDCE6u, 0xFFFFFFFEu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-    // 4-bit fixed window
-    sc tab[16];
-    sc_set_int(tab[0], 1);
-    tab[1] = a;
-    for (int i = 2; i < 16; i++) sc_mul(tab[i], tab[i - 1], a);
-    sc acc; sc_set_int(acc, 1);
+    // a^(n-2) without any table (r1g: the former 16-entry window table -- a dynamically indexed local array -- was the common factor of two
+    // wrong-result builds: the outlined copy in k_bppp_norm_verify (see above) and, inlined into k_rangeproof_rewind, a build whose
+    // 512-byte table shared its stack slot with the first 512 bytes of a live 4 KB array of the caller; both clean under
+    // compute-sanitizer, both correct when compiled for the host).
+    // n - 2 = (2^127 - 1) * 2^129 + L with L = the low 129 bits (bit 128 is 0).  f(k) := a^(2^k - 1), f(i+j) = f(i)^(2^j) * f(j).
+    sc f3, f7, f15, f31, f63, t, acc;
+    sc_sqr(t, a); sc_mul(t, t, a);                                  // f2
+    sc_sqr(t, t); sc_mul(f3, t, a);                                 // f3
+    t = f3;
+    for (int k = 0; k < 3; k++) sc_sqr(t, t);
+    sc_mul(t, t, f3);                                               // f6
+    sc_sqr(t, t); sc_mul(f7, t, a);                                 // f7
+    t = f7;
+    for (int k = 0; k < 7; k++) sc_sqr(t, t);
+    sc_mul(t, t, f7);                                               // f14
+    sc_sqr(t, t); sc_mul(f15, t, a);                                // f15
+    t = f15;
 #pragma unroll 1
-    for (int i = 63; i >= 0; i--) {
-        sc_sqr(acc, acc); sc_sqr(acc, acc); sc_sqr(acc, acc); sc_sqr(acc, acc);
-        uint32_t d = (e[i >> 3] >> ((i & 7) * 4)) & 0xFu;
-        sc_mul(acc, acc, tab[d]);
+    for (int k = 0; k < 15; k++) sc_sqr(t, t);
+    sc_mul(t, t, f15);                                              // f30
+    sc_sqr(t, t); sc_mul(f31, t, a);                                // f31
+    t = f31;
+#pragma unroll 1
+    for (int k = 0; k < 31; k++) sc_sqr(t, t);
+    sc_mul(t, t, f31);                                              // f62
+    sc_sqr(t, t); sc_mul(f63, t, a);                                // f63
+    t = f63;
+#pragma unroll 1
+    for (int k = 0; k < 63; k++) sc_sqr(t, t);
+    sc_mul(t, t, f63);                                              // f126
+    sc_sqr(t, t); sc_mul(acc, t, a);                                // f127
+    sc_sqr(acc, acc);                                               // bit 128 of the exponent is 0
+    const uint32_t lo[4] = {0xD036413Fu, 0xBFD25E8Cu, 0xAF48A03Bu, 0xBAAEDCE6u};      // low 128 bits of n - 2
+#pragma unroll 1
+    for (int i = 127; i >= 0; i--) {
+        sc_sqr(acc, acc);
+        if ((lo[i >> 5] >> (i & 31)) & 1u) sc_mul(acc, acc, a);
     }
     r = acc;
 }

@@ -140,7 +140,8 @@ int emu_rangeproof_rewind(uint8_t* blind32, uint64_t* value, uint8_t* msg, size_
     if (!rp_parse_header(h, mn, mx, proof, plen)) return 0;
     ge genp; rp_generator_load(genp, gen64);
     uint8_t bl[32]; uint64_t v = 0; size_t ml = 0;
-    if (!rp_rewind_item(bl, v, msg_cap ? msg : nullptr, msg_cap, ml, h, proof, commit33, gen64, fe_is_square(genp.y), nonce32, ev.data(), g_gt)) return 0;
+    std::vector<sc> sec(RP_MAX_RINGS); std::vector<uint8_t> prep(4096);
+    if (!rp_rewind_item(bl, v, msg_cap ? msg : nullptr, msg_cap, ml, h, proof, commit33, gen64, fe_is_square(genp.y), nonce32, ev.data(), g_gt, sec.data(), prep.data())) return 0;
     memcpy(blind32, bl, 32); *value = v; *msg_len = ml;
     return 1;
 }
