@@ -45,5 +45,24 @@ def main():
         print(json.dumps({"bench": "halfagg_verify (host buffers: host randomizer chain + H2D + terms + MSM)", "n": n, "ms": ms, "sigs_s": n / ms * 1e3}))
 
 
+def rewind_bench():
+    """8192 64-bit proofs of the fixture (nonce = commitment bytes): verify + replay + value/blind recovery, host buffers"""
+    eng = b200.Engine()
+    gold = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+    fx = np.load(os.path.join(gold, "rangeproof64_fixture.npz"))
+    reps = 128
+    proofs = np.tile(fx["proofs"], (reps, 1)); commits = np.tile(fx["commits"], (reps, 1)); n = proofs.shape[0]
+    nonces = commits[:, :32].copy()
+    plen = np.full(n, 5126)
+    for cap in (0, 4096):
+        eng.rangeproof_rewind(nonces.tobytes(), commits.tobytes(), proofs, plen, fx["gen64"], msg_cap=cap)
+        t0 = time.perf_counter()
+        ok, bl, val, msg, ml, mn, mx = eng.rangeproof_rewind(nonces.tobytes(), commits.tobytes(), proofs, plen, fx["gen64"], msg_cap=cap)
+        ms = (time.perf_counter() - t0) * 1e3
+        good = bool(ok.all()) and bool(np.array_equal(val, np.tile(fx["values"], reps)))
+        print(json.dumps({"bench": "rangeproof_rewind 64-bit (host buffers, message capacity %d)" % cap, "n": n, "ms": ms, "proofs_s": n / ms * 1e3, "values_ok": good}))
+
+
 if __name__ == "__main__":
+    rewind_bench()
     main()
