@@ -727,3 +727,46 @@ def test_pedersen_verify_tally_batch_vs_reference(engine, ref):
         pos.append(bytes(cp)); neg.append(bytes(cn)); po.append(po[-1] + np_); no.append(no[-1] + nn)
     got = engine.pedersen_verify_tally(b"".join(pos), po, b"".join(neg), no)
     assert list(got) == exp and 80 < sum(exp) < 160
+
+
+def test_empty_ragged_and_unaligned_batches(engine, ref):
+    """edge shapes of the batch ABI: n = 0 on every entry point, n = 1 and n = 129 (not a multiple of any block size), and device
+    buffers that start at odd addresses (the kernels fall back from 16-byte to byte loads) -- same verdicts as the aligned run"""
+    import torch
+    import secp256k1_zkp_b200 as b200
+    e = engine
+    z = np.zeros(0, dtype=np.uint8)
+    assert e.schnorrsig_verify(z, z, z, b200.PK_XONLY32).size == 0
+    assert e.ecdsa_verify(z, z, z, b200.SIG_COMPACT64, b200.PK_COMPRESSED33).size == 0
+    ok, pk = e.ecdsa_recover(z, z, z); assert ok.size == 0 and pk.shape == (0, 64)
+    assert e.ecmult(z, z, z).shape == (0, 64)
+    assert e.schnorrsig_aggverify(b"", b"", bytes(32)) == 1          # the empty aggregate with s = 0 verifies (spec vector 0)
+    assert e.schnorrsig_aggverify(b"", b"", bytes(31) + b"\x01") == 0
+    out = e.ecmult_multi(np.zeros((0, 32), dtype=np.uint8), np.zeros((0, 64), dtype=np.uint8))
+    assert out == bytes(64)                                            # empty sum = infinity = all-zero encoding
+    for n in (1, 129):
+        sk = b"".join(hashlib.sha256(b"rag%d-%d" % (n, i)).digest() for i in range(n))
+        msg = b"".join(hashlib.sha256(b"ragm%d-%d" % (n, i)).digest() for i in range(n))
+        sig, pk = ref.schnorr_make(sk, msg)
+        sig = sig.copy(); sig[64 * (n // 2) + 5] ^= 1
+        exp = ref.schnorr_verify(sig, msg, pk)
+        assert np.array_equal(e.schnorrsig_verify(sig, msg, pk, b200.PK_XONLY32), exp) and exp.sum() == n - 1
+        # the same batch from device buffers at odd byte offsets
+        st = torch.cuda.current_stream().cuda_stream
+
+        def odd(a, off):
+            t = torch.zeros(len(a) + 16, dtype=torch.uint8, device="cuda")
+            t[off:off + len(a)] = torch.frombuffer(bytearray(bytes(a)), dtype=torch.uint8).cuda()
+            return t, t.data_ptr() + off
+        ts, ps = odd(sig.tobytes(), 1); tm, pm = odd(msg, 3); tp, pp = odd(pk.tobytes(), 7)
+        okd = torch.zeros(n + 16, dtype=torch.uint8, device="cuda")
+        e.schnorrsig_verify_dev(okd.data_ptr() + 5, ps, pm, 32, pp, b200.PK_XONLY32, n, st)
+        torch.cuda.synchronize()
+        assert np.array_equal(okd[5:5 + n].cpu().numpy(), exp) and not okd[:5].any() and not okd[5 + n:].any()
+        rsig, rid = ref.ecdsa_sign_recoverable(sk, msg)
+        eok, epk = ref.ecdsa_recover(rsig, rid, msg)
+        tr, pr = odd(rsig.tobytes(), 9); ti, pi = odd(rid.tobytes(), 1)
+        outk = torch.zeros(64 * n + 16, dtype=torch.uint8, device="cuda")
+        e.ecdsa_recover_dev(okd.data_ptr() + 5, outk.data_ptr() + 3, pr, pi, pm, n, st)
+        torch.cuda.synchronize()
+        assert np.array_equal(okd[5:5 + n].cpu().numpy(), eok) and np.array_equal(outk[3:3 + 64 * n].cpu().numpy().reshape(n, 64), epk)
