@@ -207,6 +207,34 @@ int secp256k1_ecdsa_signature_parse_compact(const secp256k1_context* ctx, secp25
     }
     return ret;
 }
+int secp256k1_ecdsa_signature_serialize_compact(const secp256k1_context* ctx, unsigned char* output64, const secp256k1_ecdsa_signature* sig) {
+    ARG_CHECK(output64 != NULL);
+    ARG_CHECK(sig != NULL);
+    for (int half = 0; half < 2; half++)
+        for (int i = 0; i < 32; i++) output64[32 * half + i] = sig->data[32 * half + 31 - i];
+    return 1;
+}
+// src/secp256k1.c:479-496: s > n/2 -> s := n - s.  Byte-level compare / subtract on the little-endian scalar, no group arithmetic.
+int secp256k1_ecdsa_signature_normalize(const secp256k1_context* ctx, secp256k1_ecdsa_signature* sigout, const secp256k1_ecdsa_signature* sigin) {
+    ARG_CHECK(sigin != NULL);
+    static const unsigned char HALF_ORDER_BE[32] = {0x7F, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF,
+                                                    0x5D, 0x57, 0x6E, 0x73, 0x57, 0xA4, 0x50, 0x1D, 0xDF, 0xE9, 0x2F, 0x46, 0x68, 0x1B, 0x20, 0xA0};
+    unsigned char s_be[32];
+    for (int i = 0; i < 32; i++) s_be[i] = sigin->data[32 + 31 - i];
+    int high = memcmp(s_be, HALF_ORDER_BE, 32) > 0;
+    if (sigout != NULL) {
+        memmove(sigout->data, sigin->data, 64);
+        if (high) {                                   // n - s, little-endian bytes
+            int borrow = 0;
+            for (int i = 0; i < 32; i++) {
+                int d = (int)ORDER_BE[31 - i] - (int)sigin->data[32 + i] - borrow;
+                borrow = d < 0;
+                sigout->data[32 + i] = (unsigned char)(d + (borrow << 8));
+            }
+        }
+    }
+    return high;
+}
 int secp256k1_ecdsa_verify(const secp256k1_context* ctx, const secp256k1_ecdsa_signature* sig, const unsigned char* msghash32, const secp256k1_pubkey* pubkey) {
     ARG_CHECK(msghash32 != NULL);
     ARG_CHECK(sig != NULL);

@@ -310,3 +310,25 @@ def test_rangeproof_rewind_compat(apis, ref):
             assert res[0] == res[1], (i, variant)
             assert (res[0][0] == 1) == (variant != "wrong nonce")
     assert (mine.illegal, theirs.illegal) == ill0
+
+
+def test_ecdsa_signature_normalize_and_serialize_compat(apis):
+    """secp256k1_ecdsa_signature_normalize / _serialize_compact (host-only byte arithmetic) through both libraries"""
+    mine, theirs = apis
+    rnd = random.Random(9)
+    half = N // 2
+    svals = [1, half, half + 1, N - 1, 2, N - 2] + [rnd.randrange(1, N) for _ in range(40)]
+    for sv in svals:
+        c = rnd.randrange(1, N).to_bytes(32, "big") + sv.to_bytes(32, "big")
+        res = []
+        for api in (mine, theirs):
+            ok, obj = api.ecdsa_parse_compact(c)
+            out = ctypes.create_string_buffer(64)
+            r = api.lib.secp256k1_ecdsa_signature_normalize(api.ctx, out, obj)
+            r2 = api.lib.secp256k1_ecdsa_signature_normalize(api.ctx, None, obj)
+            ser = ctypes.create_string_buffer(64)
+            api.lib.secp256k1_ecdsa_signature_serialize_compact(api.ctx, ser, out)
+            res.append((ok, r, r2, out.raw, ser.raw))
+        assert res[0] == res[1], hex(sv)
+        assert res[0][1] == (1 if sv > half else 0)
+        assert int.from_bytes(res[0][4][32:], "big") == (N - sv if sv > half else sv)
