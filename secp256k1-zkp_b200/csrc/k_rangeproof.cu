@@ -5,11 +5,16 @@
 namespace b200 {
 
 #define RP_WARPS 4
-#define RP_TAB_WORDS (32 * 8 * 16)                 // per warp: 32 lanes x 8 entries x 16 words
-#define RP_WARP_BYTES (RP_TAB_WORDS * 4 + 32 + 32 * 33 + 32)   // tables (aliased with the point-sum scratch) + m + R33[32] + pad
+// per warp in shared memory: the point-sum scratch (32 Jacobian points), m, R33[32].  The lanes' odd-multiples tables are in local
+// memory (see k_verify.cu: more resident warps than the 3 blocks/SM that 16 KB of table per warp allowed).
+#ifndef RP_MINBLOCKS
+#define RP_MINBLOCKS 5
+#endif
+#define RP_TAB_WORDS ((32 * (int)sizeof(gej) + 3) / 4)
+#define RP_WARP_BYTES (RP_TAB_WORDS * 4 + 32 + 32 * 33 + 32)
 #define RP_WARP_STRIDE ((RP_WARP_BYTES + 127) & ~127)
 
-__global__ void __launch_bounds__(RP_WARPS * 32, 3) k_rangeproof_verify(uint8_t* __restrict__ ok, uint64_t* __restrict__ minv, uint64_t* __restrict__ maxv,
+__global__ void __launch_bounds__(RP_WARPS * 32, RP_MINBLOCKS) k_rangeproof_verify(uint8_t* __restrict__ ok, uint64_t* __restrict__ minv, uint64_t* __restrict__ maxv,
         const uint8_t* __restrict__ commit33, const uint8_t* __restrict__ proofs, size_t stride, const uint32_t* __restrict__ plen,
         const uint8_t* __restrict__ gen64, size_t gen_stride, const uint8_t* __restrict__ extra, size_t extra_stride,
         const uint32_t* __restrict__ extra_len, size_t n, ecmult_gtable gt, uint8_t* __restrict__ ev_out /* optional: n x 4096 bytes */) {
@@ -18,8 +23,7 @@ __global__ void __launch_bounds__(RP_WARPS * 32, 3) k_rangeproof_verify(uint8_t*
     const size_t item = (size_t)blockIdx.x * RP_WARPS + warp;
     if (item >= n) return;                                  // whole warp leaves together
     uint8_t* wbase = smem_raw + (size_t)warp * RP_WARP_STRIDE;
-    uint32_t* tabw = reinterpret_cast<uint32_t*>(wbase);
-    gej* pts = reinterpret_cast<gej*>(wbase);               // aliases the table region (used before it)
+    gej* pts = reinterpret_cast<gej*>(wbase);
     uint8_t* m32 = wbase + RP_TAB_WORDS * 4;
     uint8_t* r33 = m32 + 32;
     const uint8_t* proof = proofs + item * stride;
@@ -70,14 +74,14 @@ __global__ void __launch_bounds__(RP_WARPS * 32, 3) k_rangeproof_verify(uint8_t*
         gej_set_ge(pub, mine);
     }
     good = __all_sync(0xffffffffu, good);
-    __syncwarp();                                            // pts[] dead from here: the region becomes the tables
+    __syncwarp();
     if (!good) { if (lane == 0) ok[item] = 0; return; }
     // ---- P3/P4: ring walk
     int ring_ok = 1;
     if (lane < h.rings) {
         gej base;
         rp_ring_base(base, genp, h.exp, lane);
-        tab_shared tab = {tabw + lane, 32};
+        tab_local tab;
         ring_ok = rp_ring_walk(r33 + 33 * lane, h, proof, m32, lane, pub, base, gt, tab, ev_out ? ev_out + 4096 * item : nullptr);
     }
     ring_ok = __all_sync(0xffffffffu, ring_ok);

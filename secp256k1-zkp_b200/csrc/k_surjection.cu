@@ -4,13 +4,12 @@
 
 namespace b200 {
 
-__global__ void __launch_bounds__(128, 3) k_surjection_verify(uint8_t* __restrict__ ok, const uint8_t* __restrict__ proofs, size_t stride,
+__global__ void __launch_bounds__(128, 5) k_surjection_verify(uint8_t* __restrict__ ok, const uint8_t* __restrict__ proofs, size_t stride,
         const uint32_t* __restrict__ plen, const uint8_t* __restrict__ in_tags64, const uint32_t* __restrict__ tag_off,
         const uint8_t* __restrict__ out_tags64, size_t n, ecmult_gtable gt) {
-    extern __shared__ uint32_t smem[];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    tab_shared tab = {smem + threadIdx.x, (int)blockDim.x};
+    tab_local tab;   // local memory, see k_verify.cu
     uint32_t t0 = tag_off[i], t1 = tag_off[i + 1];
     ok[i] = (uint8_t)surjection_verify_item(proofs + stride * i, plen[i], in_tags64 + 64 * (size_t)t0, t1 - t0, out_tags64 + 64 * i, gt, tab);
 }
@@ -24,9 +23,7 @@ __global__ void __launch_bounds__(128) k_pedersen_tally(uint8_t* __restrict__ ok
 cudaError_t launch_surjection_verify(uint8_t* ok, const uint8_t* proofs, size_t stride, const uint32_t* plen, const uint8_t* in_tags64,
                                      const uint32_t* tag_off, const uint8_t* out_tags64, size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches) {
     if (n == 0) return cudaSuccess;
-    const int smem = 128 * 8 * 16 * 4;
-    cudaError_t err = cudaFuncSetAttribute(k_surjection_verify, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (err != cudaSuccess) return err;
+    const int smem = 0;
     ecmult_gtable g; g.data = gt.data; g.gw = gt.gw; g.windows = gt.windows;
     k_surjection_verify<<<(unsigned)((n + 127) / 128), 128, smem, s>>>(ok, proofs, stride, plen, in_tags64, tag_off, out_tags64, n, g);
     if (launches) *launches += 1;

@@ -7,7 +7,23 @@
 namespace b200 {
 
 #define VERIFY_BLOCK 128
+// The 8-entry odd-multiples table of each thread (512 bytes) lives in LOCAL memory (per-thread, interleaved across the warp by the
+// hardware, cached in L1), not in shared memory: with the table in shared memory an SM holds 3 blocks (12 warps at 158 registers);
+// in local memory the limit is the register file, and 5 blocks of 96-register threads (20 warps, ~1 KB of spills per thread) hide the
+// latency of the multiply chains better.  Measured (tools/ab_bench.py, 2^20 verifies): shared/3 blocks 40.0 M/s; local/3 40.2;
+// local/4 (128 regs) 41.9; local/5 (96) 43.2; local/6 (80) 42.6; local/7 41.7; local/8 40.6.
+// Shared memory is only used by the block-wide inversions (2 * VERIFY_BLOCK field elements).
+#ifdef B200_TAB_IN_SHARED         // the r1a-r1g layout, kept for A/B runs
 #define VERIFY_SMEM (VERIFY_BLOCK * 8 * 16 * 4)
+#define VERIFY_TAB(name) tab_shared name = {smem + threadIdx.x, (int)blockDim.x}
+#define B200_VERIFY_MINBLOCKS 3
+#else
+#define VERIFY_SMEM (VERIFY_BLOCK * 2 * 32)
+#define VERIFY_TAB(name) tab_local name
+#ifndef B200_VERIFY_MINBLOCKS
+#define B200_VERIFY_MINBLOCKS 5
+#endif
+#endif
 
 __device__ __forceinline__ void load_bytes_global(uint8_t* dst, const uint8_t* src, int nbytes) {
     // 16-byte vector path when aligned (contiguous per-item records), byte path otherwise
@@ -74,11 +90,11 @@ __device__ __forceinline__ void sc_block_inverse(sc& sinv, const sc& x, sc* node
     __syncthreads();                                        // the region is about to become the tables
 }
 
-__global__ void __launch_bounds__(VERIFY_BLOCK, 3) k_ecmult(uint8_t* __restrict__ out64, const uint8_t* __restrict__ a64,
+__global__ void __launch_bounds__(VERIFY_BLOCK, B200_VERIFY_MINBLOCKS) k_ecmult(uint8_t* __restrict__ out64, const uint8_t* __restrict__ a64,
         const uint8_t* __restrict__ na32, const uint8_t* __restrict__ ng32, size_t n, ecmult_gtable gt) {
     extern __shared__ uint32_t smem[];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    tab_shared tab = {smem + threadIdx.x, (int)blockDim.x};
+    VERIFY_TAB(tab);
     gej R; gej_set_infinity(R);
     if (i < n) {
         __align__(16) uint8_t in[128];
@@ -114,12 +130,12 @@ __global__ void __launch_bounds__(VERIFY_BLOCK, 3) k_ecmult(uint8_t* __restrict_
     else for (int k = 0; k < 64; k++) out64[64 * i + k] = o[k];
 }
 
-__global__ void __launch_bounds__(VERIFY_BLOCK, 3) k_schnorr_verify(uint8_t* __restrict__ ok, const uint8_t* __restrict__ sig64,
+__global__ void __launch_bounds__(VERIFY_BLOCK, B200_VERIFY_MINBLOCKS) k_schnorr_verify(uint8_t* __restrict__ ok, const uint8_t* __restrict__ sig64,
         const uint8_t* __restrict__ msg, uint32_t msglen, const uint8_t* __restrict__ pk, int pkfmt, size_t n,
         bip340_midstate mid, ecmult_gtable gt) {
     extern __shared__ uint32_t smem[];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    tab_shared tab = {smem + threadIdx.x, (int)blockDim.x};
+    VERIFY_TAB(tab);
     gej R; fe rx, z, zinv;
     int live = 0;
     if (i < n) {
@@ -135,11 +151,11 @@ __global__ void __launch_bounds__(VERIFY_BLOCK, 3) k_schnorr_verify(uint8_t* __r
     if (i < n) ok[i] = (uint8_t)(live && schnorr_verify_finish(R, rx, zinv));
 }
 
-__global__ void __launch_bounds__(VERIFY_BLOCK, 3) k_ecdsa_verify(uint8_t* __restrict__ ok, const uint8_t* __restrict__ sig64, int sigfmt,
+__global__ void __launch_bounds__(VERIFY_BLOCK, B200_VERIFY_MINBLOCKS) k_ecdsa_verify(uint8_t* __restrict__ ok, const uint8_t* __restrict__ sig64, int sigfmt,
         const uint8_t* __restrict__ msg32, const uint8_t* __restrict__ pk, int pkfmt, size_t n, ecmult_gtable gt) {
     extern __shared__ uint32_t smem[];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    tab_shared tab = {smem + threadIdx.x, (int)blockDim.x};
+    VERIFY_TAB(tab);
     ecdsa_state st;
     int live = 0;
     if (i < n) {
@@ -157,11 +173,11 @@ __global__ void __launch_bounds__(VERIFY_BLOCK, 3) k_ecdsa_verify(uint8_t* __res
 }
 
 // out64[i] = recovered public key (affine x||y big-endian; zeros when ok[i] == 0)
-__global__ void __launch_bounds__(VERIFY_BLOCK, 3) k_ecdsa_recover(uint8_t* __restrict__ ok, uint8_t* __restrict__ out64, const uint8_t* __restrict__ sig64,
+__global__ void __launch_bounds__(VERIFY_BLOCK, B200_VERIFY_MINBLOCKS) k_ecdsa_recover(uint8_t* __restrict__ ok, uint8_t* __restrict__ out64, const uint8_t* __restrict__ sig64,
         const uint8_t* __restrict__ recid, const uint8_t* __restrict__ msg32, size_t n, ecmult_gtable gt) {
     extern __shared__ uint32_t smem[];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    tab_shared tab = {smem + threadIdx.x, (int)blockDim.x};
+    VERIFY_TAB(tab);
     ecdsa_recover_state st;
     int live = 0;
     if (i < n) {
