@@ -8,7 +8,7 @@ namespace b200 {
 // per warp in shared memory: the point-sum scratch (32 Jacobian points), m, R33[32].  The lanes' odd-multiples tables are in local
 // memory (see k_verify.cu: more resident warps than the 3 blocks/SM that 16 KB of table per warp allowed).
 #ifndef RP_MINBLOCKS
-#define RP_MINBLOCKS 5
+#define RP_MINBLOCKS 4
 #endif
 #define RP_TAB_WORDS ((32 * (int)sizeof(gej) + 3) / 4)
 #define RP_WARP_BYTES (RP_TAB_WORDS * 4 + 32 + 32 * 33 + 32)
