@@ -310,8 +310,8 @@ def run_extra_workloads(eng, b200_mod, torch, dist, D, dev, stream, rank, world,
 
 
 # ------------------------------------------------------------------------------------------------
-# measured once with ncu on the 2^20 launch (profiles/r1e_*): DRAM bytes per launch, IMAD.WIDE.U32(.X) executed per verify
-NCU_DRAM_BYTES_2P20 = 784147712 + 539369728
+# measured with ncu on the 2^20 launch: DRAM bytes per launch (profiles/r1h_*, tables + spills in local memory), IMAD.WIDE.U32(.X) executed per verify (profiles/r1e_*)
+NCU_DRAM_BYTES_2P20 = 1615576832 + 1516754176
 IMAD_WIDE_EXECUTED_PER_VERIFY = 136155
 
 
@@ -489,8 +489,8 @@ def main():
             "roofline": {"bound": "int32 multiply pipe (IMAD.WIDE.U32); not hbm, not tensor", "achieved": achieved, "peak": imad_peak_tmacs, "unit": "TMAC/s",
                          "frac": achieved / imad_peak_tmacs, "traffic": NCU_DRAM_BYTES_2P20 if args.log2n == 20 else None,
                          "how": "algorithmic 1.81e5 MAC per verify (SURVEY 8d, reference algorithm) x %d verifies / %.3f ms kernel (CUDA events); peak = live IMAD.WIDE.U32 probe "
-                                "(16 independent accumulators, distinct multiplicands); traffic = dram read+write bytes of one 2^20 launch (ncu, profiles/r1e_ncu_schnorr_2p20_metrics.csv): "
-                                "inputs 135 MB + generator-table misses + local-memory write-back, 50 GB/s, not a bound" % (n, kms),
+                                "(16 independent accumulators, distinct multiplicands); traffic = dram read+write bytes of one 2^20 launch (ncu, profiles/r1h_ncu_schnorr_2p20_metrics.csv): "
+                                "inputs 135 MB + generator-table misses + local-memory tables/spills written back, 129 GB/s = 2 % of HBM, not a bound" % (n, kms),
                          "executed": {"imad_wide_per_verify": IMAD_WIDE_EXECUTED_PER_VERIFY, "tmac_s": n * IMAD_WIDE_EXECUTED_PER_VERIFY / (kms / 1e3) / 1e12,
                                       "frac_of_peak": n * IMAD_WIDE_EXECUTED_PER_VERIFY / (kms / 1e3) / 1e12 / imad_peak_tmacs,
                                       "source": "ncu SourceCounters, IMAD.WIDE.U32(.X) thread instructions per verify (profiles/r1e_ncu_summary.md)"},
