@@ -490,7 +490,7 @@ def main():
                          "frac": achieved / imad_peak_tmacs, "traffic": NCU_DRAM_BYTES_2P20 if args.log2n == 20 else None,
                          "how": "algorithmic 1.81e5 MAC per verify (SURVEY 8d, reference algorithm) x %d verifies / %.3f ms kernel (CUDA events); peak = live IMAD.WIDE.U32 probe "
                                 "(16 independent accumulators, distinct multiplicands); traffic = dram read+write bytes of one 2^20 launch (ncu, profiles/r1h_ncu_schnorr_2p20_metrics.csv): "
-                                "inputs 135 MB + generator-table misses + local-memory tables/spills written back, 129 GB/s = 2 % of HBM, not a bound" % (n, kms),
+                                "inputs 135 MB + generator-table misses + local-memory tables/spills written back, 129 GB/s = 2 %% of HBM, not a bound" % (n, kms),
                          "executed": {"imad_wide_per_verify": IMAD_WIDE_EXECUTED_PER_VERIFY, "tmac_s": n * IMAD_WIDE_EXECUTED_PER_VERIFY / (kms / 1e3) / 1e12,
                                       "frac_of_peak": n * IMAD_WIDE_EXECUTED_PER_VERIFY / (kms / 1e3) / 1e12 / imad_peak_tmacs,
                                       "source": "ncu SourceCounters, IMAD.WIDE.U32(.X) thread instructions per verify (profiles/r1e_ncu_summary.md)"},
