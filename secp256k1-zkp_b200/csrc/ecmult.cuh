@@ -7,8 +7,9 @@
 //    FIXED 4-bit window with signed ODD digits: every lane adds at the same 33 positions, no
 //    zero digits, no divergence.  The 8-entry table of odd multiples is the one ecmult_impl.h:73-115
 //    builds (same isomorphism / global-z trick, group_impl.h:289-320) so all adds are mixed adds.
-//  * the table lives in shared memory, laid out [entry][word][thread] => bank = thread, conflict free
-//    for any per-lane entry index.
+//  * the table lives in per-thread LOCAL memory (tab_local: the hardware interleaves it [word][thread] across the warp, so any per-lane
+//    entry index is a coalesced access) since r1h; before that, and still in k_bppp.cu, in shared memory laid out [entry][word][thread]
+//    (tab_shared: bank = thread, conflict free).  Never a dynamically indexed REGISTER array.
 //  * ng*G needs no doublings at all: a comb table T[j][d] = d * 2^(gw*j) * G in HBM/L2 (gw = 16:
 //    16 windows x 65536 affine points = 64 MiB, built on the GPU at engine init) replaces the
 //    reference's 2 x 8192-entry wNAF tables (precomputed_ecmult.c); 16 mixed adds per item.

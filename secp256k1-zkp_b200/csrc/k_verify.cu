@@ -1,6 +1,6 @@
 // k_verify.cu -- one-thread-per-item kernels: ecmult batch, BIP-340 verify batch, ECDSA verify batch.
-// Block = 128 threads; dynamic shared memory = 128 * 512 B = 64 KiB for the per-thread tables of odd
-// multiples (3 blocks resident per SM = 192 KiB of the 227 KiB).
+// Block = 128 threads, 5 blocks/SM at 96 registers; the per-thread tables of odd multiples (see ecmult.cuh) are in local memory,
+// dynamic shared memory (8 KiB) only holds the product trees of the block-wide inversions -- see the note at VERIFY_BLOCK below.
 #include "verify.cuh"
 #include "launch.h"
 
