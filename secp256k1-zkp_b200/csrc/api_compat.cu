@@ -207,6 +207,81 @@ int secp256k1_ecdsa_signature_parse_compact(const secp256k1_context* ctx, secp25
     }
     return ret;
 }
+// ---- strict DER signatures (src/ecdsa_impl.h:36-171 parse, :173-197 serialize): byte parsing on the host -----------------------------
+namespace {
+struct der_cursor { const unsigned char* p; const unsigned char* end; };
+// X.690 definite length, shortest form only; 0 on any violation
+int der_len(size_t* len, der_cursor& c) {
+    *len = 0;
+    if (c.p >= c.end) return 0;
+    unsigned char b1 = *c.p++;
+    if (b1 == 0xFF) return 0;
+    if ((b1 & 0x80) == 0) { *len = b1; return 1; }
+    if (b1 == 0x80) return 0;                                   // indefinite length
+    size_t left = b1 & 0x7F;
+    if (left > (size_t)(c.end - c.p)) return 0;
+    if (*c.p == 0) return 0;                                    // not the shortest length encoding
+    if (left > sizeof(size_t)) return 0;
+    while (left--) *len = (*len << 8) | *c.p++;
+    if (*len > (size_t)(c.end - c.p)) return 0;
+    if (*len < 128) return 0;                                   // long form for a short length
+    return 1;
+}
+// one INTEGER into 32 big-endian bytes; negative / too long / >= n values parse but become 0 (the signature then never verifies)
+int der_int(unsigned char* out32, der_cursor& c) {
+    memset(out32, 0, 32);
+    if (c.p == c.end || *c.p != 0x02) return 0;
+    c.p++;
+    size_t len;
+    if (!der_len(&len, c)) return 0;
+    if (len == 0 || len > (size_t)(c.end - c.p)) return 0;
+    if (c.p[0] == 0x00 && len > 1 && (c.p[1] & 0x80) == 0x00) return 0;     // excessive 0x00 padding
+    if (c.p[0] == 0xFF && len > 1 && (c.p[1] & 0x80) == 0x80) return 0;     // excessive 0xFF padding
+    int overflow = (c.p[0] & 0x80) != 0;                                    // negative
+    if (len > 0 && c.p[0] == 0) { len--; c.p++; }
+    if (len > 32) overflow = 1;
+    if (!overflow) {
+        if (len) memcpy(out32 + 32 - len, c.p, len);
+        if (memcmp(out32, ORDER_BE, 32) >= 0) overflow = 1;
+    }
+    if (overflow) memset(out32, 0, 32);
+    c.p += len;
+    return 1;
+}
+}  // namespace
+int secp256k1_ecdsa_signature_parse_der(const secp256k1_context* ctx, secp256k1_ecdsa_signature* sig, const unsigned char* input, size_t inputlen) {
+    ARG_CHECK(sig != NULL);
+    ARG_CHECK(input != NULL);
+    der_cursor c = {input, input + inputlen};
+    unsigned char rs[64];
+    size_t len;
+    int ok = c.p != c.end && *c.p++ == 0x30 && der_len(&len, c) && len == (size_t)(c.end - c.p) && der_int(rs, c) && der_int(rs + 32, c) && c.p == c.end;
+    if (ok) {
+        for (int half = 0; half < 2; half++)
+            for (int i = 0; i < 32; i++) sig->data[32 * half + i] = rs[32 * half + 31 - i];
+    } else {
+        memset(sig, 0, sizeof(*sig));
+    }
+    return ok;
+}
+int secp256k1_ecdsa_signature_serialize_der(const secp256k1_context* ctx, unsigned char* output, size_t* outputlen, const secp256k1_ecdsa_signature* sig) {
+    ARG_CHECK(output != NULL);
+    ARG_CHECK(outputlen != NULL);
+    ARG_CHECK(sig != NULL);
+    unsigned char r[33] = {0}, s[33] = {0};
+    for (int i = 0; i < 32; i++) { r[1 + i] = sig->data[31 - i]; s[1 + i] = sig->data[63 - i]; }
+    const unsigned char *rp = r, *sp = s;
+    size_t lr = 33, ls = 33;
+    while (lr > 1 && rp[0] == 0 && rp[1] < 0x80) { lr--; rp++; }
+    while (ls > 1 && sp[0] == 0 && sp[1] < 0x80) { ls--; sp++; }
+    size_t need = 6 + lr + ls;
+    if (*outputlen < need) { *outputlen = need; return 0; }
+    *outputlen = need;
+    output[0] = 0x30; output[1] = (unsigned char)(4 + lr + ls);
+    output[2] = 0x02; output[3] = (unsigned char)lr; memcpy(output + 4, rp, lr);
+    output[4 + lr] = 0x02; output[5 + lr] = (unsigned char)ls; memcpy(output + 6 + lr, sp, ls);
+    return 1;
+}
 int secp256k1_ecdsa_signature_serialize_compact(const secp256k1_context* ctx, unsigned char* output64, const secp256k1_ecdsa_signature* sig) {
     ARG_CHECK(output64 != NULL);
     ARG_CHECK(sig != NULL);

@@ -46,6 +46,18 @@ int main(void) {
     CHECK(9, secp256k1_ecdsa_recoverable_signature_convert(ctx, &esig, &rsig) == 1);
     secp256k1_ecdsa_signature_normalize(ctx, &esig, &esig);
     CHECK(10, secp256k1_ecdsa_verify(ctx, &esig, msg, &rec) == 1);
+    /* a DER signature (Wycheproof ecdsa_secp256k1_sha256_bitcoin tcId 2): parse, normalize, verify against the uncompressed key */
+    {
+        unsigned char der[80], pk65[65], h[32];
+        int dl = hex(der, "3045022100813ef79ccefa9a56f7ba805f0e478584fe5f0dd5f567bc09b5123ccbc983236502206ff18a52dcc0336f7af62400a6dd9b810732baf1ff758000d6f613a556eb31ba");
+        hex(pk65, "04b838ff44e5bc177bf21189d0766082fc9d843226887fc9760371100b7ee20a6ff0c9d75bfba7b31a6bca1974496eeb56de357071955d83c4b1badaa0b21832e9");
+        hex(h, "bb5a52f42f9c9261ed4361f59422a1e30036e7c32b270c8807a419feca605023");
+        CHECK(14, secp256k1_ecdsa_signature_parse_der(ctx, &esig, der, (size_t)dl) == 1);
+        CHECK(15, secp256k1_ec_pubkey_parse(ctx, &pub, pk65, 65) == 1);
+        CHECK(16, secp256k1_ecdsa_verify(ctx, &esig, h, &pub) == 1);
+        der[10] ^= 1;
+        CHECK(17, secp256k1_ecdsa_signature_parse_der(ctx, &esig, der, (size_t)dl) == 1 && secp256k1_ecdsa_verify(ctx, &esig, h, &pub) == 0);
+    }
     /* Pedersen commitment with the default value generator: commit / serialize / parse round trip */
     memset(blind, 0x11, 32);
     CHECK(11, secp256k1_pedersen_commit(ctx, &commit, blind, 12345, secp256k1_generator_h) == 1);

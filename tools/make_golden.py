@@ -137,7 +137,7 @@ def wycheproof(ref):
         if der_ok:
             L.secp256k1_ecdsa_signature_serialize_compact(ref.ctx, compact, sig)
         vectors.append({"tcId": int(tc), "comment": comment, "pk65": pk65.hex(), "msghash": hashlib.sha256(msg).hexdigest(),
-                        "der_ok": int(der_ok), "compact": compact.raw.hex() if der_ok else "", "expected": exp})
+                        "der": der.hex(), "der_ok": int(der_ok), "compact": compact.raw.hex() if der_ok else "", "expected": exp})
     return {"source": "src/wycheproof/ecdsa_secp256k1_sha256_bitcoin_test.h (driver src/tests.c:7803-7831); DER parsed by the reference",
             "vectors": vectors}
 
