@@ -55,6 +55,11 @@ SECP256K1_B200_API int secp256k1_context_randomize(secp256k1_context *ctx, const
 SECP256K1_B200_API int secp256k1_ec_pubkey_parse(const secp256k1_context *ctx, secp256k1_pubkey *pubkey, const unsigned char *input, size_t inputlen);
 SECP256K1_B200_API int secp256k1_ec_pubkey_serialize(const secp256k1_context *ctx, unsigned char *output, size_t *outputlen, const secp256k1_pubkey *pubkey, unsigned int flags);
 SECP256K1_B200_API int secp256k1_ecdsa_signature_parse_compact(const secp256k1_context *ctx, secp256k1_ecdsa_signature *sig, const unsigned char *input64);
+/* host-only helpers of the same API: include/secp256k1.h:462 (pubkey_cmp), :689 (seckey_verify), :867 (tagged_sha256); include/secp256k1_extrakeys.h:77 (xonly cmp) */
+SECP256K1_B200_API int secp256k1_ec_pubkey_cmp(const secp256k1_context *ctx, const secp256k1_pubkey *pubkey1, const secp256k1_pubkey *pubkey2);
+SECP256K1_B200_API int secp256k1_xonly_pubkey_cmp(const secp256k1_context *ctx, const secp256k1_xonly_pubkey *pk1, const secp256k1_xonly_pubkey *pk2);
+SECP256K1_B200_API int secp256k1_ec_seckey_verify(const secp256k1_context *ctx, const unsigned char *seckey);
+SECP256K1_B200_API int secp256k1_tagged_sha256(const secp256k1_context *ctx, unsigned char *hash32, const unsigned char *tag, size_t taglen, const unsigned char *msg, size_t msglen);
 SECP256K1_B200_API int secp256k1_ecdsa_signature_parse_der(const secp256k1_context *ctx, secp256k1_ecdsa_signature *sig, const unsigned char *input, size_t inputlen);   /* include/secp256k1.h:544, src/secp256k1.c:353, src/ecdsa_impl.h:36-171 */
 SECP256K1_B200_API int secp256k1_ecdsa_signature_serialize_der(const secp256k1_context *ctx, unsigned char *output, size_t *outputlen, const secp256k1_ecdsa_signature *sig);   /* include/secp256k1.h:569, src/ecdsa_impl.h:173-197 */
 SECP256K1_B200_API int secp256k1_ecdsa_signature_serialize_compact(const secp256k1_context *ctx, unsigned char *output64, const secp256k1_ecdsa_signature *sig);   /* include/secp256k1.h:581 */

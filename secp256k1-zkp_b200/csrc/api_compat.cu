@@ -3,6 +3,7 @@
 // the GPU.  Mirrors the control flow of src/secp256k1.c and the module main_impl.h files it cites; no reference
 // code is reused.
 #include "../../include/secp256k1_b200_compat.h"
+#include "sha256.cuh"
 
 #include <mutex>
 #include <stdio.h>
@@ -186,6 +187,40 @@ int secp256k1_xonly_pubkey_serialize(const secp256k1_context* ctx, unsigned char
     ARG_CHECK(pubkey != NULL);
     ARG_CHECK(!all_zero(pubkey->data, 32));
     for (int i = 0; i < 32; i++) output32[i] = pubkey->data[31 - i];
+    return 1;
+}
+
+// ---- host-only helpers (src/secp256k1.c:334-358, :666-675, :869-881; modules/extrakeys/main_impl.h:59-83) ---------------------------
+int secp256k1_ec_pubkey_cmp(const secp256k1_context* ctx, const secp256k1_pubkey* pubkey0, const secp256k1_pubkey* pubkey1) {
+    unsigned char out[2][33];
+    const secp256k1_pubkey* pk[2] = {pubkey0, pubkey1};
+    for (int i = 0; i < 2; i++) {       // NULL / invalid keys: illegal callback (from the serializer), then they sort as all-zero
+        size_t len = 33;
+        if (!secp256k1_ec_pubkey_serialize(ctx, out[i], &len, pk[i], (1u << 1) | (1u << 8))) memset(out[i], 0, 33);
+    }
+    return memcmp(out[0], out[1], 33);
+}
+int secp256k1_xonly_pubkey_cmp(const secp256k1_context* ctx, const secp256k1_xonly_pubkey* pk0, const secp256k1_xonly_pubkey* pk1) {
+    unsigned char out[2][32];
+    const secp256k1_xonly_pubkey* pk[2] = {pk0, pk1};
+    for (int i = 0; i < 2; i++)
+        if (!secp256k1_xonly_pubkey_serialize(ctx, out[i], pk[i])) memset(out[i], 0, 32);
+    return memcmp(out[0], out[1], 32);
+}
+static const unsigned char ORDER_BE_FWD[32] = {0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFE,
+                                               0xBA, 0xAE, 0xDC, 0xE6, 0xAF, 0x48, 0xA0, 0x3B, 0xBF, 0xD2, 0x5E, 0x8C, 0xD0, 0x36, 0x41, 0x41};
+int secp256k1_ec_seckey_verify(const secp256k1_context* ctx, const unsigned char* seckey) {
+    ARG_CHECK(seckey != NULL);
+    return !all_zero(seckey, 32) && memcmp(seckey, ORDER_BE_FWD, 32) < 0;      // 0 < key < n (scalar_set_b32_seckey)
+}
+int secp256k1_tagged_sha256(const secp256k1_context* ctx, unsigned char* hash32, const unsigned char* tag, size_t taglen, const unsigned char* msg, size_t msglen) {
+    ARG_CHECK(hash32 != NULL);
+    ARG_CHECK(tag != NULL);
+    ARG_CHECK(msg != NULL);
+    b200::sha256 h;
+    b200::sha256_init_tagged(h, tag, taglen);
+    b200::sha256_write(h, msg, msglen);
+    b200::sha256_finalize(h, hash32);
     return 1;
 }
 

@@ -77,3 +77,41 @@ def test_der_of_boundary_scalars(libs):
             body = enc(r) + enc(s)
             der = b"\x30" + bytes([len(body)]) + body
             assert _roundtrip(mine, mctx, der) == _roundtrip(theirs, rctx, der), (hex(r), hex(s))
+
+
+def test_host_only_helpers(libs):
+    """secp256k1_ec_pubkey_cmp / xonly_pubkey_cmp (on opaque objects parsed by the reference: the two libraries share the object layout),
+    secp256k1_ec_seckey_verify, secp256k1_tagged_sha256"""
+    import hashlib
+    (mine, mctx), (theirs, rctx) = libs
+    vecs = json.load(open(os.path.join(GOLD, "wycheproof_ecdsa.json")))["vectors"]
+    keys = sorted({v["pk65"] for v in vecs})[:12]
+    objs, xobjs = [], []
+    for k in keys:
+        o = ctypes.create_string_buffer(64)
+        assert theirs.secp256k1_ec_pubkey_parse(rctx, o, bytes.fromhex(k), ctypes.c_size_t(65)) == 1
+        objs.append(o)
+        x = ctypes.create_string_buffer(64)
+        if theirs.secp256k1_xonly_pubkey_parse(rctx, x, bytes.fromhex(k)[1:33]) == 1:
+            xobjs.append(x)
+    sign = lambda v: (v > 0) - (v < 0)
+    for a in objs:
+        for b in objs:
+            assert sign(mine.secp256k1_ec_pubkey_cmp(mctx, a, b)) == sign(theirs.secp256k1_ec_pubkey_cmp(rctx, a, b))
+    for a in xobjs:
+        for b in xobjs:
+            assert sign(mine.secp256k1_xonly_pubkey_cmp(mctx, a, b)) == sign(theirs.secp256k1_xonly_pubkey_cmp(rctx, a, b))
+    for k in (0, 1, N - 1, N, N + 1, 2**256 - 1, 12345):
+        kb = k.to_bytes(32, "big")
+        assert mine.secp256k1_ec_seckey_verify(mctx, kb) == theirs.secp256k1_ec_seckey_verify(rctx, kb) == (1 if 0 < k < N else 0)
+    rnd = random.Random(5)
+    for taglen, msglen in ((0, 0), (1, 1), (17, 32), (64, 55), (65, 56), (100, 200)):
+        tag = bytes(rnd.randrange(256) for _ in range(taglen)) or b""
+        msg = bytes(rnd.randrange(256) for _ in range(msglen)) or b""
+        outs = []
+        for lib, ctx in ((mine, mctx), (theirs, rctx)):
+            o = ctypes.create_string_buffer(32)
+            assert lib.secp256k1_tagged_sha256(ctx, o, tag if tag else b"\x00", ctypes.c_size_t(taglen), msg if msg else b"\x00", ctypes.c_size_t(msglen)) == 1
+            outs.append(o.raw)
+        th = hashlib.sha256(tag).digest()
+        assert outs[0] == outs[1] == hashlib.sha256(th + th + msg).digest()
