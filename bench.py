@@ -198,15 +198,17 @@ def run_extra_workloads(eng, b200_mod, torch, dist, D, dev, stream, rank, world,
     eng.ecmult_dev(pts.data_ptr(), z64.data_ptr(), z32.data_ptr(), sk.data_ptr(), m, stream)     # P_i = sk_i * G
     wsb = eng.ecmult_multi_workspace_bytes(max(m, 64))
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-    part = torch.empty(64, dtype=torch.uint8, device=dev)
+    part = torch.empty(96 if world > 1 else 64, dtype=torch.uint8, device=dev)
     final = torch.empty(64, dtype=torch.uint8, device=dev)
-    ones = torch.zeros((world, 32), dtype=torch.uint8, device=dev); ones[:, 31] = 1
+    allp = torch.empty((world, 96), dtype=torch.uint8, device=dev)
 
     def msm_step():
-        eng.ecmult_multi_dev(part.data_ptr(), None, sc.data_ptr(), pts.data_ptr(), m, ws.data_ptr(), wsb, stream)
-        if world > 1:
-            allp = D.allgather_points(part)
-            eng.ecmult_multi_dev(final.data_ptr(), None, ones.data_ptr(), allp.data_ptr(), world, ws.data_ptr(), wsb, stream)
+        if world == 1:
+            eng.ecmult_multi_dev(part.data_ptr(), None, sc.data_ptr(), pts.data_ptr(), m, ws.data_ptr(), wsb, stream)
+        else:   # shard sum stays Jacobian (no inversion), ONE all-gather of 96 bytes per rank, W-1 additions + one inversion in one block
+            eng.ecmult_multi_partial_dev(part.data_ptr(), None, sc.data_ptr(), pts.data_ptr(), m, ws.data_ptr(), wsb, stream)
+            D.allgather_partials(part, allp)
+            eng.ecmult_multi_combine_dev(final.data_ptr(), allp.data_ptr(), world, stream)
     ms = _time_dev(torch, dist, world, msm_step)
     # identity check of bench_ecmult's teardown (src/bench_ecmult.c:73-93): MSM == (sum s_i*sk_i) * G, scalars on the host
     res = (final if world > 1 else part).cpu().numpy().tobytes()

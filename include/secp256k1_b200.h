@@ -93,6 +93,26 @@ SECP256K1_B200_API int secp256k1_b200_fe_op_batch(secp256k1_b200_engine *e, int 
 SECP256K1_B200_API int secp256k1_b200_fe_op_batch_dev(secp256k1_b200_engine *e, int op, unsigned char *d_out32,
         const unsigned char *d_a32, const unsigned char *d_b32, size_t n, int iters, void *stream);
 
+/* Unit kernels of the scalar and group primitives, for parity tests against the reference's own functions (scalar_4x64_impl.h,
+ * scalar_impl.h:142, group_impl.h:503,:534,:598).  Scalar ops: a, b = n x 32 bytes big-endian, out = n x 32 (split_lambda: n x 64,
+ * r1 || r2).  Group ops: a, b = n x 96 bytes  x || y || s  (affine point, all-zero x||y = infinity, lifted to the Jacobian point
+ * (x s^2, y s^3, s) so that z != 1; the mixed addition uses b's x||y only), out = n x 64 affine x||y, zeros = infinity.  b may be NULL for
+ * one-operand ops.  The _G4 ops run the lane-parallel forms (4 lanes per item) used by the MSM tail. */
+#define SECP256K1_B200_UNIT_SC_MUL          0
+#define SECP256K1_B200_UNIT_SC_ADD          1
+#define SECP256K1_B200_UNIT_SC_NEGATE       2
+#define SECP256K1_B200_UNIT_SC_INVERSE      3
+#define SECP256K1_B200_UNIT_SC_SPLIT_LAMBDA 4
+#define SECP256K1_B200_UNIT_SC_REDUCE       5
+#define SECP256K1_B200_UNIT_GEJ_DOUBLE      8
+#define SECP256K1_B200_UNIT_GEJ_ADD         9
+#define SECP256K1_B200_UNIT_GEJ_ADD_GE      10
+#define SECP256K1_B200_UNIT_GEJ_DOUBLE_G4   24
+#define SECP256K1_B200_UNIT_GEJ_ADD_G4      25
+#define SECP256K1_B200_UNIT_GEJ_ADD_GE_G4   26
+SECP256K1_B200_API int secp256k1_b200_unit_op_batch(secp256k1_b200_engine *e, int op, unsigned char *out,
+        const unsigned char *a, const unsigned char *b, size_t n);
+
 /* Integer-pipe peak probe: blocks*threads threads each issue 16*iters register-resident IMAD.WIDE.U32
  * (32x32+64 MAC).  d_out: blocks*threads*8 bytes.  The measured MAC/s is the roofline denominator. */
 SECP256K1_B200_API int secp256k1_b200_imad_probe_dev(secp256k1_b200_engine *e, void *d_out, int blocks, int threads, int iters, void *stream);
@@ -153,6 +173,17 @@ SECP256K1_B200_API int secp256k1_b200_ecmult_multi(secp256k1_b200_engine *e, uns
         const unsigned char *scalars32, const unsigned char *points64, size_t n);
 SECP256K1_B200_API int secp256k1_b200_ecmult_multi_dev(secp256k1_b200_engine *e, unsigned char *d_out64, const unsigned char *d_g_scalar32,
         const unsigned char *d_scalars32, const unsigned char *d_points64, size_t n, void *d_workspace, size_t workspace_bytes, void *stream);
+/* Sharded MSM (one shard of the terms per GPU): _partial_dev leaves the shard's sum as a 96-byte Jacobian point
+ * (x, y, z as 8 x u32 little-endian limbs each, z = 0 <=> infinity; no field inversion); after the partial sums of all shards have been
+ * gathered (96 bytes per GPU), _combine_dev adds `count` of them and converts once: out64 = affine x||y big-endian. */
+SECP256K1_B200_API int secp256k1_b200_ecmult_multi_partial_dev(secp256k1_b200_engine *e, unsigned char *d_out96, const unsigned char *d_g_scalar32,
+        const unsigned char *d_scalars32, const unsigned char *d_points64, size_t n, void *d_workspace, size_t workspace_bytes, void *stream);
+SECP256K1_B200_API int secp256k1_b200_ecmult_multi_combine_dev(secp256k1_b200_engine *e, unsigned char *d_out64, const unsigned char *d_partials96,
+        size_t count, void *stream);
+/* Bucket window: 0 (default) = chosen from n like secp256k1_pippenger_bucket_window (src/ecmult_impl.h:597-621); 4..16 forces it
+ * (the run-time counterpart of the reference's build-time ECMULT_WINDOW_SIZE knob; above 4096 terms at least 8).  Any value gives
+ * the same result. */
+SECP256K1_B200_API int secp256k1_b200_ecmult_multi_set_window(secp256k1_b200_engine *e, int window_bits);
 
 /* ---- surjection proofs and commitment tallies (Confidential Assets) ---------------------------- */
 /* secp256k1_surjectionproof_parse + _verify (include/secp256k1_surjectionproof.h:71, src/modules/surjection/main_impl.h:360) per item.

@@ -170,6 +170,50 @@ REF_EXPORT int ref_ge_is_valid(const unsigned char *a64) {
     return secp256k1_ge_is_valid_var(&a);
 }
 
+/* batched unit operations with the operand layout of secp256k1_b200_unit_op_batch (same op codes): scalar ops on n x 32 bytes, group
+ * ops on n x 96 bytes x||y||s lifted to the Jacobian point (x s^2, y s^3, s) with secp256k1_gej_rescale (group_impl.h:869) */
+REF_EXPORT void ref_unit_op_batch(int op, unsigned char *out, const unsigned char *a, const unsigned char *b, size_t n) {
+    size_t i;
+    for (i = 0; i < n; i++) {
+        if (op < 8) {
+            secp256k1_scalar x, y, r;
+            secp256k1_scalar_set_b32(&x, a + 32 * i, NULL);
+            if (b) secp256k1_scalar_set_b32(&y, b + 32 * i, NULL); else secp256k1_scalar_set_int(&y, 0);
+            if (op == 0) secp256k1_scalar_mul(&r, &x, &y);
+            else if (op == 1) secp256k1_scalar_add(&r, &x, &y);
+            else if (op == 2) secp256k1_scalar_negate(&r, &x);
+            else if (op == 3) secp256k1_scalar_inverse_var(&r, &x);
+            else if (op == 4) {
+                secp256k1_scalar r1, r2;
+                secp256k1_scalar_split_lambda(&r1, &r2, &x);
+                secp256k1_scalar_get_b32(out + 64 * i, &r1); secp256k1_scalar_get_b32(out + 64 * i + 32, &r2);
+                continue;
+            } else r = x;
+            secp256k1_scalar_get_b32(out + 32 * i, &r);
+        } else {
+            secp256k1_ge ga, gb; secp256k1_gej aj, bj, rj; secp256k1_fe s;
+            ref_ge_from_xy(&ga, a + 96 * i);
+            secp256k1_gej_set_ge(&aj, &ga);
+            if (!ga.infinity) {
+                secp256k1_fe_set_b32_mod(&s, a + 96 * i + 64);
+                if (secp256k1_fe_normalizes_to_zero_var(&s)) secp256k1_fe_set_int(&s, 1);
+                secp256k1_gej_rescale(&aj, &s);
+            }
+            if (b) ref_ge_from_xy(&gb, b + 96 * i); else secp256k1_ge_set_infinity(&gb);
+            secp256k1_gej_set_ge(&bj, &gb);
+            if (b && !gb.infinity) {
+                secp256k1_fe_set_b32_mod(&s, b + 96 * i + 64);
+                if (secp256k1_fe_normalizes_to_zero_var(&s)) secp256k1_fe_set_int(&s, 1);
+                secp256k1_gej_rescale(&bj, &s);
+            }
+            if ((op & 15) == 8) secp256k1_gej_double_var(&rj, &aj, NULL);
+            else if ((op & 15) == 9) secp256k1_gej_add_var(&rj, &aj, &bj, NULL);
+            else secp256k1_gej_add_ge_var(&rj, &aj, &gb, NULL);
+            ref_gej_to_xy(out + 64 * i, &rj);
+        }
+    }
+}
+
 /* ---- ecmult (ecmult_impl.h:365): R = na*A + ng*G ------------------------ */
 /* a64: affine x||y BE (zero = infinity); na32/ng32 BE scalars reduced mod n; ng32 may be NULL.
  * out: affine x||y or zero.  returns !infinity */

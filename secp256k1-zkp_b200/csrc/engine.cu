@@ -47,6 +47,7 @@ struct secp256k1_b200_engine {
     uint8_t* h_pinned;         // grow-only pinned host staging for results (a D2H copy into pageable memory would block the host
     size_t pinned_bytes;       //  and serialize the chunk pipeline)
     uint64_t launches;
+    int msm_window;            // 0 = chosen from n (msm_choose_c); otherwise forced (secp256k1_b200_ecmult_multi_set_window)
     std::mutex mu;             // the reference context is usable from many threads (secp256k1.h:42-49): serialize here
 
     gtable_dev gt() const { gtable_dev g; g.data = d_gtab; g.gw = gw; g.windows = windows; return g; }
@@ -122,7 +123,7 @@ int secp256k1_b200_engine_create(secp256k1_b200_engine** out, int device, int ge
     e->windows = (256 + gw - 1) / gw;
     e->gtab_bytes = (size_t)e->windows * ((size_t)1 << gw) * 64;
     e->d_gtab = nullptr; e->d_bases = nullptr; e->d_scratch = nullptr; e->scratch_bytes = 0; e->launches = 0;
-    e->h_pinned = nullptr; e->pinned_bytes = 0;
+    e->h_pinned = nullptr; e->pinned_bytes = 0; e->msm_window = 0;
     e->stream = nullptr; e->stream2 = nullptr;
     {
         sha256 h;
@@ -203,6 +204,26 @@ int secp256k1_b200_fe_op_batch(secp256k1_b200_engine* e, int op, unsigned char* 
     else CK(cudaMemsetAsync(c.at(ob), 0, 32 * n, e->stream));
     if (!secp256k1_b200_fe_op_batch_dev(e, op, c.at(oo), c.at(oa), c.at(ob), n, iters, e->stream)) return 0;
     CK(cudaMemcpyAsync(out32, c.at(oo), 32 * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
+/* unit kernels of the scalar / group primitives (parity hardening; k_unit.cu) */
+int secp256k1_b200_unit_op_batch(secp256k1_b200_engine* e, int op, unsigned char* out, const unsigned char* a, const unsigned char* b, size_t n) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    const bool scalar = op >= 0 && op <= 5, group = (op >= 8 && op <= 10) || (op >= 24 && op <= 26);
+    if (!scalar && !group) { set_error("unit_op: unknown op"); return 0; }
+    if (n == 0) return 1;
+    const size_t in_sz = scalar ? 32 : 96, out_sz = (scalar && op != 4) ? 32 : 64;
+    std::lock_guard<std::mutex> lock(e->mu);
+    device_guard guard(e->device);
+    carver c(e);
+    size_t oa = c.add(in_sz * n), ob = c.add(in_sz * n), oo = c.add(out_sz * n);
+    if (!c.commit()) return 0;
+    CK(cudaMemcpyAsync(c.at(oa), a, in_sz * n, cudaMemcpyHostToDevice, e->stream));
+    if (b) CK(cudaMemcpyAsync(c.at(ob), b, in_sz * n, cudaMemcpyHostToDevice, e->stream));
+    CK(launch_unit_op(op, c.at(oo), c.at(oa), b ? c.at(ob) : nullptr, n, e->stream, &e->launches));
+    CK(cudaMemcpyAsync(out, c.at(oo), out_sz * n, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return 1;
 }
@@ -395,7 +416,28 @@ int secp256k1_b200_ecmult_multi_dev(secp256k1_b200_engine* e, unsigned char* d_o
     if (!e) { set_error("engine is NULL"); return 0; }
     if (workspace_bytes < msm_workspace_bytes(n)) { set_error("ecmult_multi: workspace too small (see secp256k1_b200_ecmult_multi_workspace_bytes)"); return 0; }
     device_guard guard(e->device);
-    CK(launch_msm(d_out64, d_g_scalar32, d_scalars32, d_points64, n, (uint8_t*)d_workspace, workspace_bytes, (cudaStream_t)stream, &e->launches));
+    CK(launch_msm(d_out64, 0, d_g_scalar32, d_scalars32, d_points64, n, (uint8_t*)d_workspace, workspace_bytes, e->msm_window, (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_ecmult_multi_partial_dev(secp256k1_b200_engine* e, unsigned char* d_out96, const unsigned char* d_g_scalar32,
+                                            const unsigned char* d_scalars32, const unsigned char* d_points64, size_t n,
+                                            void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (workspace_bytes < msm_workspace_bytes(n)) { set_error("ecmult_multi: workspace too small (see secp256k1_b200_ecmult_multi_workspace_bytes)"); return 0; }
+    device_guard guard(e->device);
+    CK(launch_msm(d_out96, 1, d_g_scalar32, d_scalars32, d_points64, n, (uint8_t*)d_workspace, workspace_bytes, e->msm_window, (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_ecmult_multi_combine_dev(secp256k1_b200_engine* e, unsigned char* d_out64, const unsigned char* d_partials96, size_t count, void* stream) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    device_guard guard(e->device);
+    CK(launch_gej_sum(d_out64, d_partials96, count, (cudaStream_t)stream, &e->launches));
+    return 1;
+}
+int secp256k1_b200_ecmult_multi_set_window(secp256k1_b200_engine* e, int window_bits) {
+    if (!e) { set_error("engine is NULL"); return 0; }
+    if (window_bits != 0 && (window_bits < 4 || window_bits > 16)) { set_error("ecmult_multi_set_window: window_bits must be 0 (auto) or in [4,16]"); return 0; }
+    e->msm_window = window_bits;
     return 1;
 }
 int secp256k1_b200_ecmult_multi(secp256k1_b200_engine* e, unsigned char* out64, const unsigned char* g_scalar32,

@@ -1,192 +1,523 @@
-// k_msm.cu -- Pippenger multi-scalar multiplication kernels (see msm.cuh for the algorithm).
+// k_msm.cu -- Pippenger multi-scalar multiplication kernels (see msm.cuh for the algorithm and what it replaces).
+//
+// Launch sequence of one MSM (all on the caller's stream, no host synchronisation, every size decided on the device):
+//   memset            hist / counters / buckets
+//   k_msm_prepare     thread per term: parse, GLV split, signed digits -> (window,bucket) histogram
+//   k_msm_scan_a/_b   two-level exclusive scan of the histogram: entry offsets, piece offsets, part offsets, list of multi-piece buckets
+//   k_msm_scatter     thread per term: counting-sort scatter of (term index | sign) by (window,bucket)
+//   k_msm_units       thread per piece: piece -> (first entry, count, destination)
+//   k_msm_bucket_sum  persistent warps, one lane per piece, lanes pull the next piece when theirs is done (mixed additions)
+//   k_msm_combine     block per multi-piece (hot) bucket: strided partial sums + warp-shuffle tree
+//   k_msm_r1          running sums over chunks of 8 buckets (thread per chunk, or 4 lanes per chunk when chunks are few)
+//   k_msm_r2          block per (window, sum): plain sum of the chunk L's, bit sums of the chunk A's
+//   k_msm_tail        one block: per-window bit-Horner (4 lanes per window), two window-Horner chains (4 lanes each), join, to affine
 #include "msm.cuh"
-#include "gtable.cuh"
+#include "ge_g4.cuh"
 #include "launch.h"
 
 namespace b200 {
 
 struct msm_ws {
-    uint32_t* scalars;     // [N][8]   reduced scalars, LE limbs
-    uint32_t* points;      // [N][16]  affine LE storage, zero = infinity
-    uint32_t* hist;        // [16][32768]
-    uint32_t* offsets;     // [16][32768]
-    uint32_t* cursor;      // [16][32768]
-    uint32_t* entries;     // [16][N]
-    gej_store* buckets;    // [16][32768]
-    gej_store* chunks;     // [16][1024]
-    gej_store* groups;     // [16][32]
-    gej_store* windows;    // [16]
+    uint32_t* k12;       // [N][8]     |k1|, |k2| (4 + 4 LE limbs)
+    uint8_t* flags;      // [N]
+    uint8_t* gpoint;     // [64]       generator, x||y big-endian (term N-1)
+    uint32_t* hist;      // [TB]       counts; the scatter counts them back down to zero
+    uint32_t* off;       // [TB+1]     first sorted entry of a bucket
+    uint32_t* pbase;     // [TB+1]     first piece (unit) of a bucket
+    uint32_t* mbase;     // [TB+1]     first slot in `parts` of a multi-piece bucket
+    uint32_t* blocktot;  // [nblk][4]
+    uint32_t* counters;  // [4]        [0] = number of multi-piece buckets
+    uint32_t* multi;     // [cap_multi]
+    uint32_t* entries;   // [2*nw*N]
+    msm_unit* units;     // [cap_units]
+    gej_store* buckets;  // [TB]
+    gej_store* parts;    // [cap_parts]
+    gej_store* Lq;       // [TB/8]
+    gej_store* Aq;       // [TB/8]
+    gej_store* T;        // [2*nw][MSM_MAX_SUMS]
 };
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-size_t msm_workspace_bytes(size_t n_terms) {
-    size_t N = n_terms + 1;   // + optional generator term
-    size_t b = 0;
-    b += align256(N * 32) + align256(N * 64);
-    b += 3 * align256((size_t)MSM_WINDOWS * MSM_BUCKETS * 4);
-    b += align256((size_t)MSM_WINDOWS * N * 4);
-    b += align256((size_t)MSM_WINDOWS * MSM_BUCKETS * sizeof(gej_store));
-    b += align256((size_t)MSM_WINDOWS * MSM_CHUNKS * sizeof(gej_store));
-    b += align256((size_t)MSM_WINDOWS * 32 * sizeof(gej_store));
-    b += align256((size_t)MSM_WINDOWS * sizeof(gej_store));
-    return b;
+struct msm_caps { size_t emax, cap_multi, cap_parts, cap_units, nblk; };
+static msm_caps caps_of(const msm_plan& p) {
+    msm_caps c;
+    c.emax = (size_t)2 * p.nw * p.N;
+    c.cap_multi = c.emax / p.Tp + 1;
+    c.cap_parts = 2 * (c.emax / p.Tp) + 2;
+    c.cap_units = (c.emax < p.TB ? c.emax : p.TB) + c.emax / p.Tp + 1;
+    c.nblk = (p.TB + MSM_SCAN_ELEMS - 1) / MSM_SCAN_ELEMS;
+    return c;
 }
-static msm_ws carve_ws(uint8_t* base, size_t N) {
-    msm_ws w;
+static size_t carve(msm_ws* w, uint8_t* base, const msm_plan& p) {
+    const msm_caps c = caps_of(p);
     size_t o = 0;
-    w.scalars = (uint32_t*)(base + o); o += align256(N * 32);
-    w.points = (uint32_t*)(base + o); o += align256(N * 64);
-    w.hist = (uint32_t*)(base + o); o += align256((size_t)MSM_WINDOWS * MSM_BUCKETS * 4);
-    w.offsets = (uint32_t*)(base + o); o += align256((size_t)MSM_WINDOWS * MSM_BUCKETS * 4);
-    w.cursor = (uint32_t*)(base + o); o += align256((size_t)MSM_WINDOWS * MSM_BUCKETS * 4);
-    w.entries = (uint32_t*)(base + o); o += align256((size_t)MSM_WINDOWS * N * 4);
-    w.buckets = (gej_store*)(base + o); o += align256((size_t)MSM_WINDOWS * MSM_BUCKETS * sizeof(gej_store));
-    w.chunks = (gej_store*)(base + o); o += align256((size_t)MSM_WINDOWS * MSM_CHUNKS * sizeof(gej_store));
-    w.groups = (gej_store*)(base + o); o += align256((size_t)MSM_WINDOWS * 32 * sizeof(gej_store));
-    w.windows = (gej_store*)(base + o);
-    return w;
+    auto take = [&](size_t bytes) { size_t at = o; o += align256(bytes); return base ? base + at : (uint8_t*)nullptr; };
+    uint8_t* q;
+    q = take((size_t)p.N * 32); if (w) w->k12 = (uint32_t*)q;
+    q = take(p.N); if (w) w->flags = q;
+    q = take(64); if (w) w->gpoint = q;
+    q = take((size_t)p.TB * 4); if (w) w->hist = (uint32_t*)q;           // hist and counters are adjacent: one memset
+    q = take(16); if (w) w->counters = (uint32_t*)q;
+    q = take((size_t)(p.TB + 1) * 4); if (w) w->off = (uint32_t*)q;
+    q = take((size_t)(p.TB + 1) * 4); if (w) w->pbase = (uint32_t*)q;
+    q = take((size_t)(p.TB + 1) * 4); if (w) w->mbase = (uint32_t*)q;
+    q = take(c.nblk * 16); if (w) w->blocktot = (uint32_t*)q;
+    q = take(c.cap_multi * 4); if (w) w->multi = (uint32_t*)q;
+    q = take(c.emax * 4); if (w) w->entries = (uint32_t*)q;
+    q = take(c.cap_units * sizeof(msm_unit)); if (w) w->units = (msm_unit*)q;
+    q = take((size_t)p.TB * sizeof(gej_store)); if (w) w->buckets = (gej_store*)q;
+    q = take(c.cap_parts * sizeof(gej_store)); if (w) w->parts = (gej_store*)q;
+    q = take((size_t)(p.TB / MSM_CHUNK) * sizeof(gej_store)); if (w) w->Lq = (gej_store*)q;
+    q = take((size_t)(p.TB / MSM_CHUNK) * sizeof(gej_store)); if (w) w->Aq = (gej_store*)q;
+    q = take((size_t)2 * p.nw * MSM_MAX_SUMS * sizeof(gej_store)); if (w) w->T = (gej_store*)q;
+    return o;
+}
+// window widths a caller may force (secp256k1_b200_ecmult_multi_set_window); the workspace is sized for the worst of them
+static bool c_allowed(size_t N, int c) { return c >= (N <= 4096 ? MSM_C_MIN : 8) && c <= MSM_C_MAX; }
+size_t msm_workspace_bytes(size_t n_terms) {
+    size_t best = 0;
+    for (int c = MSM_C_MIN; c <= MSM_C_MAX; c++) {
+        if (!c_allowed(n_terms + 1, c)) continue;
+        msm_plan p;
+        msm_make_plan_c(p, n_terms + 1, (uint32_t)c);
+        size_t b = carve(nullptr, nullptr, p);
+        if (b > best) best = b;
+    }
+    return best;
 }
 
-// (1) parse + histogram.  Term N-1 is the optional generator term (g_scalar * G).
-__global__ void __launch_bounds__(256) k_msm_prepare(msm_ws ws, const uint8_t* __restrict__ scalars32, const uint8_t* __restrict__ points64,
-                                                     const uint8_t* __restrict__ g_scalar32, size_t n, size_t N) {
+// ---- (1) parse + GLV split + histogram ---------------------------------------------------------------------------------------
+struct emit_hist {
+    uint32_t* hist;
+    HD void operator()(uint32_t bucket, uint32_t) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(&hist[bucket], 1u);
+#else
+        hist[bucket]++;
+#endif
+    }
+};
+__global__ void __launch_bounds__(256) k_msm_prepare(msm_ws ws, msm_plan p, const uint8_t* __restrict__ scalars32, const uint8_t* __restrict__ points64,
+                                                     const uint8_t* __restrict__ g_scalar32, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+    if (i >= p.N) return;
     sc k;
-    uint32_t p16[16];
+    int inf;
+    __align__(16) uint8_t b[64];
     if (i < n) {
-        uint8_t b[32];
-        for (int t = 0; t < 32; t++) b[t] = scalars32[32 * i + t];
+        const uint8_t* s = scalars32 + 32 * i;
+        if ((reinterpret_cast<uintptr_t>(s) & 15) == 0) { const uint4* q = reinterpret_cast<const uint4*>(s); uint4* d = reinterpret_cast<uint4*>(b); d[0] = __ldg(q); d[1] = __ldg(q + 1); }
+        else for (int t = 0; t < 32; t++) b[t] = __ldg(s + t);
         sc_set_b32(k, b);
-        fe x, y;
-        uint8_t pb[64];
-        for (int t = 0; t < 64; t++) pb[t] = points64[64 * i + t];
-        bn_from_be32(x.v, pb); bn_from_be32(y.v, pb + 32);
-        for (int t = 0; t < 8; t++) { p16[t] = x.v[t]; p16[8 + t] = y.v[t]; }
+        const uint8_t* pt = points64 + 64 * i;
+        uint32_t z = 0;
+        if ((reinterpret_cast<uintptr_t>(pt) & 15) == 0) {
+            const uint4* q = reinterpret_cast<const uint4*>(pt);
+#pragma unroll
+            for (int t = 0; t < 4; t++) { uint4 v = __ldg(q + t); z |= v.x | v.y | v.z | v.w; }
+        } else for (int t = 0; t < 64; t++) z |= __ldg(pt + t);
+        inf = (z == 0);
     } else {
-        if (g_scalar32) {
-            uint8_t b[32];
-            for (int t = 0; t < 32; t++) b[t] = g_scalar32[t];
-            sc_set_b32(k, b);
-        } else sc_set_zero(k);
+        if (g_scalar32) { for (int t = 0; t < 32; t++) b[t] = g_scalar32[t]; sc_set_b32(k, b); } else sc_set_zero(k);
+        inf = 0;
         ge g; ge_set_generator(g);
-        for (int t = 0; t < 8; t++) { p16[t] = g.x.v[t]; p16[8 + t] = g.y.v[t]; }
+        fe_get_b32(b, g.x); fe_get_b32(b + 32, g.y);
+        for (int t = 0; t < 64; t++) ws.gpoint[t] = b[t];
     }
-    for (int t = 0; t < 8; t++) ws.scalars[8 * i + t] = k.v[t];
-    uint32_t z = 0;
-    for (int t = 0; t < 16; t++) { ws.points[16 * i + t] = p16[t]; z |= p16[t]; }
-    if (z == 0) return;                      // infinity contributes nothing
-    int32_t d[MSM_WINDOWS];
-    msm_digits(d, k);
-#pragma unroll
-    for (int w = 0; w < MSM_WINDOWS; w++) {
-        if (d[w] != 0) {
-            uint32_t b = (uint32_t)(d[w] < 0 ? -d[w] : d[w]) - 1u;
-            atomicAdd(&ws.hist[(size_t)w * MSM_BUCKETS + b], 1u);
-        }
-    }
+    uint32_t k12[8], flags;
+    msm_prepare_term(k12, flags, k, inf);
+    uint4* o = reinterpret_cast<uint4*>(ws.k12 + 8 * i);
+    o[0] = make_uint4(k12[0], k12[1], k12[2], k12[3]);
+    o[1] = make_uint4(k12[4], k12[5], k12[6], k12[7]);
+    ws.flags[i] = (uint8_t)flags;
+    if (flags & 4u) return;
+    emit_hist em = {ws.hist};
+    msm_emit_digits(p, k12, flags & 1u, 0, em);
+    msm_emit_digits(p, k12 + 4, (flags >> 1) & 1u, 1, em);
 }
 
-// (2) exclusive scan of the 32768 bucket counts of one window per block (1024 threads x 32 buckets)
-__global__ void __launch_bounds__(1024) k_msm_scan(msm_ws ws) {
-    __shared__ uint32_t part[1024];
-    const uint32_t w = blockIdx.x, t = threadIdx.x;
-    const uint32_t* h = ws.hist + (size_t)w * MSM_BUCKETS + t * 32;
-    uint32_t local[32], sum = 0;
-    for (int k = 0; k < 32; k++) { local[k] = sum; sum += h[k]; }
-    part[t] = sum;
+// ---- (2) scan: offsets of entries / pieces / parts ---------------------------------------------------------------------------
+struct scan3 { uint32_t a, b, c; };
+__device__ __forceinline__ scan3 scan3_add(scan3 x, scan3 y) { scan3 r = {x.a + y.a, x.b + y.b, x.c + y.c}; return r; }
+// exclusive scan of one scan3 per thread across a 1024-thread block; returns the block total through `total`
+__device__ scan3 block_exclusive_scan3(scan3 v, scan3& total) {
+    __shared__ scan3 warp_tot[32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    scan3 inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        scan3 o;
+        o.a = __shfl_up_sync(0xffffffffu, inc.a, d); o.b = __shfl_up_sync(0xffffffffu, inc.b, d); o.c = __shfl_up_sync(0xffffffffu, inc.c, d);
+        if ((int)lane >= d) inc = scan3_add(inc, o);
+    }
+    if (lane == 31) warp_tot[wid] = inc;
     __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partial sums
-    for (uint32_t off = 1; off < 1024; off <<= 1) {
-        uint32_t v = (t >= off) ? part[t - off] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
+    if (wid == 0) {
+        scan3 w = {0, 0, 0};
+        if (lane < nw) w = warp_tot[lane];
+        scan3 winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            scan3 o;
+            o.a = __shfl_up_sync(0xffffffffu, winc.a, d); o.b = __shfl_up_sync(0xffffffffu, winc.b, d); o.c = __shfl_up_sync(0xffffffffu, winc.c, d);
+            if ((int)lane >= d) winc = scan3_add(winc, o);
+        }
+        warp_tot[lane] = winc;                      // inclusive over warps
     }
-    uint32_t base = part[t] - sum;
-    uint32_t* o = ws.offsets + (size_t)w * MSM_BUCKETS + t * 32;
-    uint32_t* c = ws.cursor + (size_t)w * MSM_BUCKETS + t * 32;
-    for (int k = 0; k < 32; k++) { o[k] = base + local[k]; c[k] = 0; }
+    __syncthreads();
+    total = warp_tot[nw - 1];
+    scan3 base = {0, 0, 0};
+    if (wid > 0) base = warp_tot[wid - 1];
+    scan3 ex = {base.a + inc.a - v.a, base.b + inc.b - v.b, base.c + inc.c - v.c};
+    __syncthreads();
+    return ex;
+}
+__device__ __forceinline__ uint32_t msm_pieces(uint32_t cnt, uint32_t Tp) { return (cnt + Tp - 1) / Tp; }
+
+__global__ void __launch_bounds__(1024) k_msm_scan_a(msm_ws ws, msm_plan p) {
+    const uint32_t first = blockIdx.x * MSM_SCAN_ELEMS + threadIdx.x * 4;
+    uint32_t cnt[4];
+    scan3 mine = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        cnt[k] = (first + k < p.TB) ? ws.hist[first + k] : 0;
+        uint32_t pc = msm_pieces(cnt[k], p.Tp);
+        mine.a += cnt[k]; mine.b += pc; mine.c += (pc > 1 ? pc : 0);
+    }
+    scan3 total;
+    scan3 ex = block_exclusive_scan3(mine, total);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (first + k < p.TB) { ws.off[first + k] = ex.a; ws.pbase[first + k] = ex.b; ws.mbase[first + k] = ex.c; }
+        uint32_t pc = msm_pieces(cnt[k], p.Tp);
+        ex.a += cnt[k]; ex.b += pc; ex.c += (pc > 1 ? pc : 0);
+    }
+    if (threadIdx.x == 0) { ws.blocktot[4 * blockIdx.x] = total.a; ws.blocktot[4 * blockIdx.x + 1] = total.b; ws.blocktot[4 * blockIdx.x + 2] = total.c; }
+}
+__global__ void __launch_bounds__(1024) k_msm_scan_b(msm_ws ws, msm_plan p) {
+    // base of this block = sum of the totals of the blocks before it (<= 288 of them: every thread strides, then a block reduction)
+    scan3 part = {0, 0, 0};
+    for (uint32_t b = threadIdx.x; b < blockIdx.x; b += blockDim.x) { part.a += ws.blocktot[4 * b]; part.b += ws.blocktot[4 * b + 1]; part.c += ws.blocktot[4 * b + 2]; }
+    scan3 base;
+    block_exclusive_scan3(part, base);
+    const uint32_t first = blockIdx.x * MSM_SCAN_ELEMS + threadIdx.x * 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t i = first + k;
+        if (i >= p.TB) break;
+        ws.off[i] += base.a; ws.pbase[i] += base.b; ws.mbase[i] += base.c;
+        if (msm_pieces(ws.hist[i], p.Tp) > 1) ws.multi[atomicAdd(&ws.counters[0], 1u)] = i;
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        ws.off[p.TB] = base.a + ws.blocktot[4 * blockIdx.x];
+        ws.pbase[p.TB] = base.b + ws.blocktot[4 * blockIdx.x + 1];
+        ws.mbase[p.TB] = base.c + ws.blocktot[4 * blockIdx.x + 2];
+    }
 }
 
-// (3) counting-sort scatter
-__global__ void __launch_bounds__(256) k_msm_scatter(msm_ws ws, size_t N) {
+// ---- (3) counting-sort scatter -----------------------------------------------------------------------------------------------
+struct emit_scatter {
+    const uint32_t* off; uint32_t* hist; uint32_t* entries; uint32_t idx;
+    HD void operator()(uint32_t bucket, uint32_t sgn) {
+#if defined(__CUDA_ARCH__)
+        uint32_t pos = off[bucket] + atomicSub(&hist[bucket], 1u) - 1u;
+#else
+        uint32_t pos = off[bucket] + (hist[bucket]--) - 1u;
+#endif
+        entries[pos] = idx | (sgn << 31);
+    }
+};
+__global__ void __launch_bounds__(256) k_msm_scatter(msm_ws ws, msm_plan p) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    uint32_t z = 0;
-    for (int t = 0; t < 16; t++) z |= ws.points[16 * i + t];
-    if (z == 0) return;
-    sc k;
-    for (int t = 0; t < 8; t++) k.v[t] = ws.scalars[8 * i + t];
-    int32_t d[MSM_WINDOWS];
-    msm_digits(d, k);
+    if (i >= p.N) return;
+    uint32_t flags = ws.flags[i];
+    if (flags & 4u) return;
+    const uint4* q = reinterpret_cast<const uint4*>(ws.k12 + 8 * i);
+    uint4 a = q[0], b = q[1];
+    uint32_t k1[4] = {a.x, a.y, a.z, a.w}, k2[4] = {b.x, b.y, b.z, b.w};
+    emit_scatter em = {ws.off, ws.hist, ws.entries, (uint32_t)i};
+    msm_emit_digits(p, k1, flags & 1u, 0, em);
+    msm_emit_digits(p, k2, (flags >> 1) & 1u, 1, em);
+}
+
+// ---- (3b) pieces -> unit descriptors -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_msm_units(msm_ws ws, msm_plan p) {
+    uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t P = ws.pbase[p.TB];
+    if (u >= P) return;
+    // largest bucket b with pbase[b] <= u  (empty buckets share their pbase with the next one; the last of a run is the non-empty one)
+    uint32_t lo = 0, hi = p.TB;                    // invariant: pbase[lo] <= u < pbase[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (ws.pbase[mid] <= u) lo = mid; else hi = mid;
+    }
+    const uint32_t b = lo, j = u - ws.pbase[b];
+    const uint32_t beg = ws.off[b], end = ws.off[b + 1], npieces = ws.pbase[b + 1] - ws.pbase[b];
+    msm_unit d;
+    d.begin = beg + j * p.Tp;
+    d.count = (end - d.begin < p.Tp) ? end - d.begin : p.Tp;
+    d.dst = (npieces == 1) ? b : (MSM_DST_PART | (ws.mbase[b] + j));
+    d.bucket = b;
+    ws.units[u] = d;
+}
+
+// ---- (4) bucket sums: one lane per piece, lanes of a warp pull pieces dynamically --------------------------------------------
+__device__ __forceinline__ void store_gej_vec(gej_store* dst, const gej& a) {
+    gej_store s;
+    msm_store_gej(s, a);
+    uint4* o = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-    for (int w = 0; w < MSM_WINDOWS; w++) {
-        if (d[w] != 0) {
-            uint32_t neg = d[w] < 0;
-            uint32_t b = (uint32_t)(neg ? -d[w] : d[w]) - 1u;
-            size_t wb = (size_t)w * MSM_BUCKETS + b;
-            uint32_t pos = ws.offsets[wb] + atomicAdd(&ws.cursor[wb], 1u);
-            ws.entries[(size_t)w * N + pos] = (uint32_t)i | (neg << 31);
+    for (int k = 0; k < 6; k++) o[k] = make_uint4(s.w[4 * k], s.w[4 * k + 1], s.w[4 * k + 2], s.w[4 * k + 3]);
+}
+__device__ __forceinline__ void load_gej_vec(gej& a, const gej_store* src) {
+    gej_store s;
+    const uint4* q = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int k = 0; k < 6; k++) { uint4 v = q[k]; s.w[4 * k] = v.x; s.w[4 * k + 1] = v.y; s.w[4 * k + 2] = v.z; s.w[4 * k + 3] = v.w; }
+    msm_load_gej(a, s);
+}
+#ifndef MSM_SUM_MINBLOCKS
+#define MSM_SUM_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(128, MSM_SUM_MINBLOCKS) k_msm_bucket_sum(msm_ws ws, msm_plan p, const uint8_t* __restrict__ points64, size_t n) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t P = ws.pbase[p.TB];
+    const uint32_t R = (P + nwarps - 1) / nwarps;                 // pieces per warp (contiguous range)
+    uint64_t first = (uint64_t)wid * R;
+    if (first >= P) return;                                       // whole warp
+    uint32_t next = (uint32_t)first;
+    const uint32_t uend = (first + R < P) ? (uint32_t)(first + R) : P;
+    bool have = false;
+    uint32_t e = 0, eend = 0, dst = 0;
+    gej acc;
+    gej_set_infinity(acc);
+    while (true) {
+        const uint32_t mask = __ballot_sync(0xffffffffu, !have);
+        if (!have) {
+            uint32_t my = next + __popc(mask & ((1u << lane) - 1u));
+            if (my < uend) {
+                const uint4 d = *reinterpret_cast<const uint4*>(ws.units + my);
+                e = d.x; eend = d.x + d.y; dst = d.z;
+                gej_set_infinity(acc);
+                have = true;
+            }
+        }
+        next += __popc(mask);
+        if (next > uend) next = uend;
+        if (!__any_sync(0xffffffffu, have)) break;
+        if (have) {
+            uint32_t v = ws.entries[e];
+            ge pt;
+            msm_load_point(pt, points64, n, ws.gpoint, v & 0x7FFFFFFFu);
+            if (v >> 31) fe_neg(pt.y, pt.y);
+            gej t;
+            gej_add_ge(t, acc, pt);
+            acc = t;
+            if (++e == eend) {
+                store_gej_vec((dst & MSM_DST_PART) ? ws.parts + (dst & ~MSM_DST_PART) : ws.buckets + dst, acc);
+                have = false;
+            }
         }
     }
 }
 
-// (4) one thread per bucket
-__global__ void __launch_bounds__(128) k_msm_bucket_sum(msm_ws ws, size_t N) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (size_t)MSM_WINDOWS * MSM_BUCKETS) return;
-    uint32_t w = (uint32_t)(t / MSM_BUCKETS);
-    uint32_t begin = ws.offsets[t], end = begin + ws.hist[t];
+// ---- (4b) multi-piece buckets: block per bucket, strided sums, warp-shuffle tree ----------------------------------------------
+__device__ __forceinline__ void gej_shfl_down(gej& o, const gej& a, int delta) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        o.x.v[k] = __shfl_down_sync(0xffffffffu, a.x.v[k], delta);
+        o.y.v[k] = __shfl_down_sync(0xffffffffu, a.y.v[k], delta);
+        o.z.v[k] = __shfl_down_sync(0xffffffffu, a.z.v[k], delta);
+    }
+    o.inf = __shfl_down_sync(0xffffffffu, a.inf, delta);
+}
+// sum of `acc` over the block's threads, result valid in thread 0.  scratch: one gej_store per warp.
+__device__ void block_sum_gej(gej& acc, gej_store* scratch) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        gej o, t;
+        gej_shfl_down(o, acc, d);
+        if ((int)lane < d) { gej_add(t, acc, o); acc = t; }
+    }
+    __syncthreads();
+    if (lane == 0) msm_store_gej(scratch[wid], acc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll 1
+        for (uint32_t w = 1; w < nw; w++) { gej o, t; msm_load_gej(o, scratch[w]); gej_add(t, acc, o); acc = t; }
+    }
+}
+__global__ void __launch_bounds__(256) k_msm_combine(msm_ws ws, msm_plan p) {
+    __shared__ gej_store scratch[8];
+    const uint32_t nm = ws.counters[0];
+    for (uint32_t i = blockIdx.x; i < nm; i += gridDim.x) {
+        const uint32_t b = ws.multi[i];
+        const uint32_t K = ws.pbase[b + 1] - ws.pbase[b], base = ws.mbase[b];
+        gej acc;
+        gej_set_infinity(acc);
+#pragma unroll 1
+        for (uint32_t k = threadIdx.x; k < K; k += blockDim.x) { gej o, t; load_gej_vec(o, ws.parts + base + k); gej_add(t, acc, o); acc = t; }
+        block_sum_gej(acc, scratch);
+        if (threadIdx.x == 0) store_gej_vec(ws.buckets + b, acc);
+        __syncthreads();
+    }
+}
+
+// ---- (5) running sums over chunks of 8 buckets --------------------------------------------------------------------------------
+template <bool G4>
+__global__ void __launch_bounds__(128) k_msm_r1(msm_ws ws, msm_plan p) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t q = G4 ? (t >> 2) : t;
+    if (q >= p.TB / MSM_CHUNK) return;                 // G4: whole groups leave together
+    const gej_store* s8 = ws.buckets + (size_t)q * MSM_CHUNK;
+    gej running, acc;
+    gej_set_infinity(running);
+    gej_set_infinity(acc);
+#pragma unroll 1
+    for (int j = MSM_CHUNK - 1; j >= 0; j--) {
+        gej s, tt;
+        load_gej_vec(s, s8 + j);
+        if (G4) { gej_add_g4(tt, running, s); running = tt; gej_add_g4(tt, acc, running); acc = tt; }
+        else { gej_add(tt, running, s); running = tt; gej_add(tt, acc, running); acc = tt; }
+    }
+    if (!G4 || (threadIdx.x & 3) == 0) { store_gej_vec(ws.Lq + q, acc); store_gej_vec(ws.Aq + q, running); }
+}
+
+// ---- (6) per window: plain sum of the L's, bit sums of the A's ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_msm_r2(msm_ws ws, msm_plan p) {
+    __shared__ gej_store scratch[8];
+    const uint32_t wi = blockIdx.x / MSM_MAX_SUMS, s = blockIdx.x % MSM_MAX_SUMS;
+    msm_win w;
+    msm_window_by_index(w, p, wi);
+    const uint32_t Q = w.Bw / MSM_CHUNK, nbits = msm_ilog2(Q), cb = w.base / MSM_CHUNK;
+    if (s > nbits) return;
+    const uint32_t count = (s == 0) ? Q : Q / 2;
     gej acc;
-    msm_bucket_sum(acc, ws.entries + (size_t)w * N, begin, end, ws.points);
-    msm_store_gej(ws.buckets[t], acc);
+    gej_set_infinity(acc);
+#pragma unroll 1
+    for (uint32_t k = threadIdx.x; k < count; k += blockDim.x) {
+        gej o, t;
+        if (s == 0) load_gej_vec(o, ws.Lq + cb + k);
+        else load_gej_vec(o, ws.Aq + cb + msm_bit_index(k, s - 1));
+        gej_add(t, acc, o); acc = t;
+    }
+    block_sum_gej(acc, scratch);
+    if (threadIdx.x == 0) store_gej_vec(ws.T + (size_t)wi * MSM_MAX_SUMS + s, acc);
 }
 
-// (5) chunk reduction
-__global__ void __launch_bounds__(128) k_msm_chunks(msm_ws ws) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (size_t)MSM_WINDOWS * MSM_CHUNKS) return;
-    uint32_t w = (uint32_t)(t / MSM_CHUNKS), ch = (uint32_t)(t % MSM_CHUNKS);
-    gej out;
-    msm_chunk_reduce(out, ws.buckets + (size_t)w * MSM_BUCKETS, ch * MSM_CHUNK);
-    msm_store_gej(ws.chunks[t], out);
-}
-// (6a) 32 chunks -> 1 group ; (6b) 32 groups -> window sum
-__global__ void __launch_bounds__(64) k_msm_groups(gej_store* dst, const gej_store* src, uint32_t ndst, uint32_t per) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ndst) return;
-    gej out;
-    msm_sum_range(out, src + (size_t)t * per, per);
-    msm_store_gej(dst[t], out);
-}
-// (6c) Horner over the windows, to affine, serialize x||y big-endian (zero = infinity)
-__global__ void k_msm_final(uint8_t* out64, msm_ws ws) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    gej r;
-    msm_horner(r, ws.windows);
-    if (r.inf) { for (int k = 0; k < 64; k++) out64[k] = 0; return; }
+// ---- (7) tail: window sums, Horner, join, output ------------------------------------------------------------------------------
+// mode 0: out = affine x||y big-endian (64 bytes, zeros = infinity); mode 1: out = gej_store (96 bytes) for a later k_gej_sum
+__device__ void write_result(uint8_t* out, const gej& r, int mode) {
+    if (mode == 1) { gej_store s; msm_store_gej(s, r); uint32_t* o = reinterpret_cast<uint32_t*>(out); for (int k = 0; k < 24; k++) o[k] = s.w[k]; return; }
+    if (r.inf) { for (int k = 0; k < 64; k++) out[k] = 0; return; }
     ge a; ge_set_gej(a, r);
-    fe_get_b32(out64, a.x); fe_get_b32(out64 + 32, a.y);
+    fe_get_b32(out, a.x); fe_get_b32(out + 32, a.y);
+}
+__global__ void __launch_bounds__(256) k_msm_tail(uint8_t* out, int mode, msm_ws ws, msm_plan p) {
+    __shared__ gej W[2 * 32];
+    __shared__ gej H[2];
+    const uint32_t g = threadIdx.x >> 2, l = threadIdx.x & 3;
+    for (uint32_t wi = g; wi < 2 * p.nw; wi += blockDim.x >> 2) {
+        msm_win w;
+        msm_window_by_index(w, p, wi);
+        gej r;
+        msm_window_from_sums(r, ws.T + (size_t)wi * MSM_MAX_SUMS, msm_ilog2(w.Bw / MSM_CHUNK));
+        if (l == 0) W[wi] = r;
+    }
+    __syncthreads();
+    if (g < 2) {
+        gej r;
+        msm_horner_half(r, W + g * p.nw, p);
+        if (l == 0) H[g] = r;
+    }
+    __syncthreads();
+    if (g == 0) {
+        gej r;
+        msm_join_halves(r, H[0], H[1]);
+        if (l == 0) write_result(out, r, mode);
+    }
 }
 
-cudaError_t launch_msm(uint8_t* out64, const uint8_t* g_scalar32, const uint8_t* scalars32, const uint8_t* points64, size_t n,
-                       uint8_t* workspace, size_t workspace_bytes, cudaStream_t s, uint64_t* launches) {
-    if (workspace_bytes < msm_workspace_bytes(n)) return cudaErrorInvalidValue;
+// sum of `count` stored Jacobian points (the per-GPU partial results of a sharded MSM) -> affine x||y big-endian
+__global__ void __launch_bounds__(128) k_gej_sum(uint8_t* out64, const uint8_t* partials96, uint32_t count) {
+    __shared__ gej S[32];
+    const uint32_t g = threadIdx.x >> 2, l = threadIdx.x & 3, ng = blockDim.x >> 2;
+    gej acc;
+    gej_set_infinity(acc);
+    for (uint32_t k = g; k < count; k += ng) {
+        gej o, t;
+        gej_store s;
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(partials96 + (size_t)96 * k);
+        for (int j = 0; j < 24; j++) s.w[j] = q[j];
+        msm_load_gej(o, s);
+        gej_add_g4(t, acc, o); acc = t;
+    }
+    if (l == 0) S[g] = acc;
+    __syncthreads();
+    for (uint32_t d = ng >> 1; d >= 1; d >>= 1) {
+        if (g < d) {
+            gej a = S[g], b = S[g + d], t;
+            gej_add_g4(t, a, b);
+            if (l == 0) S[g] = t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) write_result(out64, S[0], 0);
+}
+
+static int sum_grid_blocks() {
+    static int cached = 0;
+    if (cached) return cached;
+    int dev = 0, sms = 148, per = MSM_SUM_MINBLOCKS;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_msm_bucket_sum, 128, 0) != cudaSuccess || per < 1) per = MSM_SUM_MINBLOCKS;
+    cached = sms * per;
+    return cached;
+}
+
+cudaError_t launch_msm(uint8_t* out, int out_mode, const uint8_t* g_scalar32, const uint8_t* scalars32, const uint8_t* points64, size_t n,
+                       uint8_t* workspace, size_t workspace_bytes, int window_bits, cudaStream_t s, uint64_t* launches) {
     if (n + 1 >= ((size_t)1 << 31)) return cudaErrorInvalidValue;
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return cudaErrorInvalidValue;
     const size_t N = n + 1;
-    msm_ws ws = carve_ws(workspace, N);
-    cudaError_t err = cudaMemsetAsync(ws.hist, 0, (size_t)MSM_WINDOWS * MSM_BUCKETS * 4, s);
+    int c = window_bits ? window_bits : (int)msm_choose_c(N);
+    if (!c_allowed(N, c)) return cudaErrorInvalidValue;
+    msm_plan p;
+    msm_make_plan_c(p, N, (uint32_t)c);
+    msm_ws ws;
+    if (carve(&ws, workspace, p) > workspace_bytes) return cudaErrorInvalidValue;
+    const msm_caps caps = caps_of(p);
+    cudaError_t err = cudaMemsetAsync(ws.hist, 0, (size_t)((uint8_t*)ws.counters - (uint8_t*)ws.hist) + 16, s);
     if (err != cudaSuccess) return err;
-    k_msm_prepare<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(ws, scalars32, points64, g_scalar32, n, N);
-    k_msm_scan<<<MSM_WINDOWS, 1024, 0, s>>>(ws);
-    k_msm_scatter<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(ws, N);
-    k_msm_bucket_sum<<<(MSM_WINDOWS * MSM_BUCKETS + 127) / 128, 128, 0, s>>>(ws, N);
-    k_msm_chunks<<<(MSM_WINDOWS * MSM_CHUNKS + 127) / 128, 128, 0, s>>>(ws);
-    k_msm_groups<<<(MSM_WINDOWS * 32 + 63) / 64, 64, 0, s>>>(ws.groups, ws.chunks, MSM_WINDOWS * 32, 32);
-    k_msm_groups<<<1, 64, 0, s>>>(ws.windows, ws.groups, MSM_WINDOWS, 32);
-    k_msm_final<<<1, 32, 0, s>>>(out64, ws);
-    if (launches) *launches += 8;
+    err = cudaMemsetAsync(ws.buckets, 0, (size_t)p.TB * sizeof(gej_store), s);
+    if (err != cudaSuccess) return err;
+    const unsigned tgrid = (unsigned)((N + 255) / 256);
+    k_msm_prepare<<<tgrid, 256, 0, s>>>(ws, p, scalars32, points64, g_scalar32, n);
+    k_msm_scan_a<<<(unsigned)caps.nblk, 1024, 0, s>>>(ws, p);
+    k_msm_scan_b<<<(unsigned)caps.nblk, 1024, 0, s>>>(ws, p);
+    k_msm_scatter<<<tgrid, 256, 0, s>>>(ws, p);
+    k_msm_units<<<(unsigned)((caps.cap_units + 255) / 256), 256, 0, s>>>(ws, p);
+    size_t sum_blocks = (caps.cap_units + 127) / 128;
+    if (sum_blocks > (size_t)sum_grid_blocks()) sum_blocks = (size_t)sum_grid_blocks();
+    k_msm_bucket_sum<<<(unsigned)sum_blocks, 128, 0, s>>>(ws, p, points64, n);
+    size_t comb_blocks = caps.cap_multi < 1184 ? caps.cap_multi : 1184;
+    k_msm_combine<<<(unsigned)comb_blocks, 256, 0, s>>>(ws, p);
+    const size_t chunks = p.TB / MSM_CHUNK;
+    if (chunks <= 40960) k_msm_r1<true><<<(unsigned)((chunks * 4 + 127) / 128), 128, 0, s>>>(ws, p);
+    else k_msm_r1<false><<<(unsigned)((chunks + 127) / 128), 128, 0, s>>>(ws, p);
+    k_msm_r2<<<2 * p.nw * MSM_MAX_SUMS, 256, 0, s>>>(ws, p);
+    k_msm_tail<<<1, 256, 0, s>>>(out, out_mode, ws, p);
+    if (launches) *launches += 10;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gej_sum(uint8_t* out64, const uint8_t* partials96, size_t count, cudaStream_t s, uint64_t* launches) {
+    if (count >= ((size_t)1 << 31)) return cudaErrorInvalidValue;
+    k_gej_sum<<<1, 128, 0, s>>>(out64, partials96, (uint32_t)count);
+    if (launches) *launches += 1;
     return cudaGetLastError();
 }
 

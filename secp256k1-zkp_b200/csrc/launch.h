@@ -58,7 +58,11 @@ cudaError_t launch_halfagg_verify(uint8_t* d_ok, const uint8_t* d_pk32, const ui
                                   const uint8_t* d_z32_in, const uint32_t* hmid, const bip340_midstate_h& mid, uint8_t* ws, size_t ws_bytes,
                                   cudaStream_t s, uint64_t* launches);
 size_t msm_workspace_bytes(size_t n_terms);
-cudaError_t launch_msm(uint8_t* out64, const uint8_t* g_scalar32, const uint8_t* scalars32, const uint8_t* points64, size_t n,
-                       uint8_t* workspace, size_t workspace_bytes, cudaStream_t s, uint64_t* launches);
+// out_mode 0: out = 64 bytes affine x||y big-endian; 1: out = 96 bytes Jacobian (x, y, z LE limbs, z = 0 <=> infinity) for launch_gej_sum.
+// window_bits 0 = chosen from n (msm_choose_c)
+cudaError_t launch_msm(uint8_t* out, int out_mode, const uint8_t* g_scalar32, const uint8_t* scalars32, const uint8_t* points64, size_t n,
+                       uint8_t* workspace, size_t workspace_bytes, int window_bits, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_unit_op(int op, uint8_t* out, const uint8_t* a, const uint8_t* b, size_t n, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_gej_sum(uint8_t* out64, const uint8_t* partials96, size_t count, cudaStream_t s, uint64_t* launches);
 
 }  // namespace b200

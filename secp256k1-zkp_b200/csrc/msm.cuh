@@ -1,78 +1,180 @@
-// msm.cuh -- building blocks of the GPU Pippenger multi-scalar multiplication  R = sum_i s_i * P_i.
+// msm.cuh -- building blocks of the GPU Pippenger multi-scalar multiplication  R = g*G + sum_i s_i * P_i.
 //
 // Computes what secp256k1_ecmult_multi_var (ecmult_impl.h:823-867) -> secp256k1_ecmult_pippenger_batch (:670-731)
-// -> secp256k1_ecmult_pippenger_wnaf (:516-591) compute, re-designed for a GPU:
-//   reference: per window, clear buckets, add every point into its bucket one after the other (:545-566), then the
-//              running-sum reduction (:581-588); one thread, scratch space sized by the bucket window (:597-621).
-//   here:      c = 16-bit signed windows (16 windows, 2^15 buckets each; a scalar above n/2 is replaced by its negative and the
-//              digit signs flipped, so the recoding never carries out of the top window).  (1) every term emits its 16 signed digits and
-//              bumps a (window,bucket) histogram; (2) exclusive scan; (3) counting-sort scatter of term indices, so each
-//              bucket's points are contiguous; (4) ONE THREAD PER BUCKET sums its points with mixed adds (557 056
-//              independent threads at 2^20 terms, ~32 points each); (5) the running-sum reduction is cut into chunks of
-//              32 buckets: chunk value = L + b0*A with L = sum j*S_{b0+j}, A = sum S_{b0+j} (b0*A by a 15-bit
-//              double-and-add); (6) tree-sum of the chunks per window, Horner over the 16 windows.
-// No GLV split (it halves the windows but doubles the points: same number of bucket additions on a GPU).
+// -> secp256k1_ecmult_pippenger_wnaf (:516-591) compute, re-designed for a GPU (round 2):
+//
+//   reference                                              here
+//   ---------------------------------------------------   ---------------------------------------------------------------------
+//   dispatcher: Strauss below 88 points, else a bucket     msm_make_plan(): window width c in [4,16] chosen from n by a work model
+//   window from a table (:597-621, :823-867)               (the same trade the reference's table encodes: n*windows + buckets)
+//   ecmult_endo_split (:645-658): 2n points, the second    GLV split of the SCALAR only: windows [0,nw) hold the digits of |k1|,
+//   half multiplied by lambda (one fe_mul by beta each)    windows [nw,2nw) those of |k2|, both over the SAME point P_i; because the
+//                                                          endomorphism is a group homomorphism, sum k2_i*lambda(P_i) =
+//                                                          lambda(sum k2_i*P_i): ONE multiplication by beta at the very end
+//   wnaf_fixed digits + skew (:437-497)                    signed c-bit digits in [-2^(c-1), 2^(c-1)], the top window of each half
+//                                                          unsigned (|k| < 2^128 never carries out of it)
+//   serial bucket fill, one window after the other         counting sort by (window, bucket); buckets cut into PIECES of <= Tp entries;
+//   (:545-566)                                             one lane per piece, lanes of a warp pull pieces dynamically (no lane waits
+//                                                          for a longer bucket); pieces of a hot bucket are combined by one block with a
+//                                                          warp-shuffle tree -- 2^20 equal scalars cost the same bucket work as random ones
+//   running-sum reduction (:581-588), serial               chunks of 8 buckets (running sum, all chunks in parallel), then per window
+//                                                          sum_q L_q + 8*sum_q q*A_q with the second sum taken bit by bit (tree sums)
+//   Horner over the windows (:536-589), serial              two Horner chains (one per GLV half) side by side, every doubling / addition
+//                                                          spread over 4 lanes (ge_g4.cuh), then R = A + lambda(B)
 // Only the final point has to match the reference; it does because the group element is unique.
 #pragma once
-#include "ge.cuh"
+#include "gtable.cuh"
+#include "ge_g4.cuh"
 #include "sc.cuh"
 
 namespace B200_NS {
 
-#define MSM_C 16
-#define MSM_WINDOWS 16
-#define MSM_BUCKETS 32768            // per window: |digit| in 1..32768
-#define MSM_CHUNK 32                 // buckets per reduction chunk
-#define MSM_CHUNKS (MSM_BUCKETS / MSM_CHUNK)
+#define MSM_CHUNK 8                  // buckets per running-sum chunk
+#define MSM_PIECE_MIN 64             // smallest piece size
+#define MSM_C_MIN 4
+#define MSM_C_MAX 16
+#define MSM_MAX_SUMS 15              // per window: 1 plain sum (L) + up to 14 bit sums
+#define MSM_SCAN_ELEMS 4096          // buckets per block of the two-level scan
 
-// signed 16-bit window recoding of a scalar: k = sum d_w 2^(16w) (mod n), d_w in [-32768, 32768], w = 0..15.
-// k > n/2 is recoded as -(n - k): then the top window holds < 2^15 and nothing carries out of it.  (Without this every scalar with
-// bit 255 set put a digit 1 into a 17th window and ONE bucket thread summed half of all points serially: 256 ms at 131 072 terms.)
-HD void msm_digits(int32_t* d /*[16]*/, const sc& k0) {
-    int neg = sc_is_high(k0);
-    sc k;
-    if (neg) sc_negate(k, k0); else k = k0;
+struct msm_plan {
+    uint32_t c;        // window bits
+    uint32_t nw;       // windows per GLV half = ceil(128 / c)
+    uint32_t B;        // buckets of a regular window = 2^(c-1)   (digit magnitudes 1..B)
+    uint32_t Btop;     // buckets of the top window of a half = max(2^t, 8), t = 128 - c*(nw-1) (unsigned digit 1..2^t)
+    uint32_t HB;       // buckets per half = (nw-1)*B + Btop
+    uint32_t TB;       // total buckets = 2*HB (a multiple of 8)
+    uint32_t Tp;       // entries per piece
+    uint32_t N;        // terms incl. the generator slot (index N-1)
+};
+
+HD uint32_t msm_ilog2(uint32_t x) { uint32_t r = 0; while (x > 1) { x >>= 1; r++; } return r; }
+
+HD void msm_make_plan_c(msm_plan& p, size_t N, uint32_t c) {
+    p.c = c;
+    p.nw = (128 + c - 1) / c;
+    uint32_t t = 128 - c * (p.nw - 1);
+    p.B = 1u << (c - 1);
+    p.Btop = (1u << t) < 8u ? 8u : (1u << t);
+    p.HB = (p.nw - 1) * p.B + p.Btop;
+    p.TB = 2 * p.HB;
+    p.N = (uint32_t)N;
+    uint64_t mean4 = (uint64_t)4 * 2 * p.nw * N / p.TB;           // 4 x the mean bucket load
+    uint32_t tp = MSM_PIECE_MIN;
+    while (tp < mean4 && tp < (1u << 20)) tp <<= 1;
+    p.Tp = tp;
+}
+// window width from the number of terms: minimises (bucket additions) + (bucket-reduction work), the trade that
+// secp256k1_pippenger_bucket_window's table encodes for the CPU (ecmult_impl.h:597-621); below ~2^11 terms the MSM is latency
+// bound (a ~128-doubling chain whatever c is) and c = 8 keeps the bucket count small.
+HD uint32_t msm_choose_c(size_t N) {
+    if (N <= 2048) return 8;
+    uint32_t best = 8;
+    uint64_t bestcost = ~(uint64_t)0;
+    for (uint32_t c = 8; c <= MSM_C_MAX; c++) {
+        msm_plan p;
+        msm_make_plan_c(p, N, c);
+        uint64_t cost = (uint64_t)2 * p.nw * N + (uint64_t)4 * p.TB;
+        if (cost < bestcost) { bestcost = cost; best = c; }
+    }
+    return best;
+}
+
+// bits [pos, pos + nb) of a 128-bit magnitude (nb <= 16, pos + nb <= 128)
+HD uint32_t msm_bits128(const uint32_t* m4, uint32_t pos, uint32_t nb) {
+    uint32_t limb = pos >> 5, off = pos & 31;
+    uint32_t x = m4[limb] >> off;
+    if (off + nb > 32 && limb + 1 < 4) x |= m4[limb + 1] << (32 - off);
+    return x & ((nb >= 32) ? 0xFFFFFFFFu : ((1u << nb) - 1u));
+}
+
+// signed digits of one GLV half: emit(bucket, sign) for every non-zero digit.  bucket = half*HB + w*B + (|digit| - 1).
+template <class Emit>
+HD void msm_emit_digits(const msm_plan& p, const uint32_t* mag4, uint32_t neg, uint32_t half, Emit& emit) {
     uint32_t carry = 0;
-#pragma unroll
-    for (int w = 0; w < 16; w++) {
-        uint32_t v = ((k.v[w >> 1] >> ((w & 1) * 16)) & 0xFFFFu) + carry;
-        int32_t dw;
-        if (v > 32768u) { dw = (int32_t)v - 65536; carry = 1; }
-        else { dw = (int32_t)v; carry = 0; }
-        d[w] = neg ? -dw : dw;
+    const uint32_t base = half * p.HB;
+#pragma unroll 1
+    for (uint32_t w = 0; w < p.nw; w++) {
+        uint32_t pos = w * p.c;
+        uint32_t nb = (w + 1 < p.nw) ? p.c : (128 - pos);
+        uint32_t v = msm_bits128(mag4, pos, nb) + carry;
+        uint32_t sgn = neg;
+        if (w + 1 < p.nw && v > p.B) { v = (1u << p.c) - v; sgn ^= 1u; carry = 1; } else carry = 0;
+        if (v) emit(base + w * p.B + v - 1, sgn);
     }
 }
 
-// affine point storage used by the MSM kernels: 16 words x[8] y[8] (LE limbs), all-zero = infinity
-HD void msm_load_point(ge& p, const uint32_t* s16) {
-    uint32_t z = 0;
+// per-term preparation: GLV split (scalar_impl.h:142-180), magnitudes and signs.  flags: bit0 = k1 negative, bit1 = k2 negative,
+// bit2 = term contributes nothing (zero scalar or point at infinity).
+HD void msm_prepare_term(uint32_t* k12 /*[8]*/, uint32_t& flags, const sc& k, int point_inf) {
+    if (point_inf || sc_is_zero(k)) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) { p.x.v[k] = s16[k]; p.y.v[k] = s16[8 + k]; z |= s16[k] | s16[8 + k]; }
-    p.inf = (z == 0);
+        for (int t = 0; t < 8; t++) k12[t] = 0;
+        flags = 4;
+        return;
+    }
+    sc k1, k2;
+    sc_split_lambda(k1, k2, k);
+    uint32_t n1 = (uint32_t)sc_is_high(k1), n2 = (uint32_t)sc_is_high(k2);
+    sc_cond_negate(k1, (int)n1);
+    sc_cond_negate(k2, (int)n2);
+#pragma unroll
+    for (int t = 0; t < 4; t++) { k12[t] = k1.v[t]; k12[4 + t] = k2.v[t]; }
+    flags = n1 | (n2 << 1);
 }
 
-// Jacobian point storage: 25 words (x, y, z, inf)
-struct gej_store { uint32_t w[25]; };
+// Jacobian point storage: 24 words x, y, z (LE limbs); z == 0 (all words) <=> infinity, so zeroed memory is a valid "empty".
+struct gej_store { uint32_t w[24]; };
 HD void msm_store_gej(gej_store& s, const gej& a) {
+    if (a.inf) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) { s.w[k] = a.x.v[k]; s.w[8 + k] = a.y.v[k]; s.w[16 + k] = a.z.v[k]; }
-    s.w[24] = (uint32_t)a.inf;
+        for (int k = 0; k < 24; k++) s.w[k] = 0;
+        return;
+    }
+    fe z = a.z;
+    fe_normalize(z);                 // a weakly reduced z could be p itself only if it were 0 mod p, which a finite point never has;
+#pragma unroll                       // normalising keeps "all words zero" an exact test anyway
+    for (int k = 0; k < 8; k++) { s.w[k] = a.x.v[k]; s.w[8 + k] = a.y.v[k]; s.w[16 + k] = z.v[k]; }
 }
 HD void msm_load_gej(gej& a, const gej_store& s) {
+    uint32_t zz = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { a.x.v[k] = s.w[k]; a.y.v[k] = s.w[8 + k]; a.z.v[k] = s.w[16 + k]; }
-    a.inf = (int)s.w[24];
+    for (int k = 0; k < 8; k++) { a.x.v[k] = s.w[k]; a.y.v[k] = s.w[8 + k]; a.z.v[k] = s.w[16 + k]; zz |= s.w[16 + k]; }
+    a.inf = (zz == 0);
 }
 
-// (4) bucket sum: acc = sum over sorted entries [begin,end) of +-P[idx]; entry = idx | sign<<31
-HD void msm_bucket_sum(gej& acc, const uint32_t* entries, uint32_t begin, uint32_t end, const uint32_t* points16) {
+// a unit of bucket work: <= Tp consecutive sorted entries of one bucket
+struct msm_unit { uint32_t begin, count, dst, bucket; };   // dst: bucket index, or 0x80000000 | index into the parts array
+#define MSM_DST_PART 0x80000000u
+
+// affine point i of the input (x||y big-endian, raw 256-bit values); index n = the generator slot
+HD void msm_load_point(ge& p, const uint8_t* points64, size_t n, const uint8_t* gpoint64, uint32_t idx) {
+    const uint8_t* s = (idx < n) ? points64 + (size_t)64 * idx : gpoint64;
+#if defined(__CUDA_ARCH__)
+    if ((reinterpret_cast<uintptr_t>(s) & 15) == 0) {
+        const uint4* q = reinterpret_cast<const uint4*>(s);
+        uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+        // big-endian 32 bytes -> LE limbs: limb 7 = first word byte-swapped
+        p.x.v[7] = __byte_perm(a.x, 0, 0x0123); p.x.v[6] = __byte_perm(a.y, 0, 0x0123); p.x.v[5] = __byte_perm(a.z, 0, 0x0123); p.x.v[4] = __byte_perm(a.w, 0, 0x0123);
+        p.x.v[3] = __byte_perm(b.x, 0, 0x0123); p.x.v[2] = __byte_perm(b.y, 0, 0x0123); p.x.v[1] = __byte_perm(b.z, 0, 0x0123); p.x.v[0] = __byte_perm(b.w, 0, 0x0123);
+        p.y.v[7] = __byte_perm(c.x, 0, 0x0123); p.y.v[6] = __byte_perm(c.y, 0, 0x0123); p.y.v[5] = __byte_perm(c.z, 0, 0x0123); p.y.v[4] = __byte_perm(c.w, 0, 0x0123);
+        p.y.v[3] = __byte_perm(d.x, 0, 0x0123); p.y.v[2] = __byte_perm(d.y, 0, 0x0123); p.y.v[1] = __byte_perm(d.z, 0, 0x0123); p.y.v[0] = __byte_perm(d.w, 0, 0x0123);
+        p.inf = 0;
+        return;
+    }
+#endif
+    bn_from_be32(p.x.v, s);
+    bn_from_be32(p.y.v, s + 32);
+    p.inf = 0;
+}
+
+// sum of one unit: acc = sum over its entries of +-P[idx]   (entry = idx | sign << 31; infinity points never become entries)
+HD void msm_unit_sum(gej& acc, const msm_unit& u, const uint32_t* entries, const uint8_t* points64, size_t n, const uint8_t* gpoint64) {
     gej_set_infinity(acc);
 #pragma unroll 1
-    for (uint32_t e = begin; e < end; e++) {
+    for (uint32_t e = u.begin; e < u.begin + u.count; e++) {
         uint32_t v = entries[e];
         ge p;
-        msm_load_point(p, points16 + (size_t)(v & 0x7FFFFFFFu) * 16);
-        if (p.inf) continue;
+        msm_load_point(p, points64, n, gpoint64, v & 0x7FFFFFFFu);
         if (v >> 31) fe_neg(p.y, p.y);
         gej t;
         gej_add_ge(t, acc, p);
@@ -80,63 +182,85 @@ HD void msm_bucket_sum(gej& acc, const uint32_t* entries, uint32_t begin, uint32
     }
 }
 
-// (5) chunk reduction over buckets b0+1 .. b0+MSM_CHUNK (bucket index b holds multiplier b+1):
-//     out = sum_{j=0}^{CHUNK-1} (b0 + j + 1) * S[b0 + j]
-HD void msm_chunk_reduce(gej& out, const gej_store* bucket_sums /* window base */, uint32_t b0) {
+// window geometry from a bucket / chunk position
+struct msm_win { uint32_t half, w, base, Bw; };             // base = first bucket of the window
+HD void msm_window_of_bucket(msm_win& o, const msm_plan& p, uint32_t bucket) {
+    o.half = bucket / p.HB;
+    uint32_t r = bucket - o.half * p.HB;
+    o.w = r / p.B;
+    if (o.w > p.nw - 1) o.w = p.nw - 1;
+    o.base = o.half * p.HB + o.w * p.B;
+    o.Bw = (o.w == p.nw - 1) ? p.Btop : p.B;
+}
+HD void msm_window_by_index(msm_win& o, const msm_plan& p, uint32_t wi /* 0 .. 2*nw-1 */) {
+    o.half = wi / p.nw;
+    o.w = wi - o.half * p.nw;
+    o.base = o.half * p.HB + o.w * p.B;
+    o.Bw = (o.w == p.nw - 1) ? p.Btop : p.B;
+}
+
+// running-sum chunk (reference :581-588 on 8 buckets): L = sum_{j<8} (j+1)*S_j, A = sum_j S_j
+HD void msm_chunk_r1(gej& L, gej& A, const gej_store* s8) {
     gej running, acc;
     gej_set_infinity(running);
     gej_set_infinity(acc);
 #pragma unroll 1
     for (int j = MSM_CHUNK - 1; j >= 0; j--) {
         gej s, t;
-        msm_load_gej(s, bucket_sums[b0 + j]);
-        gej_add(t, running, s); running = t;       // running = sum_{i>=j} S_i
-        gej_add(t, acc, running); acc = t;         // acc = sum_j (j+1) S_j   (local multipliers 1..CHUNK)
+        msm_load_gej(s, s8[j]);
+        gej_add(t, running, s); running = t;
+        gej_add(t, acc, running); acc = t;
     }
-    // + b0 * A, A = running (plain sum of the chunk)
-    if (b0 != 0 && !running.inf) {
-        gej m;
-        gej_set_infinity(m);
-#pragma unroll 1
-        for (int bit = 14; bit >= 0; bit--) {
-            gej t;
-            if (!m.inf) { gej_double(t, m); m = t; }
-            if ((b0 >> bit) & 1u) { gej_add(t, m, running); m = t; }
-        }
-        gej t;
-        gej_add(t, acc, m); acc = t;
-    }
-    out = acc;
+    L = acc;
+    A = running;
 }
 
-// sum of `count` stored Jacobian points
-HD void msm_sum_range(gej& out, const gej_store* v, uint32_t count) {
+// element k of bit-sum j over Q chunk sums: the k-th index q in [0, Q) whose bit j is set
+HD uint32_t msm_bit_index(uint32_t k, uint32_t j) { return ((k >> j) << (j + 1)) | (1u << j) | (k & ((1u << j) - 1u)); }
+
+// The three functions below run on a GROUP OF 4 LANES on the device (ge_g4.cuh: all four lanes call with identical arguments);
+// compiled for the host they are plain single-thread code.
+// window sum from its plain sum T[0] = sum_q L_q and bit sums T[1 + j] = sum_{q: bit j} A_q:
+//   W = T[0] + 8 * sum_j 2^j T[1 + j]
+HD void msm_window_from_sums(gej& W, const gej_store* T, uint32_t nbits) {
     gej acc;
     gej_set_infinity(acc);
 #pragma unroll 1
-    for (uint32_t i = 0; i < count; i++) {
+    for (int j = (int)nbits - 1; j >= 0; j--) {
         gej s, t;
-        msm_load_gej(s, v[i]);
-        gej_add(t, acc, s); acc = t;
+        if (!acc.inf) { gej_double_g4(t, acc); acc = t; }
+        msm_load_gej(s, T[1 + j]);
+        gej_add_g4(t, acc, s); acc = t;
     }
-    out = acc;
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) if (!acc.inf) { gej t; gej_double_g4(t, acc); acc = t; }
+    gej s, t;
+    msm_load_gej(s, T[0]);
+    gej_add_g4(t, acc, s);
+    W = t;
 }
 
-// (6) Horner over windows: R = sum_w 2^(16 w) * W[w]
-HD void msm_horner(gej& out, const gej_store* window_sums) {
+// Horner over the nw windows of one half: sum_w 2^(c w) W[w]
+HD void msm_horner_half(gej& out, const gej* W, const msm_plan& p) {
     gej acc;
     gej_set_infinity(acc);
 #pragma unroll 1
-    for (int w = MSM_WINDOWS - 1; w >= 0; w--) {
+    for (int w = (int)p.nw - 1; w >= 0; w--) {
         if (!acc.inf) {
 #pragma unroll 1
-            for (int k = 0; k < MSM_C; k++) { gej t; gej_double(t, acc); acc = t; }
+            for (uint32_t k = 0; k < p.c; k++) { gej t; gej_double_g4(t, acc); acc = t; }
         }
-        gej s, t;
-        msm_load_gej(s, window_sums[w]);
-        gej_add(t, acc, s); acc = t;
+        gej t, ww = W[w];
+        gej_add_g4(t, acc, ww); acc = t;
     }
     out = acc;
+}
+
+// R = A + lambda(B), lambda(X, Y, Z) = (beta X, Y, Z)   (group_impl.h ge_mul_lambda on Jacobian coordinates)
+HD void msm_join_halves(gej& R, const gej& A, const gej& Bh) {
+    gej lb = Bh;
+    if (!lb.inf) { fe beta; fe_set_beta(beta); fe_mul(lb.x, lb.x, beta); }
+    gej_add_g4(R, A, lb);
 }
 
 }  // namespace B200_NS

@@ -68,3 +68,15 @@ def allgather_points(xy64):
     out = torch.empty((world, 64), dtype=torch.uint8, device=xy64.device)
     dist.all_gather_into_tensor(out.view(-1), xy64.view(-1))
     return out
+
+
+def allgather_partials(p96, out=None):
+    """MSM shard sums: 96-byte Jacobian points (secp256k1_b200_ecmult_multi_partial_dev), one per rank -> (world, 96)"""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if out is None:
+        out = torch.empty((world, 96), dtype=torch.uint8, device=p96.device)
+    if world == 1:
+        out.view(-1).copy_(p96.view(-1))
+        return out
+    dist.all_gather_into_tensor(out.view(-1), p96.view(-1))
+    return out

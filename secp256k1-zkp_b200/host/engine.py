@@ -69,6 +69,10 @@ def load_library():
     lib.secp256k1_b200_ecmult_multi_workspace_bytes.restype = sz
     lib.secp256k1_b200_ecmult_multi.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
     lib.secp256k1_b200_ecmult_multi_dev.argtypes = [vp, u8p, u8p, u8p, u8p, sz, vp, sz, vp]
+    lib.secp256k1_b200_ecmult_multi_partial_dev.argtypes = [vp, u8p, u8p, u8p, u8p, sz, vp, sz, vp]
+    lib.secp256k1_b200_ecmult_multi_combine_dev.argtypes = [vp, u8p, u8p, sz, vp]
+    lib.secp256k1_b200_ecmult_multi_set_window.argtypes = [vp, ci]
+    lib.secp256k1_b200_unit_op_batch.argtypes = [vp, ci, u8p, u8p, u8p, sz]
     lib.secp256k1_b200_point_codec_batch.argtypes = [vp, u8p, u8p, u8p, sz, ctypes.c_uint32, ci, sz]
     lib.secp256k1_b200_sha256_state_init.argtypes = [u8p]
     lib.secp256k1_b200_sha256_state_init.restype = None
@@ -263,6 +267,27 @@ class Engine:
 
     def ecmult_multi_dev(self, d_out64, d_g_scalar32, d_scalars32, d_points64, n, d_workspace, workspace_bytes, stream=0):
         self._ck(self._lib.secp256k1_b200_ecmult_multi_dev(self._h, d_out64, d_g_scalar32, d_scalars32, d_points64, n, d_workspace, workspace_bytes, stream))
+
+    def ecmult_multi_partial_dev(self, d_out96, d_g_scalar32, d_scalars32, d_points64, n, d_workspace, workspace_bytes, stream=0):
+        """one shard of a sharded MSM: 96-byte Jacobian partial sum (no inversion); combine with ecmult_multi_combine_dev"""
+        self._ck(self._lib.secp256k1_b200_ecmult_multi_partial_dev(self._h, d_out96, d_g_scalar32, d_scalars32, d_points64, n, d_workspace, workspace_bytes, stream))
+
+    def ecmult_multi_combine_dev(self, d_out64, d_partials96, count, stream=0):
+        self._ck(self._lib.secp256k1_b200_ecmult_multi_combine_dev(self._h, d_out64, d_partials96, count, stream))
+
+    def ecmult_multi_set_window(self, window_bits):
+        """0 = bucket window chosen from n (default); 4..16 forces it"""
+        self._ck(self._lib.secp256k1_b200_ecmult_multi_set_window(self._h, window_bits))
+
+    def unit_op(self, op, a, b=None):
+        """unit kernels of the scalar / group primitives (secp256k1_b200_unit_op_batch)"""
+        scalar = op < 8
+        a = _u8(a, len(a) if not hasattr(a, "size") else a.size, "a")
+        n = a.size // (32 if scalar else 96)
+        bb = _u8(b, a.size, "b") if b is not None else None
+        out = np.empty(n * (32 if (scalar and op != 4) else 64), dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_unit_op_batch(self._h, op, _p(out), _p(a), _p(bb), n))
+        return out
 
     def point_codec(self, data, in_len, fmt):
         a = _u8(data, len(data) if not hasattr(data, "size") else data.size, "data")

@@ -148,42 +148,81 @@ int emu_rangeproof_rewind(uint8_t* blind32, uint64_t* value, uint8_t* msg, size_
 int emu_pedersen_commit(uint8_t* out33, const uint8_t* blind32, uint64_t value, const uint8_t* gen64) {
     return pedersen_commit_item(out33, blind32, value, gen64, g_gt);
 }
-// the k_msm_* kernel pipeline executed sequentially
-int emu_msm(uint8_t* out64, const uint8_t* g_sc32, const uint8_t* scalars32, const uint8_t* points64, size_t n) {
+// the k_msm_* kernel pipeline (k_msm.cu) executed sequentially with the same index logic: digits -> histogram -> scan (entries / pieces /
+// parts) -> scatter -> units -> unit sums -> multi-piece combine -> chunk running sums -> plain / bit sums -> window sums -> Horner -> join.
+// c = 0: window chosen from n; tp != 0 forces the piece size (to exercise multi-piece buckets with few terms).
+struct emu_emit_hist { std::vector<uint32_t>* h; void operator()(uint32_t b, uint32_t) { (*h)[b]++; } };
+struct emu_emit_scatter { std::vector<uint32_t>* off; std::vector<uint32_t>* h; std::vector<uint32_t>* ent; uint32_t idx;
+    void operator()(uint32_t b, uint32_t sgn) { uint32_t pos = (*off)[b] + ((*h)[b]--) - 1u; (*ent)[pos] = idx | (sgn << 31); } };
+int emu_msm2(uint8_t* out64, const uint8_t* g_sc32, const uint8_t* scalars32, const uint8_t* points64, size_t n, int c, uint32_t tp) {
     const size_t N = n + 1;
-    std::vector<uint32_t> scal(N * 8), pts(N * 16), hist((size_t)MSM_WINDOWS * MSM_BUCKETS, 0), offs(hist.size()), cur(hist.size(), 0), entries((size_t)MSM_WINDOWS * N);
+    msm_plan p; msm_make_plan_c(p, N, c ? (uint32_t)c : msm_choose_c(N));
+    if (tp) p.Tp = tp;
+    std::vector<uint32_t> k12(N * 8), hist(p.TB, 0), off(p.TB + 1), pbase(p.TB + 1), mbase(p.TB + 1), multi, entries((size_t)2 * p.nw * N);
+    std::vector<uint8_t> flags(N);
+    uint8_t gpoint[64]; { ge g; ge_set_generator(g); fe_get_b32(gpoint, g.x); fe_get_b32(gpoint + 32, g.y); }
     for (size_t i = 0; i < N; i++) {
-        sc k;
-        if (i < n) { sc_set_b32(k, scalars32 + 32 * i); fe x, y; bn_from_be32(x.v, points64 + 64 * i); bn_from_be32(y.v, points64 + 64 * i + 32);
-                     for (int t = 0; t < 8; t++) { pts[16 * i + t] = x.v[t]; pts[16 * i + 8 + t] = y.v[t]; } }
-        else { if (g_sc32) sc_set_b32(k, g_sc32); else sc_set_zero(k); ge g; ge_set_generator(g); for (int t = 0; t < 8; t++) { pts[16 * i + t] = g.x.v[t]; pts[16 * i + 8 + t] = g.y.v[t]; } }
-        for (int t = 0; t < 8; t++) scal[8 * i + t] = k.v[t];
+        sc k; int inf = 0;
+        if (i < n) { sc_set_b32(k, scalars32 + 32 * i); inf = 1; for (int t = 0; t < 64; t++) if (points64[64 * i + t]) inf = 0; }
+        else { if (g_sc32) sc_set_b32(k, g_sc32); else sc_set_zero(k); }
+        uint32_t f; msm_prepare_term(&k12[8 * i], f, k, inf); flags[i] = (uint8_t)f;
+        if (f & 4u) continue;
+        emu_emit_hist em = {&hist};
+        msm_emit_digits(p, &k12[8 * i], f & 1u, 0, em);
+        msm_emit_digits(p, &k12[8 * i + 4], (f >> 1) & 1u, 1, em);
     }
-    auto is_inf = [&](size_t i) { uint32_t z = 0; for (int t = 0; t < 16; t++) z |= pts[16 * i + t]; return z == 0; };
-    for (size_t i = 0; i < N; i++) {
-        if (is_inf(i)) continue;
-        sc k; for (int t = 0; t < 8; t++) k.v[t] = scal[8 * i + t];
-        int32_t d[MSM_WINDOWS]; msm_digits(d, k);
-        for (int w = 0; w < MSM_WINDOWS; w++) if (d[w]) hist[(size_t)w * MSM_BUCKETS + (uint32_t)(d[w] < 0 ? -d[w] : d[w]) - 1]++;
+    uint32_t ro = 0, rp = 0, rm = 0;
+    for (uint32_t b = 0; b < p.TB; b++) {
+        uint32_t pc = (hist[b] + p.Tp - 1) / p.Tp;
+        off[b] = ro; pbase[b] = rp; mbase[b] = rm;
+        if (pc > 1) multi.push_back(b);
+        ro += hist[b]; rp += pc; rm += (pc > 1 ? pc : 0);
     }
-    for (int w = 0; w < MSM_WINDOWS; w++) { uint32_t run = 0; for (int b = 0; b < MSM_BUCKETS; b++) { offs[(size_t)w * MSM_BUCKETS + b] = run; run += hist[(size_t)w * MSM_BUCKETS + b]; } }
+    off[p.TB] = ro; pbase[p.TB] = rp; mbase[p.TB] = rm;
     for (size_t i = 0; i < N; i++) {
-        if (is_inf(i)) continue;
-        sc k; for (int t = 0; t < 8; t++) k.v[t] = scal[8 * i + t];
-        int32_t d[MSM_WINDOWS]; msm_digits(d, k);
-        for (int w = 0; w < MSM_WINDOWS; w++) if (d[w]) {
-            uint32_t neg = d[w] < 0; size_t wb = (size_t)w * MSM_BUCKETS + (uint32_t)(neg ? -d[w] : d[w]) - 1;
-            entries[(size_t)w * N + offs[wb] + cur[wb]++] = (uint32_t)i | (neg << 31);
+        uint32_t f = flags[i];
+        if (f & 4u) continue;
+        emu_emit_scatter em = {&off, &hist, &entries, (uint32_t)i};
+        msm_emit_digits(p, &k12[8 * i], f & 1u, 0, em);
+        msm_emit_digits(p, &k12[8 * i + 4], (f >> 1) & 1u, 1, em);
+    }
+    std::vector<gej_store> buckets(p.TB), parts(rm + 1), Lq(p.TB / MSM_CHUNK), Aq(p.TB / MSM_CHUNK), T((size_t)2 * p.nw * MSM_MAX_SUMS);
+    memset(buckets.data(), 0, buckets.size() * sizeof(gej_store));
+    for (uint32_t u = 0; u < rp; u++) {                                   // k_msm_units + k_msm_bucket_sum
+        uint32_t lo = 0, hi = p.TB;
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (pbase[mid] <= u) lo = mid; else hi = mid; }
+        uint32_t b = lo, j = u - pbase[b], npieces = pbase[b + 1] - pbase[b];
+        msm_unit d; d.begin = off[b] + j * p.Tp; d.count = off[b + 1] - d.begin < p.Tp ? off[b + 1] - d.begin : p.Tp; d.bucket = b;
+        d.dst = npieces == 1 ? b : (MSM_DST_PART | (mbase[b] + j));
+        gej acc; msm_unit_sum(acc, d, entries.data(), points64, n, gpoint);
+        msm_store_gej((d.dst & MSM_DST_PART) ? parts[d.dst & ~MSM_DST_PART] : buckets[d.dst], acc);
+    }
+    for (uint32_t b : multi) {                                            // k_msm_combine
+        gej acc; gej_set_infinity(acc);
+        for (uint32_t k = 0; k < pbase[b + 1] - pbase[b]; k++) { gej o, t; msm_load_gej(o, parts[mbase[b] + k]); gej_add(t, acc, o); acc = t; }
+        msm_store_gej(buckets[b], acc);
+    }
+    for (uint32_t q = 0; q < p.TB / MSM_CHUNK; q++) { gej L, A; msm_chunk_r1(L, A, buckets.data() + (size_t)q * MSM_CHUNK); msm_store_gej(Lq[q], L); msm_store_gej(Aq[q], A); }
+    std::vector<gej> W(2 * p.nw);
+    for (uint32_t wi = 0; wi < 2 * p.nw; wi++) {                          // k_msm_r2 + first phase of k_msm_tail
+        msm_win w; msm_window_by_index(w, p, wi);
+        uint32_t Q = w.Bw / MSM_CHUNK, nbits = msm_ilog2(Q), cb = w.base / MSM_CHUNK;
+        for (uint32_t s = 0; s <= nbits; s++) {
+            gej acc; gej_set_infinity(acc);
+            uint32_t count = s == 0 ? Q : Q / 2;
+            for (uint32_t k = 0; k < count; k++) { gej o, t; msm_load_gej(o, s == 0 ? Lq[cb + k] : Aq[cb + msm_bit_index(k, s - 1)]); gej_add(t, acc, o); acc = t; }
+            msm_store_gej(T[(size_t)wi * MSM_MAX_SUMS + s], acc);
         }
+        msm_window_from_sums(W[wi], T.data() + (size_t)wi * MSM_MAX_SUMS, nbits);
     }
-    std::vector<gej_store> buckets(hist.size()), chunks((size_t)MSM_WINDOWS * MSM_CHUNKS), groups(MSM_WINDOWS * 32), windows(MSM_WINDOWS);
-    for (size_t t = 0; t < hist.size(); t++) { gej acc; msm_bucket_sum(acc, entries.data() + (t / MSM_BUCKETS) * N, offs[t], offs[t] + hist[t], pts.data()); msm_store_gej(buckets[t], acc); }
-    for (size_t t = 0; t < chunks.size(); t++) { gej o; msm_chunk_reduce(o, buckets.data() + (t / MSM_CHUNKS) * MSM_BUCKETS, (uint32_t)(t % MSM_CHUNKS) * MSM_CHUNK); msm_store_gej(chunks[t], o); }
-    for (size_t t = 0; t < groups.size(); t++) { gej o; msm_sum_range(o, chunks.data() + t * 32, 32); msm_store_gej(groups[t], o); }
-    for (size_t t = 0; t < windows.size(); t++) { gej o; msm_sum_range(o, groups.data() + t * 32, 32); msm_store_gej(windows[t], o); }
-    gej r; msm_horner(r, windows.data());
+    gej H[2], r;
+    msm_horner_half(H[0], W.data(), p);
+    msm_horner_half(H[1], W.data() + p.nw, p);
+    msm_join_halves(r, H[0], H[1]);
     return gej_to_xy64(out64, r);
 }
+int emu_msm(uint8_t* out64, const uint8_t* g_sc32, const uint8_t* scalars32, const uint8_t* points64, size_t n) { return emu_msm2(out64, g_sc32, scalars32, points64, n, 0, 0); }
+int emu_msm_choose_c(size_t N) { return (int)msm_choose_c(N); }
 // k_bppp_norm_verify lane by lane; mode 0 = plain SHA-256 transcript, 1 = tests' initial-data transcript
 int emu_bppp_norm_verify(const uint8_t* proof, size_t plen, const uint8_t* commit64, const uint8_t* rho32, const uint8_t* gens64, uint32_t g_len,
                          const uint8_t* c_vec32, uint32_t h_len, int mode) {

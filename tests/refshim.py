@@ -50,6 +50,18 @@ class RefLib:
         self.lib.ref_ecmult_batch(out, _buf(a64), na32, _buf(ng32), ctypes.c_size_t(n))
         return np.frombuffer(out.raw, dtype=np.uint8).reshape(n, 64)
 
+    def unit_op(self, op, a, b=None):
+        """reference side of secp256k1_b200_unit_op_batch (same op codes and operand layouts)"""
+        scalar = op < 8
+        a = np.ascontiguousarray(np.frombuffer(a, dtype=np.uint8) if isinstance(a, (bytes, bytearray)) else a, dtype=np.uint8).reshape(-1)
+        n = a.size // (32 if scalar else 96)
+        out = np.zeros(n * (32 if (scalar and op != 4) else 64), dtype=np.uint8)
+        if b is not None:
+            b = np.ascontiguousarray(np.frombuffer(b, dtype=np.uint8) if isinstance(b, (bytes, bytearray)) else b, dtype=np.uint8).reshape(-1)
+        self.lib.ref_unit_op_batch(ctypes.c_int(op), out.ctypes.data_as(ctypes.c_void_p), a.ctypes.data_as(ctypes.c_void_p),
+                                   b.ctypes.data_as(ctypes.c_void_p) if b is not None else None, ctypes.c_size_t(n))
+        return out
+
     def ecmult_multi(self, sc32, pt64, g_sc32=None, scratch_bytes=0):
         sc32 = _buf(sc32)
         n = len(sc32) // 32

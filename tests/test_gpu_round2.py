@@ -1,0 +1,265 @@
+"""GPU parity tests added in round 2 (run with -m gpu on a B200), all through the C ABI and bit-exact against the reference compiled into
+oracle/_ref:
+  * device unit kernels of the scalar / group primitives on the PTX limb path (and the 4-lane forms of the MSM tail) on >= 10^5 inputs with
+    deterministic degenerate cases (a = b, a = -b, infinity on either side, z != 1), the reference's scalar edge vectors
+    (src/tests.c:2456 run_scalar_tests) and the GLV near-split-bound scalars (src/tests.c:4779 run_ecmult_near_split_bound);
+  * the size-adaptive MSM (window from n, every forced window), hot buckets, the sharded partial/combine path, bench_ecmult's point set."""
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+P = 2**256 - 2**32 - 977
+N = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+LAMBDA = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
+G64 = bytes.fromhex("79BE667EF9DCBBAC55A06295CE870B07029BFCDB2DCE28D959F2815B16F81798"
+                    "483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8")
+U_SC_MUL, U_SC_ADD, U_SC_NEG, U_SC_INV, U_SC_SPLIT, U_SC_RED = 0, 1, 2, 3, 4, 5
+U_DBL, U_ADD, U_ADD_GE, U_DBL_G4, U_ADD_G4, U_ADD_GE_G4 = 8, 9, 10, 24, 25, 26
+
+
+def b32(x):
+    return int(x).to_bytes(32, "big")
+
+
+# scalars on which the reference's own tests concentrate: 0, 1, n-1, the halves of n, lambda, the GLV split bounds
+# (src/tests.c:4779-4800 run_ecmult_near_split_bound: multiples of the lattice vectors around which split_lambda changes branch)
+def _edge_scalars():
+    a1 = 0x3086D221A7D46BCDE86C90E49284EB15
+    b1 = 0xE4437ED6010E88286F547FA90ABFE4C3          # -b1 of the lattice basis
+    a2 = 0x114CA50F7A8E2F3F657C1108D9D44CFD8
+    edge = [0, 1, 2, N - 1, N - 2, (N - 1) // 2, (N + 1) // 2, LAMBDA, N - LAMBDA, (LAMBDA * LAMBDA) % N, 2**128, 2**128 - 1, 2**127, 2**255, 2**256 - 1,
+            N, N + 1, 2**256 - 2**128, 0xFFFFFFFF, 2**64, 2**192 - 1]
+    for v in (a1, b1, a2):
+        for m in (1, 2, 3, 2**64, 2**100, 2**127):
+            for d in (-2, -1, 0, 1, 2):
+                edge.append((v * m + d) % 2**256)
+                edge.append((N - v * m + d) % 2**256)
+    # run_scalar_tests (src/tests.c:2456) style patterns: runs of 0x00 / 0xFF bytes
+    rnd = random.Random(99)
+    for _ in range(200):
+        bs = bytearray(32)
+        i = 0
+        while i < 32:
+            run = rnd.randint(1, 8)
+            fill = rnd.choice([0x00, 0xFF, rnd.randint(0, 255)])
+            for j in range(i, min(32, i + run)):
+                bs[j] = fill
+            i += run
+        edge.append(int.from_bytes(bs, "big"))
+    return edge
+
+
+def test_unit_scalar_ops_vs_reference(engine, ref):
+    rnd = random.Random(21)
+    edge = _edge_scalars()
+    n = 100000
+    a = [rnd.choice(edge) if i % 3 == 0 else rnd.getrandbits(256) for i in range(n)] + [x for x in edge for _ in range(4)]
+    b = [rnd.choice(edge) if i % 5 == 0 else rnd.getrandbits(256) for i in range(n)] + [rnd.choice(edge) for x in edge for _ in range(4)]
+    A = b"".join(b32(x) for x in a)
+    B = b"".join(b32(x) for x in b)
+    for op in (U_SC_MUL, U_SC_ADD):
+        assert np.array_equal(engine.unit_op(op, A, B), ref.unit_op(op, A, B)), op
+    for op in (U_SC_NEG, U_SC_SPLIT, U_SC_RED):
+        assert np.array_equal(engine.unit_op(op, A), ref.unit_op(op, A)), op
+    m = 20000 + len(edge) * 4
+    assert np.array_equal(engine.unit_op(U_SC_INV, A[-32 * m:]), ref.unit_op(U_SC_INV, A[-32 * m:]))
+    # split_lambda invariants on the GPU output itself: k = r1 + lambda*r2 (mod n), both halves < 2^128 in absolute value
+    out = engine.unit_op(U_SC_SPLIT, A).reshape(-1, 64)
+    for i in range(0, len(a), 997):
+        r1 = int.from_bytes(bytes(out[i, :32]), "big"); r2 = int.from_bytes(bytes(out[i, 32:]), "big")
+        assert (r1 + LAMBDA * r2 - a[i]) % N == 0
+        assert min(r1, N - r1) < 2**128 and min(r2, N - r2) < 2**128
+
+
+def _points(ref, ks):
+    n = len(ks)
+    return np.frombuffer(ref.ecmult_batch(G64 * n, bytes(32 * n), b"".join(b32(k) for k in ks)).tobytes(), dtype=np.uint8).reshape(n, 64)
+
+
+def test_unit_group_ops_vs_reference(engine, ref):
+    """gej_double / gej_add / gej_add_ge and their 4-lane forms: 10^5 operand pairs over a pool of 2048 points, with every degenerate
+    relation placed deterministically: equal points with different z, opposite points, infinity left / right / both, z = 1 and z = p - 1"""
+    rnd = random.Random(22)
+    pool_k = [rnd.getrandbits(256) % N for _ in range(2048)]
+    pool = _points(ref, pool_k)
+    n = 100000
+    ia = np.array([rnd.randrange(2048) for _ in range(n)])
+    ib = np.array([rnd.randrange(2048) for _ in range(n)])
+    A = np.zeros((n, 96), dtype=np.uint8); B = np.zeros((n, 96), dtype=np.uint8)
+    A[:, :64] = pool[ia]; B[:, :64] = pool[ib]
+    zs = np.frombuffer(b"".join(b32(rnd.choice([1, 2, P - 1, P - 2, 3]) if i % 7 == 0 else rnd.getrandbits(256)) for i in range(2 * n)), dtype=np.uint8).reshape(2 * n, 32)
+    A[:, 64:] = zs[:n]; B[:, 64:] = zs[n:]
+    kinds = {0: 0, 1: 0, 2: 0, 3: 0, 4: 0, 5: 0}
+    for i in range(0, n, 4):
+        kind = (i // 4) % 8
+        if kind == 0:                                   # a == b (doubling branch), different z
+            B[i, :64] = A[i, :64]
+        elif kind == 1:                                 # a == -b (result infinity)
+            B[i, :32] = A[i, :32]
+            y = int.from_bytes(bytes(A[i, 32:64]), "big")
+            B[i, 32:64] = np.frombuffer(b32(P - y), dtype=np.uint8)
+        elif kind == 2:
+            A[i, :64] = 0                               # infinity + b
+        elif kind == 3:
+            B[i, :64] = 0                               # a + infinity
+        elif kind == 4:
+            A[i, :64] = 0; B[i, :64] = 0
+        elif kind == 5:                                 # a == b and equal z too
+            B[i] = A[i]
+        kinds[kind if kind < 6 else 0] += 1
+    assert all(v > 1000 for v in kinds.values())
+    Ab, Bb = A.tobytes(), B.tobytes()
+    exp_dbl, exp_add, exp_mix = ref.unit_op(U_DBL, Ab), ref.unit_op(U_ADD, Ab, Bb), ref.unit_op(U_ADD_GE, Ab, Bb)
+    assert np.array_equal(engine.unit_op(U_DBL, Ab), exp_dbl)
+    assert np.array_equal(engine.unit_op(U_ADD, Ab, Bb), exp_add)
+    assert np.array_equal(engine.unit_op(U_ADD_GE, Ab, Bb), exp_mix)
+    assert np.array_equal(engine.unit_op(U_DBL_G4, Ab), exp_dbl)
+    assert np.array_equal(engine.unit_op(U_ADD_G4, Ab, Bb), exp_add)
+    assert np.array_equal(engine.unit_op(U_ADD_GE_G4, Ab, Bb), exp_mix)
+    # sanity of the expectation itself: the a == -b items really are infinity, the a == b items are the doubling
+    e = exp_add.reshape(n, 64)
+    assert not e[4].any() and np.array_equal(e[0], exp_dbl.reshape(n, 64)[0])
+
+
+# ---- MSM ------------------------------------------------------------------------------------------------------------------------
+def _msm_inputs(ref, rnd, m, hot_from=None):
+    ks = [rnd.getrandbits(256) % N for _ in range(m)]
+    pts = bytearray(_points(ref, ks).tobytes()) if m else bytearray()
+    edge = [0, 1, N - 1, 2**255, 32768, 32769, 65535 << 16, N - 32768, 2**128 - 1, 2**128, (N - 1) // 2, (N + 1) // 2, LAMBDA, N - LAMBDA]
+    scs = [rnd.choice(edge) if i % 4 == 0 else rnd.getrandbits(256) % N for i in range(m)]
+    if m >= 8:
+        pts[64 * 3:64 * 4] = bytes(64)
+        pts[64 * 5:64 * 6] = pts[64 * 4:64 * 5]; scs[5] = (N - scs[4]) % N
+        pts[64 * 6:64 * 7] = pts[64 * 4:64 * 5]; scs[6] = scs[4]
+    if hot_from is not None:
+        for i in range(hot_from, m):
+            scs[i] = scs[hot_from]
+    return b"".join(b32(x) for x in scs), bytes(pts)
+
+
+def test_msm_dispatch_sizes_vs_reference(engine, ref):
+    """every size class of the dispatcher (secp256k1_ecmult_multi_var picks Strauss below 88 points and a bucket window from n,
+    src/ecmult_impl.h:597-621,:823-867): window chosen from n, with and without the generator term"""
+    rnd = random.Random(56)
+    engine.ecmult_multi_set_window(0)
+    for m in (0, 1, 2, 8, 87, 88, 300, 2047, 4096, 9000, 40000):
+        sc, pts = _msm_inputs(ref, rnd, m, hot_from=(m // 2 if m in (300, 9000) else None))
+        for g in (None, b32(rnd.getrandbits(256) % N), b32(0)):
+            ok, exp = ref.ecmult_multi(sc, pts, g, scratch_bytes=64 << 20)
+            assert ok == 1
+            assert engine.ecmult_multi(sc, pts, g) == exp, (m, g is None)
+
+
+def test_msm_every_window_width(engine, ref):
+    rnd = random.Random(57)
+    try:
+        for m, cs in ((150, range(4, 17)), (6000, range(8, 17))):
+            sc, pts = _msm_inputs(ref, rnd, m, hot_from=m - 70)
+            g = b32(rnd.getrandbits(256) % N)
+            ok, exp = ref.ecmult_multi(sc, pts, g, scratch_bytes=64 << 20)
+            assert ok == 1
+            for c in cs:
+                engine.ecmult_multi_set_window(c)
+                assert engine.ecmult_multi(sc, pts, g) == exp, (m, c)
+    finally:
+        engine.ecmult_multi_set_window(0)
+
+
+def test_msm_bench_ecmult_point_set(engine, ref):
+    """config 3 of BASELINE.json as src/bench_ecmult.c builds it (:262-276, :362-371): s_i = SHA256("ecmult" || LE32(i)) mod n,
+    P_i = 2^i * G; expected = (sum s_i 2^i) * G with scalars only (:286-298), and the reference's own ecmult_multi_var"""
+    m = 32768
+    scs = [int.from_bytes(hashlib.sha256(b"ecmult" + i.to_bytes(4, "little")).digest(), "big") % N for i in range(m)]
+    ks = [pow(2, i, N) for i in range(m)]
+    pts = _points(ref, ks).tobytes()
+    sc = b"".join(b32(x) for x in scs)
+    tot = sum(s * k for s, k in zip(scs, ks)) % N
+    exp = bytes(engine.ecmult(bytes(64), bytes(32), b32(tot))[0])
+    assert engine.ecmult_multi(sc, pts) == exp
+    ok, exp2 = ref.ecmult_multi(sc, pts, None, scratch_bytes=64 << 20)
+    assert ok == 1 and exp2 == exp
+
+
+def _dev_msm(engine, torch, sc_t, pt_t, m, partial=False):
+    wsb = engine.ecmult_multi_workspace_bytes(m)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(96 if partial else 64, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    fn = engine.ecmult_multi_partial_dev if partial else engine.ecmult_multi_dev
+    fn(out.data_ptr(), None, sc_t.data_ptr(), pt_t.data_ptr(), m, ws.data_ptr(), wsb, st)
+    return out, ws, wsb, st
+
+
+def test_msm_sharded_partial_and_combine(engine, ref):
+    """an MSM shards by terms; W partial Jacobian sums are gathered and added once.  Shard sizes are ragged on purpose."""
+    import torch
+    rnd = random.Random(58)
+    m = 3000
+    sc, pts = _msm_inputs(ref, rnd, m)
+    ok, exp = ref.ecmult_multi(sc, pts, None, scratch_bytes=64 << 20)
+    sc_t = torch.frombuffer(bytearray(sc), dtype=torch.uint8).cuda().reshape(m, 32)
+    pt_t = torch.frombuffer(bytearray(pts), dtype=torch.uint8).cuda().reshape(m, 64)
+    for world in (1, 2, 3, 8):
+        cuts = [m * r // world for r in range(world + 1)]
+        cuts[1] = min(cuts[1], 1) if world == 3 else cuts[1]             # a one-term shard
+        parts = torch.zeros((world, 96), dtype=torch.uint8, device="cuda")
+        keep = []
+        for r in range(world):
+            lo, hi = cuts[r], cuts[r + 1]
+            o, ws, wsb, st = _dev_msm(engine, torch, sc_t[lo:hi].contiguous(), pt_t[lo:hi].contiguous(), hi - lo, partial=True)
+            torch.cuda.synchronize()
+            parts[r] = o
+            keep.append(ws)
+        out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        engine.ecmult_multi_combine_dev(out.data_ptr(), parts.data_ptr(), world, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert out.cpu().numpy().tobytes() == exp, world
+    # all partials infinity / zero partials
+    z = torch.zeros((4, 96), dtype=torch.uint8, device="cuda")
+    out = torch.ones(64, dtype=torch.uint8, device="cuda")
+    engine.ecmult_multi_combine_dev(out.data_ptr(), z.data_ptr(), 4, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert not out.cpu().numpy().any()
+
+
+def test_msm_adversarial_skew_time_and_value(engine, ref):
+    """2^20 IDENTICAL scalars: every window has ONE bucket holding every term.  Value: k * sum(P_i).  Time: at most 2x the random-scalar
+    MSM of the same size (pieces spread a hot bucket over the whole GPU; round 1 put it on one thread)."""
+    import torch
+    n = 1 << 20
+    dev = torch.device("cuda")
+    gen = torch.Generator(device=dev); gen.manual_seed(5)
+    sk = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=gen); sk[:, 0] &= 0x7F
+    z64, z32 = torch.zeros((n, 64), dtype=torch.uint8, device=dev), torch.zeros((n, 32), dtype=torch.uint8, device=dev)
+    pts = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    engine.ecmult_dev(pts.data_ptr(), z64.data_ptr(), z32.data_ptr(), sk.data_ptr(), n, st)
+    rnd_sc = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=gen)
+    k = random.Random(3).getrandbits(256) % N
+    same = torch.frombuffer(bytearray(b32(k)), dtype=torch.uint8).to(dev).repeat(n, 1).contiguous()
+    wsb = engine.ecmult_multi_workspace_bytes(n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    out = torch.zeros(64, dtype=torch.uint8, device=dev)
+
+    def run(sc):
+        for _ in range(2):
+            engine.ecmult_multi_dev(out.data_ptr(), None, sc.data_ptr(), pts.data_ptr(), n, ws.data_ptr(), wsb, st)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            engine.ecmult_multi_dev(out.data_ptr(), None, sc.data_ptr(), pts.data_ptr(), n, ws.data_ptr(), wsb, st)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 3, out.cpu().numpy().tobytes()
+    t_rand, _ = run(rnd_sc)
+    t_same, got = run(same)
+    tot = sum(int.from_bytes(bytes(r), "big") for r in sk.cpu().numpy()) % N
+    exp = bytes(engine.ecmult(bytes(64), bytes(32), b32(tot * k % N))[0])
+    assert got == exp
+    print("MSM 2^20: random %.3f ms, identical scalars %.3f ms" % (t_rand, t_same))
+    assert t_same <= 2.0 * t_rand, (t_rand, t_same)

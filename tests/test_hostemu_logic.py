@@ -234,21 +234,42 @@ def test_rangeproof_and_pedersen_logic(emu, ref):
                 assert ref.rangeproof_verify_one(bytes(commits[i]), bytes(bad), gen) == _emu_rp(emu, bytes(commits[i]), bytes(bad), gen)
 
 
+def _msm_case(rnd, ref, m, same_scalar_from=None):
+    ks = [rnd.getrandbits(256) % N for _ in range(m)]
+    pts = bytearray(ref.ecmult_batch(G64 * m, bytes(32 * m), b"".join(b32(k) for k in ks)).tobytes()) if m else bytearray()
+    edge = [0, 1, N - 1, 2**255, 32768, 32769, 65535 << 16, N - 32768, 2**128 - 1, 2**128, 2**127, (N - 1) // 2, (N + 1) // 2, LAMBDA, N - LAMBDA]
+    scs = [rnd.choice(edge) if i % 4 == 0 else rnd.getrandbits(256) % N for i in range(m)]
+    if m >= 7:
+        pts[64 * 3:64 * 4] = bytes(64)                                       # point at infinity
+        pts[64 * 5:64 * 6] = pts[64 * 4:64 * 5]; scs[5] = (N - scs[4]) % N   # cancelling pair
+        pts[64 * 6:64 * 7] = pts[64 * 4:64 * 5]; scs[6] = scs[4]             # equal points in one bucket (doubling branch)
+    if same_scalar_from is not None:
+        for i in range(same_scalar_from, m):
+            scs[i] = scs[same_scalar_from]                                   # hot buckets: many terms share every digit
+    return b"".join(b32(x) for x in scs), bytes(pts)
+
+
+LAMBDA = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
+
+
 def test_msm_pipeline_logic(emu, ref):
+    """the GPU MSM pipeline (k_msm.cu) executed sequentially on the host: every window width, forced small pieces (multi-piece buckets +
+    combine), hot buckets, edge scalars incl. the GLV split bounds -- against the reference's ecmult_multi_var"""
     rnd = random.Random(5)
-    for m in (0, 1, 7, 100, 300):
-        ks = [rnd.getrandbits(256) % N for _ in range(m)]
-        pts = bytearray(ref.ecmult_batch(G64 * m, bytes(32 * m), b"".join(b32(k) for k in ks)).tobytes()) if m else bytearray()
-        scs = [rnd.choice([0, 1, N - 1, 2**255, 32768, 32769, 65535 << 16, N - 32768]) if i % 4 == 0 else rnd.getrandbits(256) % N for i in range(m)]
-        if m >= 7:
-            pts[64 * 3:64 * 4] = bytes(64)
-            pts[64 * 5:64 * 6] = pts[64 * 4:64 * 5]; scs[5] = (N - scs[4]) % N
-        sc = b"".join(b32(x) for x in scs)
+    emu.emu_msm2.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32]
+    cases = [(0, 0, 0), (1, 0, 0), (7, 0, 0), (100, 0, 0), (300, 0, 0)]
+    cases += [(23, c, 0) for c in range(4, 17)]                              # every window width (top-window geometry differs for each)
+    cases += [(150, 5, 2), (150, 8, 3), (90, 13, 1)]                         # tiny pieces: multi-piece buckets, parts, combine
+    for (m, c, tp) in cases:
+        sc, pts = _msm_case(rnd, ref, m, same_scalar_from=(40 if tp else None))
         for g in (None, b32(rnd.getrandbits(256) % N)):
             out = ctypes.create_string_buffer(64)
-            emu.emu_msm(out, g, sc if m else None, bytes(pts) if m else None, ctypes.c_size_t(m))
-            ok, exp = ref.ecmult_multi(sc, bytes(pts), g, scratch_bytes=1 << 22)
-            assert ok == 1 and out.raw == exp, (m, g is None)
+            emu.emu_msm2(out, g, sc if m else None, pts if m else None, m, c, tp)
+            ok, exp = ref.ecmult_multi(sc, pts, g, scratch_bytes=1 << 22)
+            assert ok == 1 and out.raw == exp, (m, c, tp, g is None)
+    # the dispatcher: window width grows with n, c = 8 below 2^11 terms, 16 at 2^20
+    cs = [emu.emu_msm_choose_c(ctypes.c_size_t(n)) for n in (1, 88, 2048, 1 << 13, 1 << 15, 1 << 17, 1 << 20, 1 << 24)]
+    assert cs[0] == 8 and cs[1] == 8 and cs == sorted(cs) and cs[5] == 13 and cs[6] == 16 and cs[7] == 16, cs
 
 
 def test_bppp_norm_verify_logic(emu, ref):
