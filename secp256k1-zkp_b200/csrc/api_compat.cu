@@ -349,6 +349,14 @@ int secp256k1_ecdsa_verify(const secp256k1_context* ctx, const secp256k1_ecdsa_s
     ARG_CHECK(msghash32 != NULL);
     ARG_CHECK(sig != NULL);
     ARG_CHECK(pubkey != NULL);
+    {   // the reference evaluates  !is_high(s) && pubkey_load(..) && sig_verify(..)  in this order (src/secp256k1.c:509-511): a high s returns 0
+        // quietly, before pubkey_load's ARG_CHECK can fire on a zeroed key
+        static const unsigned char HALF_ORDER_LE[32] = {0xA0, 0x20, 0x1B, 0x68, 0x46, 0x2F, 0xE9, 0xDF, 0x1D, 0x50, 0xA4, 0x57, 0x73, 0x6E, 0x57, 0x5D,
+                                                        0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0x7F};
+        int high = 0;
+        for (int i = 31; i >= 0; i--) if (sig->data[32 + i] != HALF_ORDER_LE[i]) { high = sig->data[32 + i] > HALF_ORDER_LE[i]; break; }
+        if (high) return 0;
+    }
     ARG_CHECK(!all_zero(pubkey->data, 32));
     ENGINE_OR_FAIL(e);
     unsigned char ok = 0;
@@ -438,6 +446,11 @@ int secp256k1_schnorrsig_verify(const secp256k1_context* ctx, const unsigned cha
     ARG_CHECK(sig64 != NULL);
     ARG_CHECK(msg != NULL || msglen == 0);
     ARG_CHECK(pubkey != NULL);
+    {   // r >= p and s >= n return 0 before secp256k1_xonly_pubkey_load runs its ARG_CHECK (modules/schnorrsig/main_impl.h:231-242)
+        static const unsigned char FIELD_P_BE[32] = {0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF,
+                                                     0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFE, 0xFF, 0xFF, 0xFC, 0x2F};
+        if (memcmp(sig64, FIELD_P_BE, 32) >= 0 || memcmp(sig64 + 32, ORDER_BE, 32) >= 0) return 0;
+    }
     ARG_CHECK(!all_zero(pubkey->data, 32));
     ENGINE_OR_FAIL(e);
     unsigned char ok = 0, dummy = 0;
@@ -548,15 +561,16 @@ int secp256k1_rangeproof_verify(const secp256k1_context* ctx, uint64_t* min_valu
     ARG_CHECK(extra_commit != NULL || extra_commit_len == 0);
     ARG_CHECK(gen != NULL);
     if (plen > 0xFFFFFFFFull || extra_commit_len > 0xFFFFFFFFull) return 0;
+    if (plen < 65) return 0;                      // secp256k1_rangeproof_getheader_impl rejects before reading anything (rangeproof_impl.h:492)
     ENGINE_OR_FAIL(e);
     unsigned char ok = 0;
     uint32_t pl = (uint32_t)plen, el = (uint32_t)extra_commit_len;
     uint64_t mn = 0, mx = 0;
     // the header outputs are written even when the proof fails later (rangeproof_impl.h:565); when the header itself is rejected
     // the reference leaves the caller's variables partially written -- the device reports exactly what was written so far
-    GPU_CALL(secp256k1_b200_rangeproof_verify_batch(e, &ok, &mn, &mx, commit->data, proof, plen ? plen : 1, &pl, gen->data, 0,
+    GPU_CALL(secp256k1_b200_rangeproof_verify_batch(e, &ok, &mn, &mx, commit->data, proof, plen, &pl, gen->data, 0,
                                                     extra_commit_len ? extra_commit : NULL, extra_commit_len, extra_commit_len ? &el : NULL, 1));
-    if (plen >= 65 && (proof[0] & 128) == 0) { *min_value = mn; *max_value = mx; }
+    if ((proof[0] & 128) == 0) { *min_value = mn; *max_value = mx; }
     return ok;
 }
 
@@ -574,15 +588,16 @@ int secp256k1_rangeproof_rewind(const secp256k1_context* ctx, unsigned char* bli
     ARG_CHECK(gen != NULL);
     ARG_CHECK(ctx->proper);                       // ecmult_gen context built (:47)
     if (plen > 0xFFFFFFFFull || extra_commit_len > 0xFFFFFFFFull) return 0;
+    if (plen < 65) return 0;
     ENGINE_OR_FAIL(e);
     unsigned char ok = 0, blind[32];
     uint32_t pl = (uint32_t)plen, el = (uint32_t)extra_commit_len, ml = 0;
     uint64_t mn = 0, mx = 0, value = 0;
     size_t cap = (message_out && outlen) ? (*outlen > 4096 ? 4096 : *outlen) : 0;       // at most 4096 message bytes exist (rangeproof_impl.h:359)
     GPU_CALL(secp256k1_b200_rangeproof_rewind_batch(e, &ok, blind, &value, cap ? message_out : NULL, cap, &ml, &mn, &mx, nonce, commit->data, proof,
-                                                    plen ? plen : 1, &pl, gen->data, 0, extra_commit_len ? extra_commit : NULL, extra_commit_len,
+                                                    plen, &pl, gen->data, 0, extra_commit_len ? extra_commit : NULL, extra_commit_len,
                                                     extra_commit_len ? &el : NULL, 1));
-    if (plen >= 65 && (proof[0] & 128) == 0) { *min_value = mn; *max_value = mx; }
+    if ((proof[0] & 128) == 0) { *min_value = mn; *max_value = mx; }
     if (!ok) return 0;
     if (blind_out) memcpy(blind_out, blind, 32);
     if (value_out) *value_out = value;

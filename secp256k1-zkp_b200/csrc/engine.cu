@@ -6,7 +6,6 @@
 #include "launch.h"
 #include "sha256.cuh"
 
-#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -46,7 +45,7 @@ struct secp256k1_b200_engine {
     size_t scratch_bytes;
     uint8_t* h_pinned;         // grow-only pinned host staging for results (a D2H copy into pageable memory would block the host
     size_t pinned_bytes;       //  and serialize the chunk pipeline)
-    uint64_t launches;
+    uint64_t launches;         // updated with atomic adds by the launchers (_dev calls may come from many threads)
     int msm_window;            // 0 = chosen from n (msm_choose_c); otherwise forced (secp256k1_b200_ecmult_multi_set_window)
     std::mutex mu;             // the reference context is usable from many threads (secp256k1.h:42-49): serialize here
 
@@ -168,7 +167,7 @@ void secp256k1_b200_engine_destroy(secp256k1_b200_engine* e) {
 
 void* secp256k1_b200_engine_table_ptr(secp256k1_b200_engine* e) { return e ? (void*)e->d_gtab : nullptr; }
 size_t secp256k1_b200_engine_table_bytes(const secp256k1_b200_engine* e) { return e ? e->gtab_bytes : 0; }
-uint64_t secp256k1_b200_engine_launch_count(const secp256k1_b200_engine* e) { return e ? e->launches : 0; }
+uint64_t secp256k1_b200_engine_launch_count(const secp256k1_b200_engine* e) { return e ? __atomic_load_n(&e->launches, __ATOMIC_RELAXED) : 0; }
 int secp256k1_b200_engine_device(const secp256k1_b200_engine* e) { return e ? e->device : -1; }
 
 int secp256k1_b200_engine_table_build(secp256k1_b200_engine* e) {
@@ -499,20 +498,12 @@ int secp256k1_b200_schnorrsig_aggverify(secp256k1_b200_engine* e, int* ok, const
     // The randomizer chain is one running SHA-256 over all signatures: serial by construction.  With host buffers it is
     // walked here on the host (while the uploads above are in flight); the _dev entry point walks it in a one-thread kernel.
     std::vector<uint8_t> z(32 * n + 32);
-    const bool timing = getenv("SECP256K1_B200_TIMING") != nullptr;
-    auto t0 = std::chrono::steady_clock::now();
     b200_host_halfagg_z_chain(z.data(), e->mid_halfagg, aggsig, pubkeys32, msgs32, n, 0);     // host_sha256.cpp (SHA extensions when present)
-    auto t1 = std::chrono::steady_clock::now();
     if (n) CK(cudaMemcpyAsync(c.at(oz), z.data(), 32 * n, cudaMemcpyHostToDevice, e->stream));
     CK(launch_halfagg_verify(c.at(oo), c.at(opk), c.at(om), n, c.at(oa), n ? c.at(oz) : nullptr, e->mid_halfagg, e->mid, c.at(ow), wsb, e->stream, &e->launches));
     unsigned char r = 0;
     CK(cudaMemcpyAsync(&r, c.at(oo), 1, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    if (timing) {
-        auto t2 = std::chrono::steady_clock::now();
-        fprintf(stderr, "[b200 timing] aggverify n=%zu: randomizer chain %.2f ms, device part (terms + MSM + copies) %.2f ms\n", n,
-                std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
-    }
     *ok = r;
     return 1;
 }
@@ -637,8 +628,7 @@ int secp256k1_b200_bppp_norm_verify_batch(secp256k1_b200_engine* e, unsigned cha
     carver c(e);
     size_t ng = g_len + h_len;
     size_t op = c.add(proof_stride * n), ol = c.add(4 * n), ot = c.add(104 * n), orh = c.add(32 * n), og = c.add(64 * ng),
-           oc = c.add(32 * h_len * n), ocm = c.add(64 * n), ook = c.add(n), odbg = c.add(33 * 64 * n);
-    const char* dbgfile = getenv("SECP256K1_B200_BPPP_DEBUG");
+           oc = c.add(32 * h_len * n), ocm = c.add(64 * n), ook = c.add(n);
     if (!c.commit()) return 0;
     CK(cudaMemcpyAsync(c.at(op), proofs, proof_stride * n, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(c.at(ol), plen, 4 * n, cudaMemcpyHostToDevice, e->stream));
@@ -647,15 +637,7 @@ int secp256k1_b200_bppp_norm_verify_batch(secp256k1_b200_engine* e, unsigned cha
     CK(cudaMemcpyAsync(c.at(og), gens64, 64 * ng, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(c.at(oc), c_vec32, 32 * h_len * n, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(c.at(ocm), commits64, 64 * n, cudaMemcpyHostToDevice, e->stream));
-    if (dbgfile) {
-        CK(launch_bppp_norm_verify(c.at(ook), c.at(op), proof_stride, (const uint32_t*)c.at(ol), c.at(ot), c.at(orh), c.at(og), (uint32_t)g_len, c.at(oc),
-                                   (uint32_t)h_len, c.at(ocm), n, e->gt(), e->stream, &e->launches, c.at(odbg)));
-        std::vector<unsigned char> h(33 * 64 * n);
-        CK(cudaMemcpyAsync(h.data(), c.at(odbg), h.size(), cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaStreamSynchronize(e->stream));
-        FILE* f = fopen(dbgfile, "wb");
-        if (f) { fwrite(h.data(), 1, h.size(), f); fclose(f); }
-    } else if (!secp256k1_b200_bppp_norm_verify_batch_dev(e, c.at(ook), c.at(op), proof_stride, (const uint32_t*)c.at(ol), c.at(ot), c.at(orh), c.at(og), g_len,
+    if (!secp256k1_b200_bppp_norm_verify_batch_dev(e, c.at(ook), c.at(op), proof_stride, (const uint32_t*)c.at(ol), c.at(ot), c.at(orh), c.at(og), g_len,
                                                    c.at(oc), h_len, c.at(ocm), n, e->stream)) return 0;
     CK(cudaMemcpyAsync(ok, c.at(ook), n, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));

@@ -6,8 +6,12 @@
 // operands, each lane multiplies a different pair of field elements at every step, and the products are exchanged with
 // __shfl_sync: a doubling is 3 multiplication steps deep instead of 7, a Jacobian addition 6 instead of 16, a mixed addition 6
 // instead of 11.  Squarings are executed as multiplications so that all lanes run the same instruction stream.
-// Contract: the 4 lanes of a group (lane & ~3 .. +3) call with identical arguments and receive identical results; different
-// groups of a warp may take different paths (the shuffles are masked to the group).
+//
+// Contract (r2b): ALL 32 LANES OF THE WARP call together, converged; the 4 lanes of a group (lane & ~3 .. +3) pass identical arguments
+// and receive identical results; the 8 groups of a warp work on 8 different items.  Control flow inside is warp-uniform (the
+// degenerate cases are resolved by selects, or by branches taken on a warp vote), so every shuffle is a plain full-mask SHFL.  The
+// first version masked the shuffles to the group and let groups branch independently: ptxas then wraps every exchange in a
+// WARPSYNC.COLLECTIVE region and a doubling took ~3 us instead of ~1 (profiles/r2a: k_msm_tail 600 us for ~130 doublings).
 // Host build (tests/hostemu): the same names fall back to the plain one-thread functions.
 #pragma once
 #include "ge.cuh"
@@ -15,13 +19,12 @@
 namespace B200_NS {
 
 #if defined(__CUDA_ARCH__)
-__device__ __forceinline__ uint32_t g4_mask() { return 0xFu << ((threadIdx.x & 31u) & ~3u); }
+#define G4_FULL 0xffffffffu
 __device__ __forceinline__ fe g4_bcast(const fe& a, int src) {
     fe r;
-    const uint32_t m = g4_mask();
     const int lane = (int)((threadIdx.x & 31u) & ~3u) + src;
 #pragma unroll
-    for (int k = 0; k < 8; k++) r.v[k] = __shfl_sync(m, a.v[k], lane);
+    for (int k = 0; k < 8; k++) r.v[k] = __shfl_sync(G4_FULL, a.v[k], lane);
     return r;
 }
 __device__ __forceinline__ fe g4_sel(int l, const fe& a0, const fe& a1, const fe& a2, const fe& a3) {
@@ -36,9 +39,12 @@ __device__ __forceinline__ fe g4_sel2(int l, const fe& a0, const fe& a1) {      
     for (int k = 0; k < 8; k++) r.v[k] = (l & 1) ? a1.v[k] : a0.v[k];
     return r;
 }
+__device__ __forceinline__ void g4_gej_select(gej& r, const gej& a, bool take) {   // r = take ? a : r
+    if (take) r = a;
+}
 
+// r = 2a.  Branch free: an infinite input just carries its flag through (the arithmetic runs on whatever the coordinates hold).
 static __device__ __noinline__ void gej_double_g4(gej& r, const gej& a) {
-    if (a.inf) { r = a; return; }
     const int l = (int)(threadIdx.x & 3u);
     fe p, q, o;
     // step 1: Y*Z | Y*Y | X*X
@@ -58,15 +64,44 @@ static __device__ __noinline__ void gej_double_g4(gej& r, const gej& a) {
     fe_sub(t, t, x3);
     // step 3 (every lane, no exchange): (t - x3) * L
     fe_mul(o, t, lq);
+    const int inf = a.inf;
     fe_sub(r.y, o, ss);
     r.x = x3;
     r.z = u;
-    r.inf = 0;
+    r.inf = inf;
+}
+
+// steps 4..6 shared by the two additions: given h, rr, (x1, s1 = "y1 * z2^3") and zz = z1*z2 (or z1)
+__device__ __forceinline__ void g4_add_finish(gej& g, int l, const fe& h, const fe& rr, const fe& u1, const fe& s1, const fe& zz) {
+    fe p, q, o;
+    // step 4: h^2 | rr^2 | zz*h
+    p = g4_sel(l, h, rr, zz, zz);
+    q = g4_sel(l, h, rr, h, h);
+    fe_mul(o, p, q);
+    fe hh = g4_bcast(o, 0), x3 = g4_bcast(o, 1), z3 = g4_bcast(o, 2);
+    // step 5: hh*h | u1*hh
+    p = g4_sel2(l, hh, u1);
+    q = g4_sel2(l, h, hh);
+    fe_mul(o, p, q);
+    fe hhh = g4_bcast(o, 0), v = g4_bcast(o, 1);
+    fe_sub(x3, x3, hhh);
+    fe_sub(x3, x3, v);
+    fe_sub(x3, x3, v);
+    fe_sub(v, v, x3);
+    // step 6: (v - x3)*rr | hhh*s1
+    p = g4_sel2(l, v, hhh);
+    q = g4_sel2(l, rr, s1);
+    fe_mul(o, p, q);
+    fe m = g4_bcast(o, 0), w = g4_bcast(o, 1);
+    fe_sub(g.y, m, w);
+    g.x = x3;
+    g.z = z3;
+    g.inf = 0;
 }
 
 static __device__ __noinline__ void gej_add_g4(gej& r, const gej& a, const gej& b) {
-    if (a.inf) { r = b; return; }
-    if (b.inf) { r = a; return; }
+    const bool triv = a.inf || b.inf;
+    if (__all_sync(G4_FULL, triv)) { gej t = a.inf ? b : a; r = t; return; }      // warp-uniform shortcut (sparse buckets)
     const int l = (int)(threadIdx.x & 3u);
     fe p, q, o;
     // step 1: z1^2 | z2^2 | z1*z2
@@ -87,40 +122,24 @@ static __device__ __noinline__ void gej_add_g4(gej& r, const gej& a, const gej& 
     fe h, rr;
     fe_sub(h, u2, u1);
     fe_sub(rr, s2, s1);
-    if (fe_is_zero(h)) {
-        if (fe_is_zero(rr)) gej_double_g4(r, a);
-        else gej_set_infinity(r);
-        return;
-    }
-    // step 4: h^2 | rr^2 | zz*h
-    p = g4_sel(l, h, rr, zz, zz);
-    q = g4_sel(l, h, rr, h, h);
-    fe_mul(o, p, q);
-    fe hh = g4_bcast(o, 0), x3 = g4_bcast(o, 1), z3 = g4_bcast(o, 2);
-    // step 5: hh*h | u1*hh
-    p = g4_sel2(l, hh, u1);
-    q = g4_sel2(l, h, hh);
-    fe_mul(o, p, q);
-    fe hhh = g4_bcast(o, 0), v = g4_bcast(o, 1);
-    fe_sub(x3, x3, hhh);
-    fe_sub(x3, x3, v);
-    fe_sub(x3, x3, v);
-    fe_sub(v, v, x3);
-    // step 6: (v - x3)*rr | hhh*s1
-    p = g4_sel2(l, v, hhh);
-    q = g4_sel2(l, rr, s1);
-    fe_mul(o, p, q);
-    fe m = g4_bcast(o, 0), w = g4_bcast(o, 1);
-    fe_sub(r.y, m, w);
-    r.x = x3;
-    r.z = z3;
-    r.inf = 0;
+    const bool hz = fe_is_zero(h), rz = fe_is_zero(rr);
+    gej g;
+    g4_add_finish(g, l, h, rr, u1, s1, zz);
+    const bool need_dbl = !triv && hz && rz;
+    gej d;
+    if (__any_sync(G4_FULL, need_dbl)) gej_double_g4(d, a);                        // branch on a warp vote
+    gej out;
+    if (a.inf) out = b;
+    else if (b.inf) out = a;
+    else if (hz) { if (rz) out = d; else gej_set_infinity(out); }
+    else out = g;
+    r = out;
 }
 
 // r = a + b, b affine
 static __device__ __noinline__ void gej_add_ge_g4(gej& r, const gej& a, const ge& b) {
-    if (a.inf) { gej_set_ge(r, b); return; }
-    if (b.inf) { r = a; return; }
+    const bool triv = a.inf || b.inf;
+    if (__all_sync(G4_FULL, triv)) { gej t; if (a.inf) gej_set_ge(t, b); else t = a; r = t; return; }
     const int l = (int)(threadIdx.x & 3u);
     fe p, q, o, z12;
     fe_mul(z12, a.z, a.z);                                      // step 1 (every lane)
@@ -133,34 +152,18 @@ static __device__ __noinline__ void gej_add_ge_g4(gej& r, const gej& a, const ge
     fe h, rr;
     fe_sub(h, u2, a.x);
     fe_sub(rr, s2, a.y);
-    if (fe_is_zero(h)) {
-        if (fe_is_zero(rr)) gej_double_g4(r, a);
-        else gej_set_infinity(r);
-        return;
-    }
-    // step 4: h^2 | rr^2 | z1*h
-    p = g4_sel(l, h, rr, a.z, a.z);
-    q = g4_sel(l, h, rr, h, h);
-    fe_mul(o, p, q);
-    fe hh = g4_bcast(o, 0), x3 = g4_bcast(o, 1), z3 = g4_bcast(o, 2);
-    // step 5: hh*h | x1*hh
-    p = g4_sel2(l, hh, a.x);
-    q = g4_sel2(l, h, hh);
-    fe_mul(o, p, q);
-    fe hhh = g4_bcast(o, 0), v = g4_bcast(o, 1);
-    fe_sub(x3, x3, hhh);
-    fe_sub(x3, x3, v);
-    fe_sub(x3, x3, v);
-    fe_sub(v, v, x3);
-    // step 6: (v - x3)*rr | hhh*y1
-    p = g4_sel2(l, v, hhh);
-    q = g4_sel2(l, rr, a.y);
-    fe_mul(o, p, q);
-    fe m = g4_bcast(o, 0), w = g4_bcast(o, 1);
-    fe_sub(r.y, m, w);
-    r.x = x3;
-    r.z = z3;
-    r.inf = 0;
+    const bool hz = fe_is_zero(h), rz = fe_is_zero(rr);
+    gej g;
+    g4_add_finish(g, l, h, rr, a.x, a.y, a.z);
+    const bool need_dbl = !triv && hz && rz;
+    gej d;
+    if (__any_sync(G4_FULL, need_dbl)) gej_double_g4(d, a);
+    gej out;
+    if (a.inf) gej_set_ge(out, b);
+    else if (b.inf) out = a;
+    else if (hz) { if (rz) out = d; else gej_set_infinity(out); }
+    else out = g;
+    r = out;
 }
 #else
 HD void gej_double_g4(gej& r, const gej& a) { gej t; gej_double(t, a); r = t; }

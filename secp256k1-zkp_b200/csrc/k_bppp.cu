@@ -11,7 +11,7 @@ namespace b200 {
 __global__ void __launch_bounds__(BP_WARPS * 32, 3) k_bppp_norm_verify(uint8_t* __restrict__ ok, const uint8_t* __restrict__ proofs, size_t stride,
         const uint32_t* __restrict__ plen, const uint8_t* __restrict__ transcripts, const uint8_t* __restrict__ rho32,
         const uint8_t* __restrict__ gens64, uint32_t g_len, const uint8_t* __restrict__ c_vec32, uint32_t h_len,
-        const uint8_t* __restrict__ commits64, size_t n, ecmult_gtable gt, uint8_t* dbg) {
+        const uint8_t* __restrict__ commits64, size_t n, ecmult_gtable gt) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t item = (size_t)blockIdx.x * BP_WARPS + warp;
@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(BP_WARPS * 32, 3) k_bppp_norm_verify(uint8_t* 
     sc rho;
     int good = !sc_set_b32(rho, rho32 + 32 * item);          // the reference's callers CHECK(!overflow); reject here
     bppp_ctx c;
+    good = good && plen[item] <= stride;                     // device-side lengths are not trusted
     good = good && bppp_prepare(c, proof, plen[item], tr, rho, g_len, h_len);
     if (!good) { if (lane == 0) ok[item] = 0; return; }      // uniform across the warp
 
@@ -70,11 +71,6 @@ __global__ void __launch_bounds__(BP_WARPS * 32, 3) k_bppp_norm_verify(uint8_t* 
             gej_add_ge(sum, acc, cm); acc = sum;
         }
     }
-    if (dbg) {   // diagnostics: per-lane partial sums as affine x||y
-        uint8_t* o = dbg + (item * 33 + lane) * 64;
-        if (acc.inf) { for (int k = 0; k < 64; k++) o[k] = 0; }
-        else { ge a; ge_set_gej(a, acc); fe_get_b32(o, a.x); fe_get_b32(o + 32, a.y); }
-    }
     bad = __any_sync(0xffffffffu, bad);
     __syncwarp();                                            // all table use finished: the region becomes the sum scratch
     pts[lane] = acc;
@@ -85,26 +81,20 @@ __global__ void __launch_bounds__(BP_WARPS * 32, 3) k_bppp_norm_verify(uint8_t* 
     }
     if (lane == 0) {
         ok[item] = (uint8_t)(!bad && pts[0].inf);
-        if (dbg) {
-            uint8_t* o = dbg + (item * 33 + 32) * 64;
-            gej tot = pts[0];
-            if (tot.inf) { for (int k = 0; k < 64; k++) o[k] = 0; }
-            else { ge a; ge_set_gej(a, tot); fe_get_b32(o, a.x); fe_get_b32(o + 32, a.y); }
-        }
     }
 }
 
 cudaError_t launch_bppp_norm_verify(uint8_t* ok, const uint8_t* proofs, size_t stride, const uint32_t* plen, const uint8_t* transcripts,
                                     const uint8_t* rho32, const uint8_t* gens64, uint32_t g_len, const uint8_t* c_vec32, uint32_t h_len,
-                                    const uint8_t* commits64, size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches, uint8_t* dbg) {
+                                    const uint8_t* commits64, size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches) {
     if (n == 0) return cudaSuccess;
     const int smem = BP_WARPS * BP_WARP_STRIDE;
     cudaError_t err = cudaFuncSetAttribute(k_bppp_norm_verify, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return err;
     ecmult_gtable g; g.data = gt.data; g.gw = gt.gw; g.windows = gt.windows;
     k_bppp_norm_verify<<<(unsigned)((n + BP_WARPS - 1) / BP_WARPS), BP_WARPS * 32, smem, s>>>(ok, proofs, stride, plen, transcripts, rho32, gens64, g_len,
-                                                                                          c_vec32, h_len, commits64, n, g, dbg);
-    if (launches) *launches += 1;
+                                                                                          c_vec32, h_len, commits64, n, g);
+    if (launches) __atomic_fetch_add(launches, (uint64_t)1, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }
 

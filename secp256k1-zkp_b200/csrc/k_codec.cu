@@ -19,7 +19,7 @@ cudaError_t launch_codec(uint8_t* ok, uint8_t* out64, const uint8_t* in, size_t 
                          cudaStream_t s, uint64_t* launches) {
     if (n == 0) return cudaSuccess;
     k_codec<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(ok, out64, in, in_stride, in_len, fmt, n);
-    if (launches) *launches += 1;
+    if (launches) __atomic_fetch_add(launches, (uint64_t)1, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }
 

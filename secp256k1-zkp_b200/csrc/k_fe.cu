@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) k_imad_probe(uint64_t* out, int iters, ui
 }
 cudaError_t launch_imad_probe(uint64_t* out, int blocks, int threads, int iters, cudaStream_t s, uint64_t* launches) {
     k_imad_probe<<<blocks, threads, 0, s>>>(out, iters, 12345u);
-    if (launches) *launches += 1;
+    if (launches) __atomic_fetch_add(launches, (uint64_t)1, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }
 

@@ -34,7 +34,7 @@ cudaError_t launch_gtable_build(uint32_t* d_tab, uint32_t* d_bases, int gw, int 
     if (err != cudaSuccess) return err;
     size_t total = ((size_t)1 << gw) * (size_t)windows;
     k_gtable_entries<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_tab, d_bases, gw, windows);
-    if (launches) *launches += 2;
+    if (launches) __atomic_fetch_add(launches, (uint64_t)2, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }
 

@@ -79,16 +79,16 @@ cudaError_t launch_halfagg_verify(uint8_t* d_ok, const uint8_t* d_pk32, const ui
         halfagg_midstate hm;
         for (int i = 0; i < 8; i++) hm.s[i] = hmid[i];
         k_halfagg_z<<<1, 32, 0, s>>>(z, hm, d_aggsig, d_pk32, d_msgs32, n);
-        if (launches) *launches += 1;
+        if (launches) __atomic_fetch_add(launches, (uint64_t)1, __ATOMIC_RELAXED);
     }
     bip340_midstate m;
     for (int i = 0; i < 8; i++) m.s[i] = mid.s[i];
     k_halfagg_terms<<<(unsigned)((n + 128) / 128), 128, 0, s>>>(scalars, points, gsc, fail, d_aggsig, d_pk32, d_msgs32, d_z32_in ? d_z32_in : z, n, m);
-    if (launches) *launches += 1;
+    if (launches) __atomic_fetch_add(launches, (uint64_t)1, __ATOMIC_RELAXED);
     err = launch_msm(out64, 0, gsc, scalars, points, 2 * n, ws, msm_workspace_bytes(2 * n), 0, s, launches);
     if (err != cudaSuccess) return err;
     k_halfagg_finish<<<1, 32, 0, s>>>(d_ok, out64, fail);
-    if (launches) *launches += 1;
+    if (launches) __atomic_fetch_add(launches, (uint64_t)1, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }
 

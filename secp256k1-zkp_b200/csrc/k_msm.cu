@@ -26,15 +26,16 @@ struct msm_ws {
     uint32_t* pbase;     // [TB+1]     first piece (unit) of a bucket
     uint32_t* mbase;     // [TB+1]     first slot in `parts` of a multi-piece bucket
     uint32_t* blocktot;  // [nblk][4]
-    uint32_t* counters;  // [4]        [0] = number of multi-piece buckets
-    uint32_t* multi;     // [cap_multi]
+    uint32_t* counters;  // [4]        [0] = number of large multi-piece buckets (> MSM_SMALL_MULTI pieces), [1] = small ones
+    uint32_t* multi;     // [cap_multi]  large multi-piece buckets
+    uint32_t* multi_s;   // [cap_multi]  small multi-piece buckets
     uint32_t* entries;   // [2*nw*N]
     msm_unit* units;     // [cap_units]
     gej_store* buckets;  // [TB]
     gej_store* parts;    // [cap_parts]
     gej_store* Lq;       // [TB/8]
     gej_store* Aq;       // [TB/8]
-    gej_store* T;        // [2*nw][MSM_MAX_SUMS]
+    gej_store* T;        // [2*nw][MSM_MAX_SUMS][MSM_R2_PARTS]
 };
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -63,13 +64,14 @@ static size_t carve(msm_ws* w, uint8_t* base, const msm_plan& p) {
     q = take((size_t)(p.TB + 1) * 4); if (w) w->mbase = (uint32_t*)q;
     q = take(c.nblk * 16); if (w) w->blocktot = (uint32_t*)q;
     q = take(c.cap_multi * 4); if (w) w->multi = (uint32_t*)q;
+    q = take(c.cap_multi * 4); if (w) w->multi_s = (uint32_t*)q;
     q = take(c.emax * 4); if (w) w->entries = (uint32_t*)q;
     q = take(c.cap_units * sizeof(msm_unit)); if (w) w->units = (msm_unit*)q;
     q = take((size_t)p.TB * sizeof(gej_store)); if (w) w->buckets = (gej_store*)q;
     q = take(c.cap_parts * sizeof(gej_store)); if (w) w->parts = (gej_store*)q;
     q = take((size_t)(p.TB / MSM_CHUNK) * sizeof(gej_store)); if (w) w->Lq = (gej_store*)q;
     q = take((size_t)(p.TB / MSM_CHUNK) * sizeof(gej_store)); if (w) w->Aq = (gej_store*)q;
-    q = take((size_t)2 * p.nw * MSM_MAX_SUMS * sizeof(gej_store)); if (w) w->T = (gej_store*)q;
+    q = take((size_t)2 * p.nw * MSM_MAX_SUMS * MSM_R2_PARTS * sizeof(gej_store)); if (w) w->T = (gej_store*)q;
     return o;
 }
 // window widths a caller may force (secp256k1_b200_ecmult_multi_set_window); the workspace is sized for the worst of them
@@ -206,7 +208,9 @@ __global__ void __launch_bounds__(1024) k_msm_scan_b(msm_ws ws, msm_plan p) {
         uint32_t i = first + k;
         if (i >= p.TB) break;
         ws.off[i] += base.a; ws.pbase[i] += base.b; ws.mbase[i] += base.c;
-        if (msm_pieces(ws.hist[i], p.Tp) > 1) ws.multi[atomicAdd(&ws.counters[0], 1u)] = i;
+        const uint32_t pc = msm_pieces(ws.hist[i], p.Tp);
+        if (pc > MSM_SMALL_MULTI) ws.multi[atomicAdd(&ws.counters[0], 1u)] = i;
+        else if (pc > 1) ws.multi_s[atomicAdd(&ws.counters[1], 1u)] = i;
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
         ws.off[p.TB] = base.a + ws.blocktot[4 * blockIdx.x];
@@ -312,7 +316,11 @@ __global__ void __launch_bounds__(128, MSM_SUM_MINBLOCKS) k_msm_bucket_sum(msm_w
             msm_load_point(pt, points64, n, ws.gpoint, v & 0x7FFFFFFFu);
             if (v >> 31) fe_neg(pt.y, pt.y);
             gej t;
+#ifdef MSM_SUM_INLINE_ADD
+            gej_add_ge_t<true>(t, acc, pt, nullptr);      // field multiplications inlined: this loop is the whole kernel, the body fits the I-cache
+#else
             gej_add_ge(t, acc, pt);
+#endif
             acc = t;
             if (++e == eend) {
                 store_gej_vec((dst & MSM_DST_PART) ? ws.parts + (dst & ~MSM_DST_PART) : ws.buckets + dst, acc);
@@ -365,12 +373,29 @@ __global__ void __launch_bounds__(256) k_msm_combine(msm_ws ws, msm_plan p) {
     }
 }
 
+// small multi-piece buckets (2 .. MSM_SMALL_MULTI pieces): one thread each
+__global__ void __launch_bounds__(128) k_msm_combine_small(msm_ws ws, msm_plan p) {
+    const uint32_t nm = ws.counters[1];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nm; i += gridDim.x * blockDim.x) {
+        const uint32_t b = ws.multi_s[i];
+        const uint32_t K = ws.pbase[b + 1] - ws.pbase[b], base = ws.mbase[b];
+        gej acc;
+        load_gej_vec(acc, ws.parts + base);
+#pragma unroll 1
+        for (uint32_t k = 1; k < K; k++) { gej o, t; load_gej_vec(o, ws.parts + base + k); gej_add(t, acc, o); acc = t; }
+        store_gej_vec(ws.buckets + b, acc);
+    }
+}
+
 // ---- (5) running sums over chunks of 8 buckets --------------------------------------------------------------------------------
 template <bool G4>
 __global__ void __launch_bounds__(128) k_msm_r1(msm_ws ws, msm_plan p) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t q = G4 ? (t >> 2) : t;
-    if (q >= p.TB / MSM_CHUNK) return;                 // G4: whole groups leave together
+    const uint32_t nchunks = p.TB / MSM_CHUNK;
+    uint32_t q = G4 ? (t >> 2) : t;
+    const bool valid = q < nchunks;
+    if (!G4 && !valid) return;
+    if (!valid) q = nchunks - 1;                      // G4: the whole warp stays (full-mask shuffles); surplus groups redo the last chunk
     const gej_store* s8 = ws.buckets + (size_t)q * MSM_CHUNK;
     gej running, acc;
     gej_set_infinity(running);
@@ -382,29 +407,32 @@ __global__ void __launch_bounds__(128) k_msm_r1(msm_ws ws, msm_plan p) {
         if (G4) { gej_add_g4(tt, running, s); running = tt; gej_add_g4(tt, acc, running); acc = tt; }
         else { gej_add(tt, running, s); running = tt; gej_add(tt, acc, running); acc = tt; }
     }
-    if (!G4 || (threadIdx.x & 3) == 0) { store_gej_vec(ws.Lq + q, acc); store_gej_vec(ws.Aq + q, running); }
+    if (valid && (!G4 || (threadIdx.x & 3) == 0)) { store_gej_vec(ws.Lq + q, acc); store_gej_vec(ws.Aq + q, running); }
 }
 
-// ---- (6) per window: plain sum of the L's, bit sums of the A's ------------------------------------------------------------------
+// ---- (6) per window: plain sum of the L's, bit sums of the A's; <= MSM_R2_ELEMS chunk sums per block ----------------------------
 __global__ void __launch_bounds__(256) k_msm_r2(msm_ws ws, msm_plan p) {
     __shared__ gej_store scratch[8];
-    const uint32_t wi = blockIdx.x / MSM_MAX_SUMS, s = blockIdx.x % MSM_MAX_SUMS;
+    const uint32_t part = blockIdx.x % MSM_R2_PARTS, ws_i = blockIdx.x / MSM_R2_PARTS;
+    const uint32_t wi = ws_i / MSM_MAX_SUMS, s = ws_i % MSM_MAX_SUMS;
     msm_win w;
     msm_window_by_index(w, p, wi);
     const uint32_t Q = w.Bw / MSM_CHUNK, nbits = msm_ilog2(Q), cb = w.base / MSM_CHUNK;
-    if (s > nbits) return;
     const uint32_t count = (s == 0) ? Q : Q / 2;
+    const uint32_t lo = part * MSM_R2_ELEMS, hi = (lo + MSM_R2_ELEMS < count) ? lo + MSM_R2_ELEMS : count;
     gej acc;
     gej_set_infinity(acc);
+    if (s <= nbits && lo < count) {                                     // block-uniform
 #pragma unroll 1
-    for (uint32_t k = threadIdx.x; k < count; k += blockDim.x) {
-        gej o, t;
-        if (s == 0) load_gej_vec(o, ws.Lq + cb + k);
-        else load_gej_vec(o, ws.Aq + cb + msm_bit_index(k, s - 1));
-        gej_add(t, acc, o); acc = t;
+        for (uint32_t k = lo + threadIdx.x; k < hi; k += blockDim.x) {
+            gej o, t;
+            if (s == 0) load_gej_vec(o, ws.Lq + cb + k);
+            else load_gej_vec(o, ws.Aq + cb + msm_bit_index(k, s - 1));
+            gej_add(t, acc, o); acc = t;
+        }
+        block_sum_gej(acc, scratch);
     }
-    block_sum_gej(acc, scratch);
-    if (threadIdx.x == 0) store_gej_vec(ws.T + (size_t)wi * MSM_MAX_SUMS + s, acc);
+    if (threadIdx.x == 0) store_gej_vec(ws.T + (size_t)blockIdx.x, acc);   // unused slots hold infinity
 }
 
 // ---- (7) tail: window sums, Horner, join, output ------------------------------------------------------------------------------
@@ -418,26 +446,29 @@ __device__ void write_result(uint8_t* out, const gej& r, int mode) {
 __global__ void __launch_bounds__(256) k_msm_tail(uint8_t* out, int mode, msm_ws ws, msm_plan p) {
     __shared__ gej W[2 * 32];
     __shared__ gej H[2];
-    const uint32_t g = threadIdx.x >> 2, l = threadIdx.x & 3;
-    for (uint32_t wi = g; wi < 2 * p.nw; wi += blockDim.x >> 2) {
+    const uint32_t g = threadIdx.x >> 2, l = threadIdx.x & 3, ngroups = blockDim.x >> 2;
+    const uint32_t maxbits = msm_ilog2((p.B > p.Btop ? p.B : p.Btop) / MSM_CHUNK);
+    for (uint32_t base = 0; base < 2 * p.nw; base += ngroups) {        // every warp runs every round (4-lane operations need whole warps)
+        const uint32_t wi = base + g;
+        const bool valid = wi < 2 * p.nw;
+        const uint32_t wic = valid ? wi : 0;
         msm_win w;
-        msm_window_by_index(w, p, wi);
+        msm_window_by_index(w, p, wic);
         gej r;
-        msm_window_from_sums(r, ws.T + (size_t)wi * MSM_MAX_SUMS, msm_ilog2(w.Bw / MSM_CHUNK));
-        if (l == 0) W[wi] = r;
+        msm_window_from_sums(r, ws.T + (size_t)wic * MSM_MAX_SUMS * MSM_R2_PARTS, msm_ilog2(w.Bw / MSM_CHUNK), maxbits);
+        if (valid && l == 0) W[wi] = r;
     }
     __syncthreads();
-    if (g < 2) {
+    if (threadIdx.x >= 32) return;                                      // the rest is one warp's work
+    {
         gej r;
-        msm_horner_half(r, W + g * p.nw, p);
-        if (l == 0) H[g] = r;
+        msm_horner_half(r, W + (g & 1) * p.nw, p);                     // groups 0 / 1 own the halves, the other six recompute them
+        if (g < 2 && l == 0) H[g] = r;
     }
-    __syncthreads();
-    if (g == 0) {
-        gej r;
-        msm_join_halves(r, H[0], H[1]);
-        if (l == 0) write_result(out, r, mode);
-    }
+    __syncwarp();
+    gej r, a = H[0], b = H[1];
+    msm_join_halves(r, a, b);
+    if (threadIdx.x == 0) write_result(out, r, mode);
 }
 
 // sum of `count` stored Jacobian points (the per-GPU partial results of a sharded MSM) -> affine x||y big-endian
@@ -446,22 +477,26 @@ __global__ void __launch_bounds__(128) k_gej_sum(uint8_t* out64, const uint8_t* 
     const uint32_t g = threadIdx.x >> 2, l = threadIdx.x & 3, ng = blockDim.x >> 2;
     gej acc;
     gej_set_infinity(acc);
-    for (uint32_t k = g; k < count; k += ng) {
+    for (uint32_t k0 = 0; k0 < count; k0 += ng) {                       // uniform trip count; surplus groups add infinity
+        const uint32_t k = k0 + g;
         gej o, t;
-        gej_store s;
-        const uint32_t* q = reinterpret_cast<const uint32_t*>(partials96 + (size_t)96 * k);
-        for (int j = 0; j < 24; j++) s.w[j] = q[j];
-        msm_load_gej(o, s);
+        gej_set_infinity(o);
+        if (k < count) {
+            gej_store s;
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(partials96 + (size_t)96 * k);
+            for (int j = 0; j < 24; j++) s.w[j] = q[j];
+            msm_load_gej(o, s);
+        }
         gej_add_g4(t, acc, o); acc = t;
     }
     if (l == 0) S[g] = acc;
     __syncthreads();
     for (uint32_t d = ng >> 1; d >= 1; d >>= 1) {
-        if (g < d) {
-            gej a = S[g], b = S[g + d], t;
-            gej_add_g4(t, a, b);
-            if (l == 0) S[g] = t;
-        }
+        gej a = S[g], b, t;
+        if (g < d) b = S[g + d]; else gej_set_infinity(b);
+        gej_add_g4(t, a, b);
+        __syncthreads();
+        if (g < d && l == 0) S[g] = t;
         __syncthreads();
     }
     if (threadIdx.x == 0) write_result(out64, S[0], 0);
@@ -505,19 +540,22 @@ cudaError_t launch_msm(uint8_t* out, int out_mode, const uint8_t* g_scalar32, co
     k_msm_bucket_sum<<<(unsigned)sum_blocks, 128, 0, s>>>(ws, p, points64, n);
     size_t comb_blocks = caps.cap_multi < 1184 ? caps.cap_multi : 1184;
     k_msm_combine<<<(unsigned)comb_blocks, 256, 0, s>>>(ws, p);
+    size_t combs_blocks = (caps.cap_multi + 127) / 128;
+    if (combs_blocks > 2368) combs_blocks = 2368;
+    k_msm_combine_small<<<(unsigned)combs_blocks, 128, 0, s>>>(ws, p);
     const size_t chunks = p.TB / MSM_CHUNK;
     if (chunks <= 40960) k_msm_r1<true><<<(unsigned)((chunks * 4 + 127) / 128), 128, 0, s>>>(ws, p);
     else k_msm_r1<false><<<(unsigned)((chunks + 127) / 128), 128, 0, s>>>(ws, p);
-    k_msm_r2<<<2 * p.nw * MSM_MAX_SUMS, 256, 0, s>>>(ws, p);
+    k_msm_r2<<<2 * p.nw * MSM_MAX_SUMS * MSM_R2_PARTS, 256, 0, s>>>(ws, p);
     k_msm_tail<<<1, 256, 0, s>>>(out, out_mode, ws, p);
-    if (launches) *launches += 10;
+    if (launches) __atomic_fetch_add(launches, (uint64_t)11, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }
 
 cudaError_t launch_gej_sum(uint8_t* out64, const uint8_t* partials96, size_t count, cudaStream_t s, uint64_t* launches) {
     if (count >= ((size_t)1 << 31)) return cudaErrorInvalidValue;
     k_gej_sum<<<1, 128, 0, s>>>(out64, partials96, (uint32_t)count);
-    if (launches) *launches += 1;
+    if (launches) __atomic_fetch_add(launches, (uint64_t)1, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }
 

@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(RP_WARPS * 32, RP_MINBLOCKS) k_rangeproof_veri
     const uint8_t* g64 = gen64 + gen_stride * item;
     const uint8_t* ex = extra ? extra + extra_stride * item : nullptr;
     const size_t exl = (extra && extra_len) ? extra_len[item] : 0;
+    // the _dev entry points take lengths from device memory: a length beyond its stride would read the neighbour's record
+    if (pl > stride || (ex && exl > extra_stride)) { if (lane == 0) { ok[item] = 0; minv[item] = 0; maxv[item] = 0; } return; }
 
     rp_header h;
     uint64_t mn = 0, mx = 0;
@@ -144,7 +146,7 @@ cudaError_t launch_rangeproof_verify(uint8_t* ok, uint64_t* minv, uint64_t* maxv
     if (err != cudaSuccess) return err;
     k_rangeproof_verify<<<(unsigned)((n + RP_WARPS - 1) / RP_WARPS), RP_WARPS * 32, smem, s>>>(ok, minv, maxv, commit33, proofs, stride, plen,
                                                                                             gen64, gen_stride, extra, extra_stride, extra_len, n, to_gt(gt), ev_out);
-    if (launches) *launches += 1;
+    if (launches) __atomic_fetch_add(launches, (uint64_t)1, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }
 cudaError_t launch_rangeproof_rewind(uint8_t* ok, uint8_t* blind32, uint64_t* value, uint8_t* msg, size_t msg_stride, uint32_t* msg_len,
@@ -154,14 +156,14 @@ cudaError_t launch_rangeproof_rewind(uint8_t* ok, uint8_t* blind32, uint64_t* va
     if (n == 0) return cudaSuccess;
     k_rangeproof_rewind<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(ok, blind32, value, msg, msg_stride, msg_len, nonce32, commit33, proofs, stride, plen,
                                                                  gen64, gen_stride, ev, scratch, n, to_gt(gt));
-    if (launches) *launches += 1;
+    if (launches) __atomic_fetch_add(launches, (uint64_t)1, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }
 cudaError_t launch_pedersen_commit(uint8_t* ok, uint8_t* out33, const uint8_t* blind32, const uint64_t* value, const uint8_t* gen64, size_t gen_stride,
                                    size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches) {
     if (n == 0) return cudaSuccess;
     k_pedersen_commit<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(ok, out33, blind32, value, gen64, gen_stride, n, to_gt(gt));
-    if (launches) *launches += 1;
+    if (launches) __atomic_fetch_add(launches, (uint64_t)1, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }
 

@@ -24,7 +24,7 @@ cudaError_t launch_schnorr_sign(uint8_t* sig64, uint8_t* pk32, uint8_t* ok, cons
     for (int i = 0; i < 32; i++) cc.zero_mask[i] = c.zero_mask[i];
     ecmult_gtable g; g.data = gt.data; g.gw = gt.gw; g.windows = gt.windows;
     k_schnorr_sign<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(sig64, pk32, ok, sk32, msg, msglen, n, cc, g);
-    if (launches) *launches += 1;
+    if (launches) __atomic_fetch_add(launches, (uint64_t)1, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }
 

@@ -29,8 +29,9 @@ __device__ void unit_store_gej(uint8_t* out64, const gej& r) {
 __global__ void __launch_bounds__(128) k_unit_op(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool g4 = op >= 24;
-    const size_t i = g4 ? (t >> 2) : t;
-    if (i >= n) return;                       // g4: whole groups leave together
+    size_t i = g4 ? (t >> 2) : t;
+    const bool valid = i < n;
+    if (!valid) { if (!g4) return; i = n - 1; }   // 4-lane forms need whole warps: surplus groups redo the last item and store nothing
     if (op < 8) {
         sc x, y, r;
         sc_set_b32(x, a + 32 * i);
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(128) k_unit_op(int op, uint8_t* __restrict__ o
     case 25: gej_add_g4(R, A, B); break;
     default: gej_add_ge_g4(R, A, Ba); break;
     }
-    if (!g4 || (threadIdx.x & 3) == 0) unit_store_gej(out + 64 * i, R);
+    if (valid && (!g4 || (threadIdx.x & 3) == 0)) unit_store_gej(out + 64 * i, R);
 }
 
 cudaError_t launch_unit_op(int op, uint8_t* out, const uint8_t* a, const uint8_t* b, size_t n, cudaStream_t s, uint64_t* launches) {
@@ -71,7 +72,7 @@ cudaError_t launch_unit_op(int op, uint8_t* out, const uint8_t* a, const uint8_t
     if (!ok) return cudaErrorInvalidValue;
     size_t threads = op >= 24 ? 4 * n : n;
     k_unit_op<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(op, out, a, b, n);
-    if (launches) *launches += 1;
+    if (launches) __atomic_fetch_add(launches, (uint64_t)1, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }
 

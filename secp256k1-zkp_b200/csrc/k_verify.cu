@@ -114,6 +114,9 @@ __global__ void __launch_bounds__(VERIFY_BLOCK, B200_VERIFY_MINBLOCKS) k_ecmult(
         ecmult(R, aj, na, ng, gt, tab);
     }
     fe zz, zinv;
+    // a64 is taken as given (like the reference's static secp256k1_ecmult); an off-curve input can reach Z = 0 with inf = 0.  Such a result
+    // is reported as infinity and must not enter the inversion this block shares (a zero factor would zero every other item's 1/z).
+    if (!R.inf && fe_is_zero(R.z)) gej_set_infinity(R);
     if (!R.inf) zz = R.z; else fe_set_int(zz, 1);
     fe_block_inverse(zinv, zz, reinterpret_cast<fe*>(smem));
     if (i >= n) return;
@@ -146,6 +149,7 @@ __global__ void __launch_bounds__(VERIFY_BLOCK, B200_VERIFY_MINBLOCKS) k_schnorr
         // messages of arbitrary (batch-uniform) length are hashed straight from global memory
         live = schnorr_verify_prepare(R, rx, in, msg + (size_t)msglen * i, msglen, in + 64, pkfmt, mid, gt, tab);
     }
+    if (live && fe_is_zero(R.z)) live = 0;                    // defence in depth: never feed a zero into the shared inversion
     if (live) z = R.z; else fe_set_int(z, 1);
     fe_block_inverse(zinv, z, reinterpret_cast<fe*>(smem));   // all threads of the block take part
     if (i < n) ok[i] = (uint8_t)(live && schnorr_verify_finish(R, rx, zinv));
@@ -193,6 +197,7 @@ __global__ void __launch_bounds__(VERIFY_BLOCK, B200_VERIFY_MINBLOCKS) k_ecdsa_r
     gej Q; gej_set_infinity(Q);
     if (live) live = ecdsa_recover_finish(Q, st, rn, gt, tab);
     fe z, zinv;
+    if (live && fe_is_zero(Q.z)) live = 0;
     if (live) z = Q.z; else fe_set_int(z, 1);
     fe_block_inverse(zinv, z, reinterpret_cast<fe*>(smem));   // one field inversion per block
     if (i >= n) return;
@@ -222,7 +227,7 @@ cudaError_t launch_ecmult(uint8_t* out64, const uint8_t* a64, const uint8_t* na3
     cudaError_t err = set_smem(k_ecmult);
     if (err != cudaSuccess) return err;
     k_ecmult<<<(unsigned)((n + VERIFY_BLOCK - 1) / VERIFY_BLOCK), VERIFY_BLOCK, VERIFY_SMEM, s>>>(out64, a64, na32, ng32, n, to_gt(gt));
-    if (launches) *launches += 1;
+    if (launches) __atomic_fetch_add(launches, (uint64_t)1, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }
 cudaError_t launch_schnorr_verify(uint8_t* ok, const uint8_t* sig64, const uint8_t* msg, uint32_t msglen, const uint8_t* pk, int pkfmt,
@@ -233,7 +238,7 @@ cudaError_t launch_schnorr_verify(uint8_t* ok, const uint8_t* sig64, const uint8
     bip340_midstate m;
     for (int i = 0; i < 8; i++) m.s[i] = mid.s[i];
     k_schnorr_verify<<<(unsigned)((n + VERIFY_BLOCK - 1) / VERIFY_BLOCK), VERIFY_BLOCK, VERIFY_SMEM, s>>>(ok, sig64, msg, msglen, pk, pkfmt, n, m, to_gt(gt));
-    if (launches) *launches += 1;
+    if (launches) __atomic_fetch_add(launches, (uint64_t)1, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }
 cudaError_t launch_ecdsa_verify(uint8_t* ok, const uint8_t* sig64, int sigfmt, const uint8_t* msg32, const uint8_t* pk, int pkfmt,
@@ -242,7 +247,7 @@ cudaError_t launch_ecdsa_verify(uint8_t* ok, const uint8_t* sig64, int sigfmt, c
     cudaError_t err = set_smem(k_ecdsa_verify);
     if (err != cudaSuccess) return err;
     k_ecdsa_verify<<<(unsigned)((n + VERIFY_BLOCK - 1) / VERIFY_BLOCK), VERIFY_BLOCK, VERIFY_SMEM, s>>>(ok, sig64, sigfmt, msg32, pk, pkfmt, n, to_gt(gt));
-    if (launches) *launches += 1;
+    if (launches) __atomic_fetch_add(launches, (uint64_t)1, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }
 
@@ -252,7 +257,7 @@ cudaError_t launch_ecdsa_recover(uint8_t* ok, uint8_t* out64, const uint8_t* sig
     cudaError_t err = set_smem(k_ecdsa_recover);
     if (err != cudaSuccess) return err;
     k_ecdsa_recover<<<(unsigned)((n + VERIFY_BLOCK - 1) / VERIFY_BLOCK), VERIFY_BLOCK, VERIFY_SMEM, s>>>(ok, out64, sig64, recid, msg32, n, to_gt(gt));
-    if (launches) *launches += 1;
+    if (launches) __atomic_fetch_add(launches, (uint64_t)1, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }
 

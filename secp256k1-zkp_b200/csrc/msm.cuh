@@ -30,7 +30,11 @@
 namespace B200_NS {
 
 #define MSM_CHUNK 8                  // buckets per running-sum chunk
-#define MSM_PIECE_MIN 64             // smallest piece size
+#define MSM_PIECE_MIN 16             // smallest piece size
+#define MSM_PIECE_MAX 4096
+#define MSM_SMALL_MULTI 8            // multi-piece buckets with at most this many pieces are combined by one thread, larger ones by a block
+#define MSM_R2_ELEMS 2048            // chunk sums per block of the plain / bit sums
+#define MSM_R2_PARTS 4               // => at most 4 blocks per sum (the largest window has 8192 chunks)
 #define MSM_C_MIN 4
 #define MSM_C_MAX 16
 #define MSM_MAX_SUMS 15              // per window: 1 plain sum (L) + up to 14 bit sums
@@ -58,25 +62,22 @@ HD void msm_make_plan_c(msm_plan& p, size_t N, uint32_t c) {
     p.HB = (p.nw - 1) * p.B + p.Btop;
     p.TB = 2 * p.HB;
     p.N = (uint32_t)N;
-    uint64_t mean4 = (uint64_t)4 * 2 * p.nw * N / p.TB;           // 4 x the mean bucket load
+    // piece size: small enough that the pieces outnumber the GPU's lanes several times over (~2^19 pieces when there is that much
+    // work) and that no lane walks a long bucket alone -- the top window of a half holds only ~0.6 * 2^t distinct digits, so its
+    // buckets are several times fuller than the others -- but not smaller than 16 entries (every extra piece costs a Jacobian addition).
+    uint64_t e = ((uint64_t)2 * p.nw * N) >> 19;
     uint32_t tp = MSM_PIECE_MIN;
-    while (tp < mean4 && tp < (1u << 20)) tp <<= 1;
+    while (tp * 2 <= e && tp < MSM_PIECE_MAX) tp <<= 1;
     p.Tp = tp;
 }
-// window width from the number of terms: minimises (bucket additions) + (bucket-reduction work), the trade that
-// secp256k1_pippenger_bucket_window's table encodes for the CPU (ecmult_impl.h:597-621); below ~2^11 terms the MSM is latency
-// bound (a ~128-doubling chain whatever c is) and c = 8 keeps the bucket count small.
+// Window width from the number of terms -- the counterpart of secp256k1_pippenger_bucket_window's table (ecmult_impl.h:597-621).
+// On the GPU wide windows win much earlier than on a CPU: more buckets = more parallel lanes, and the bucket reduction is parallel
+// too.  Measured (tools/msm_bench.py --sweep, profiles/r2*_msm_sweep.jsonl); below 2^12 terms the MSM is latency bound (a ~128-doubling
+// chain whatever c is) and a narrow window keeps the reduction short.
 HD uint32_t msm_choose_c(size_t N) {
-    if (N <= 2048) return 8;
-    uint32_t best = 8;
-    uint64_t bestcost = ~(uint64_t)0;
-    for (uint32_t c = 8; c <= MSM_C_MAX; c++) {
-        msm_plan p;
-        msm_make_plan_c(p, N, c);
-        uint64_t cost = (uint64_t)2 * p.nw * N + (uint64_t)4 * p.TB;
-        if (cost < bestcost) { bestcost = cost; best = c; }
-    }
-    return best;
+    if (N < ((size_t)1 << 12)) return 8;
+    if (N < ((size_t)1 << 16)) return 13;
+    return 16;
 }
 
 // bits [pos, pos + nb) of a 128-bit magnitude (nb <= 16, pos + nb <= 128)
@@ -218,26 +219,28 @@ HD void msm_chunk_r1(gej& L, gej& A, const gej_store* s8) {
 // element k of bit-sum j over Q chunk sums: the k-th index q in [0, Q) whose bit j is set
 HD uint32_t msm_bit_index(uint32_t k, uint32_t j) { return ((k >> j) << (j + 1)) | (1u << j) | (k & ((1u << j) - 1u)); }
 
-// The three functions below run on a GROUP OF 4 LANES on the device (ge_g4.cuh: all four lanes call with identical arguments);
-// compiled for the host they are plain single-thread code.
+// The three functions below run on GROUPS OF 4 LANES on the device (ge_g4.cuh: a whole warp calls together, every group with its own
+// arguments, all loops with warp-uniform trip counts); compiled for the host they are plain single-thread code.
 // window sum from its plain sum T[0] = sum_q L_q and bit sums T[1 + j] = sum_{q: bit j} A_q:
 //   W = T[0] + 8 * sum_j 2^j T[1 + j]
-HD void msm_window_from_sums(gej& W, const gej_store* T, uint32_t nbits) {
+HD void msm_window_from_sums(gej& W, const gej_store* T /* [1 + bits][MSM_R2_PARTS] */, uint32_t nbits, uint32_t maxbits) {
     gej acc;
     gej_set_infinity(acc);
 #pragma unroll 1
-    for (int j = (int)nbits - 1; j >= 0; j--) {
-        gej s, t;
-        if (!acc.inf) { gej_double_g4(t, acc); acc = t; }
-        msm_load_gej(s, T[1 + j]);
-        gej_add_g4(t, acc, s); acc = t;
-    }
+    for (int j = (int)maxbits - 1; j >= -1; j--) {                // j = -1: the plain sum, after the multiplication by 8
+        const int slot = j + 1;
+        if (j == -1) {
 #pragma unroll 1
-    for (int k = 0; k < 3; k++) if (!acc.inf) { gej t; gej_double_g4(t, acc); acc = t; }
-    gej s, t;
-    msm_load_gej(s, T[0]);
-    gej_add_g4(t, acc, s);
-    W = t;
+            for (int k = 0; k < 3; k++) { gej t; gej_double_g4(t, acc); acc = t; }
+        } else { gej t; gej_double_g4(t, acc); acc = t; }
+#pragma unroll 1
+        for (int part = 0; part < MSM_R2_PARTS; part++) {
+            gej s, t;
+            if (slot <= (int)nbits) msm_load_gej(s, T[slot * MSM_R2_PARTS + part]); else gej_set_infinity(s);
+            gej_add_g4(t, acc, s); acc = t;
+        }
+    }
+    W = acc;
 }
 
 // Horner over the nw windows of one half: sum_w 2^(c w) W[w]
@@ -246,10 +249,8 @@ HD void msm_horner_half(gej& out, const gej* W, const msm_plan& p) {
     gej_set_infinity(acc);
 #pragma unroll 1
     for (int w = (int)p.nw - 1; w >= 0; w--) {
-        if (!acc.inf) {
 #pragma unroll 1
-            for (uint32_t k = 0; k < p.c; k++) { gej t; gej_double_g4(t, acc); acc = t; }
-        }
+        for (uint32_t k = 0; k < p.c; k++) { gej t; gej_double_g4(t, acc); acc = t; }      // doubling infinity is free of branches
         gej t, ww = W[w];
         gej_add_g4(t, acc, ww); acc = t;
     }

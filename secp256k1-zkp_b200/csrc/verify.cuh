@@ -41,8 +41,10 @@ HD void sc_from_le32(sc& r, const uint8_t* b) {
 HD int pubkey_load(ge& p, const uint8_t* pk, int fmt) {
     if (fmt == PK_OPAQUE64) {
         ge_from_opaque64(p, pk);
-        // secp256k1_pubkey_load ARG_CHECKs x != 0 (secp256k1.c:282): an all-zero (unparsed) key is invalid
-        return !fe_is_zero(p.x);
+        // secp256k1_pubkey_load ARG_CHECKs x != 0 (secp256k1.c:282): an all-zero (unparsed) key is invalid.  The reference trusts the
+        // rest of the object (it can only come from its own parser); a batch API cannot: an off-curve point such as (x, 0) would double
+        // to Z = 0 and poison the inversion its thread block shares.  Off-curve opaque keys are therefore rejected (3 field operations).
+        return !fe_is_zero(p.x) && ge_is_valid(p);
     } else if (fmt == PK_XONLY32) {
         fe x;
         if (!fe_set_b32(x, pk)) return 0;

@@ -186,7 +186,8 @@ int emu_msm2(uint8_t* out64, const uint8_t* g_sc32, const uint8_t* scalars32, co
         msm_emit_digits(p, &k12[8 * i], f & 1u, 0, em);
         msm_emit_digits(p, &k12[8 * i + 4], (f >> 1) & 1u, 1, em);
     }
-    std::vector<gej_store> buckets(p.TB), parts(rm + 1), Lq(p.TB / MSM_CHUNK), Aq(p.TB / MSM_CHUNK), T((size_t)2 * p.nw * MSM_MAX_SUMS);
+    std::vector<gej_store> buckets(p.TB), parts(rm + 1), Lq(p.TB / MSM_CHUNK), Aq(p.TB / MSM_CHUNK), T((size_t)2 * p.nw * MSM_MAX_SUMS * MSM_R2_PARTS);
+    memset(T.data(), 0, T.size() * sizeof(gej_store));
     memset(buckets.data(), 0, buckets.size() * sizeof(gej_store));
     for (uint32_t u = 0; u < rp; u++) {                                   // k_msm_units + k_msm_bucket_sum
         uint32_t lo = 0, hi = p.TB;
@@ -207,13 +208,14 @@ int emu_msm2(uint8_t* out64, const uint8_t* g_sc32, const uint8_t* scalars32, co
     for (uint32_t wi = 0; wi < 2 * p.nw; wi++) {                          // k_msm_r2 + first phase of k_msm_tail
         msm_win w; msm_window_by_index(w, p, wi);
         uint32_t Q = w.Bw / MSM_CHUNK, nbits = msm_ilog2(Q), cb = w.base / MSM_CHUNK;
-        for (uint32_t s = 0; s <= nbits; s++) {
+        for (uint32_t s = 0; s <= nbits; s++) for (uint32_t part = 0; part < MSM_R2_PARTS; part++) {
             gej acc; gej_set_infinity(acc);
-            uint32_t count = s == 0 ? Q : Q / 2;
-            for (uint32_t k = 0; k < count; k++) { gej o, t; msm_load_gej(o, s == 0 ? Lq[cb + k] : Aq[cb + msm_bit_index(k, s - 1)]); gej_add(t, acc, o); acc = t; }
-            msm_store_gej(T[(size_t)wi * MSM_MAX_SUMS + s], acc);
+            uint32_t count = s == 0 ? Q : Q / 2, lo = part * MSM_R2_ELEMS, hi = lo + MSM_R2_ELEMS < count ? lo + MSM_R2_ELEMS : count;
+            for (uint32_t k = lo; k < hi; k++) { gej o, t; msm_load_gej(o, s == 0 ? Lq[cb + k] : Aq[cb + msm_bit_index(k, s - 1)]); gej_add(t, acc, o); acc = t; }
+            msm_store_gej(T[((size_t)wi * MSM_MAX_SUMS + s) * MSM_R2_PARTS + part], acc);
         }
-        msm_window_from_sums(W[wi], T.data() + (size_t)wi * MSM_MAX_SUMS, nbits);
+        uint32_t maxbits = msm_ilog2((p.B > p.Btop ? p.B : p.Btop) / MSM_CHUNK);
+        msm_window_from_sums(W[wi], T.data() + (size_t)wi * MSM_MAX_SUMS * MSM_R2_PARTS, nbits, maxbits);
     }
     gej H[2], r;
     msm_horner_half(H[0], W.data(), p);

@@ -263,3 +263,33 @@ def test_msm_adversarial_skew_time_and_value(engine, ref):
     assert got == exp
     print("MSM 2^20: random %.3f ms, identical scalars %.3f ms" % (t_rand, t_same))
     assert t_same <= 2.0 * t_rand, (t_rand, t_same)
+
+
+# ---- cross-item isolation of the block-shared inversions (a crafted off-curve key must not touch its neighbours) -----------
+def test_offcurve_key_does_not_poison_its_block(engine, ref):
+    import secp256k1_zkp_b200 as b200
+    n = 512
+    sk = b"".join(hashlib.sha256(b"iso-sk%d" % i).digest() for i in range(n))
+    msg = b"".join(hashlib.sha256(b"iso-msg%d" % i).digest() for i in range(n))
+    sig, pk = ref.schnorr_make(sk, msg)
+    okc, opaque = engine.point_codec(pk, 32, 1)                      # x-only -> 64-byte opaque secp256k1_xonly_pubkey (x, y little-endian)
+    assert okc.all()
+    opaque = opaque.copy(); sig = sig.copy()
+    for j in (5, 130, 131, 300):                                     # (x, 0): not on the curve; doubling it gives Z = 0
+        opaque[j, 32:] = 0
+        sig[64 * j:64 * j + 32] = 0                                  # r = 0: what a zeroed shared inverse would have made "valid"
+    got = engine.schnorrsig_verify(sig, msg, opaque, b200.PK_OPAQUE64)
+    exp = np.ones(n, dtype=np.uint8); exp[[5, 130, 131, 300]] = 0
+    assert np.array_equal(got, exp)
+    # raw ecmult (points taken as given): the off-curve items report infinity, every other item is untouched
+    ks = [int.from_bytes(hashlib.sha256(b"iso-k%d" % i).digest(), "big") % N for i in range(n)]
+    pts = _points(ref, ks).copy()
+    na = b"".join(b32(k) for k in ks)
+    clean = engine.ecmult(pts, na, na)
+    assert np.array_equal(clean, np.frombuffer(ref.ecmult_batch(pts.tobytes(), na, na).tobytes(), dtype=np.uint8).reshape(n, 64))
+    bad = pts.copy()
+    for j in (7, 129, 400):
+        bad[j, 32:] = 0
+    out = engine.ecmult(bad, na, na)
+    mask = np.ones(n, dtype=bool); mask[[7, 129, 400]] = False
+    assert np.array_equal(out[mask], clean[mask])

@@ -253,7 +253,8 @@ LAMBDA = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
 
 
 def test_msm_pipeline_logic(emu, ref):
-    """the GPU MSM pipeline (k_msm.cu) executed sequentially on the host: every window width, forced small pieces (multi-piece buckets +
+    """(also covers MSM_R2_PARTS > 1: c = 16 has 8192 chunk sums in the top window)
+    the GPU MSM pipeline (k_msm.cu) executed sequentially on the host: every window width, forced small pieces (multi-piece buckets +
     combine), hot buckets, edge scalars incl. the GLV split bounds -- against the reference's ecmult_multi_var"""
     rnd = random.Random(5)
     emu.emu_msm2.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32]
@@ -269,7 +270,7 @@ def test_msm_pipeline_logic(emu, ref):
             assert ok == 1 and out.raw == exp, (m, c, tp, g is None)
     # the dispatcher: window width grows with n, c = 8 below 2^11 terms, 16 at 2^20
     cs = [emu.emu_msm_choose_c(ctypes.c_size_t(n)) for n in (1, 88, 2048, 1 << 13, 1 << 15, 1 << 17, 1 << 20, 1 << 24)]
-    assert cs[0] == 8 and cs[1] == 8 and cs == sorted(cs) and cs[5] == 13 and cs[6] == 16 and cs[7] == 16, cs
+    assert cs[0] == 8 and cs[1] == 8 and cs == sorted(cs) and cs[3] == 13 and cs[6] == 16 and cs[7] == 16, cs
 
 
 def test_bppp_norm_verify_logic(emu, ref):
