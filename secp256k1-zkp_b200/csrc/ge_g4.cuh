@@ -20,6 +20,15 @@ namespace B200_NS {
 
 #if defined(__CUDA_ARCH__)
 #define G4_FULL 0xffffffffu
+// -DB200_G4_INLINE: the operations (and the field multiplications inside them) are inlined at their call sites -- for kernels that are
+// nothing but a latency-bound chain (k_msm_tail, k_msm_r1<true>): no argument copies through local memory, no call overhead.
+#ifdef B200_G4_INLINE
+#define G4_FN static __device__ __forceinline__
+#define G4_MUL(o, p, q) fe_mul_inl(o, p, q)
+#else
+#define G4_FN static __device__ __noinline__
+#define G4_MUL(o, p, q) fe_mul(o, p, q)
+#endif
 __device__ __forceinline__ fe g4_bcast(const fe& a, int src) {
     fe r;
     const int lane = (int)((threadIdx.x & 31u) & ~3u) + src;
@@ -44,26 +53,26 @@ __device__ __forceinline__ void g4_gej_select(gej& r, const gej& a, bool take) {
 }
 
 // r = 2a.  Branch free: an infinite input just carries its flag through (the arithmetic runs on whatever the coordinates hold).
-static __device__ __noinline__ void gej_double_g4(gej& r, const gej& a) {
+G4_FN void gej_double_g4(gej& r, const gej& a) {
     const int l = (int)(threadIdx.x & 3u);
     fe p, q, o;
     // step 1: Y*Z | Y*Y | X*X
     p = g4_sel(l, a.y, a.y, a.x, a.x);
     q = g4_sel(l, a.z, a.y, a.x, a.x);
-    fe_mul(o, p, q);
+    G4_MUL(o, p, q);
     fe u = g4_bcast(o, 0), s = g4_bcast(o, 1), lq = g4_bcast(o, 2);
     fe_mul_small(lq, lq, 3);
     fe_half(lq, lq);                                  // L = 3/2 X^2
     // step 2: X*s | s*s | L*L
     p = g4_sel(l, a.x, s, lq, lq);
     q = g4_sel(l, s, s, lq, lq);
-    fe_mul(o, p, q);
+    G4_MUL(o, p, q);
     fe t = g4_bcast(o, 0), ss = g4_bcast(o, 1), x3 = g4_bcast(o, 2);
     fe_sub(x3, x3, t);
     fe_sub(x3, x3, t);
     fe_sub(t, t, x3);
     // step 3 (every lane, no exchange): (t - x3) * L
-    fe_mul(o, t, lq);
+    G4_MUL(o, t, lq);
     const int inf = a.inf;
     fe_sub(r.y, o, ss);
     r.x = x3;
@@ -77,12 +86,12 @@ __device__ __forceinline__ void g4_add_finish(gej& g, int l, const fe& h, const 
     // step 4: h^2 | rr^2 | zz*h
     p = g4_sel(l, h, rr, zz, zz);
     q = g4_sel(l, h, rr, h, h);
-    fe_mul(o, p, q);
+    G4_MUL(o, p, q);
     fe hh = g4_bcast(o, 0), x3 = g4_bcast(o, 1), z3 = g4_bcast(o, 2);
     // step 5: hh*h | u1*hh
     p = g4_sel2(l, hh, u1);
     q = g4_sel2(l, h, hh);
-    fe_mul(o, p, q);
+    G4_MUL(o, p, q);
     fe hhh = g4_bcast(o, 0), v = g4_bcast(o, 1);
     fe_sub(x3, x3, hhh);
     fe_sub(x3, x3, v);
@@ -91,7 +100,7 @@ __device__ __forceinline__ void g4_add_finish(gej& g, int l, const fe& h, const 
     // step 6: (v - x3)*rr | hhh*s1
     p = g4_sel2(l, v, hhh);
     q = g4_sel2(l, rr, s1);
-    fe_mul(o, p, q);
+    G4_MUL(o, p, q);
     fe m = g4_bcast(o, 0), w = g4_bcast(o, 1);
     fe_sub(g.y, m, w);
     g.x = x3;
@@ -99,7 +108,7 @@ __device__ __forceinline__ void g4_add_finish(gej& g, int l, const fe& h, const 
     g.inf = 0;
 }
 
-static __device__ __noinline__ void gej_add_g4(gej& r, const gej& a, const gej& b) {
+G4_FN void gej_add_g4(gej& r, const gej& a, const gej& b) {
     const bool triv = a.inf || b.inf;
     if (__all_sync(G4_FULL, triv)) { gej t = a.inf ? b : a; r = t; return; }      // warp-uniform shortcut (sparse buckets)
     const int l = (int)(threadIdx.x & 3u);
@@ -107,17 +116,17 @@ static __device__ __noinline__ void gej_add_g4(gej& r, const gej& a, const gej& 
     // step 1: z1^2 | z2^2 | z1*z2
     p = g4_sel(l, a.z, b.z, a.z, a.z);
     q = g4_sel(l, a.z, b.z, b.z, b.z);
-    fe_mul(o, p, q);
+    G4_MUL(o, p, q);
     fe z12 = g4_bcast(o, 0), z22 = g4_bcast(o, 1), zz = g4_bcast(o, 2);
     // step 2: x1*z2^2 | x2*z1^2 | y1*z2 | y2*z1
     p = g4_sel(l, a.x, b.x, a.y, b.y);
     q = g4_sel(l, z22, z12, b.z, a.z);
-    fe_mul(o, p, q);
+    G4_MUL(o, p, q);
     fe u1 = g4_bcast(o, 0), u2 = g4_bcast(o, 1), t1 = g4_bcast(o, 2), t2 = g4_bcast(o, 3);
     // step 3: t1*z2^2 | t2*z1^2
     p = g4_sel2(l, t1, t2);
     q = g4_sel2(l, z22, z12);
-    fe_mul(o, p, q);
+    G4_MUL(o, p, q);
     fe s1 = g4_bcast(o, 0), s2 = g4_bcast(o, 1);
     fe h, rr;
     fe_sub(h, u2, u1);
@@ -137,18 +146,18 @@ static __device__ __noinline__ void gej_add_g4(gej& r, const gej& a, const gej& 
 }
 
 // r = a + b, b affine
-static __device__ __noinline__ void gej_add_ge_g4(gej& r, const gej& a, const ge& b) {
+G4_FN void gej_add_ge_g4(gej& r, const gej& a, const ge& b) {
     const bool triv = a.inf || b.inf;
     if (__all_sync(G4_FULL, triv)) { gej t; if (a.inf) gej_set_ge(t, b); else t = a; r = t; return; }
     const int l = (int)(threadIdx.x & 3u);
     fe p, q, o, z12;
-    fe_mul(z12, a.z, a.z);                                      // step 1 (every lane)
+    G4_MUL(z12, a.z, a.z);                                      // step 1 (every lane)
     // step 2: x2*z1^2 | y2*z1
     p = g4_sel2(l, b.x, b.y);
     q = g4_sel2(l, z12, a.z);
-    fe_mul(o, p, q);
+    G4_MUL(o, p, q);
     fe u2 = g4_bcast(o, 0), t2 = g4_bcast(o, 1), s2;
-    fe_mul(s2, t2, z12);                                        // step 3 (every lane)
+    G4_MUL(s2, t2, z12);                                        // step 3 (every lane)
     fe h, rr;
     fe_sub(h, u2, a.x);
     fe_sub(rr, s2, a.y);

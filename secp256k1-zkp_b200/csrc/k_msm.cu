@@ -11,6 +11,9 @@
 //   k_msm_r1          running sums over chunks of 8 buckets (thread per chunk, or 4 lanes per chunk when chunks are few)
 //   k_msm_r2          block per (window, sum): plain sum of the chunk L's, bit sums of the chunk A's
 //   k_msm_tail        one block: per-window bit-Horner (4 lanes per window), two window-Horner chains (4 lanes each), join, to affine
+#ifndef MSM_G4_OUTLINED
+#define B200_G4_INLINE 1          // the 4-lane group operations inlined into the (few) latency-bound loops of this file
+#endif
 #include "msm.cuh"
 #include "ge_g4.cuh"
 #include "launch.h"
@@ -26,7 +29,8 @@ struct msm_ws {
     uint32_t* pbase;     // [TB+1]     first piece (unit) of a bucket
     uint32_t* mbase;     // [TB+1]     first slot in `parts` of a multi-piece bucket
     uint32_t* blocktot;  // [nblk][4]
-    uint32_t* counters;  // [4]        [0] = number of large multi-piece buckets (> MSM_SMALL_MULTI pieces), [1] = small ones
+    uint32_t* counters;  // [4 + 2*nw*MSM_MAX_SUMS]  [0] = number of large multi-piece buckets (> MSM_SMALL_MULTI pieces), [1] = small ones,
+                         //            [4 + sum] = blocks of that plain / bit sum that have finished (k_msm_r2)
     uint32_t* multi;     // [cap_multi]  large multi-piece buckets
     uint32_t* multi_s;   // [cap_multi]  small multi-piece buckets
     uint32_t* entries;   // [2*nw*N]
@@ -58,7 +62,7 @@ static size_t carve(msm_ws* w, uint8_t* base, const msm_plan& p) {
     q = take(p.N); if (w) w->flags = q;
     q = take(64); if (w) w->gpoint = q;
     q = take((size_t)p.TB * 4); if (w) w->hist = (uint32_t*)q;           // hist and counters are adjacent: one memset
-    q = take(16); if (w) w->counters = (uint32_t*)q;
+    q = take(16 + (size_t)2 * p.nw * MSM_MAX_SUMS * 4); if (w) w->counters = (uint32_t*)q;
     q = take((size_t)(p.TB + 1) * 4); if (w) w->off = (uint32_t*)q;
     q = take((size_t)(p.TB + 1) * 4); if (w) w->pbase = (uint32_t*)q;
     q = take((size_t)(p.TB + 1) * 4); if (w) w->mbase = (uint32_t*)q;
@@ -280,8 +284,18 @@ __device__ __forceinline__ void load_gej_vec(gej& a, const gej_store* src) {
     for (int k = 0; k < 6; k++) { uint4 v = q[k]; s.w[4 * k] = v.x; s.w[4 * k + 1] = v.y; s.w[4 * k + 2] = v.z; s.w[4 * k + 3] = v.w; }
     msm_load_gej(a, s);
 }
+__device__ __forceinline__ void load_gej_cg(gej& a, const gej_store* src) {      // L2 load: data written by another block of this kernel
+    gej_store s;
+    const uint4* q = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int k = 0; k < 6; k++) { uint4 v = __ldcg(q + k); s.w[4 * k] = v.x; s.w[4 * k + 1] = v.y; s.w[4 * k + 2] = v.z; s.w[4 * k + 3] = v.w; }
+    msm_load_gej(a, s);
+}
 #ifndef MSM_SUM_MINBLOCKS
-#define MSM_SUM_MINBLOCKS 5
+#define MSM_SUM_MINBLOCKS 4        // measured (profiles/r2b): inlined addition at 4 blocks/SM 3.97 ms per 2^20-term MSM, 5 blocks 4.04, outlined/5 4.22
+#endif
+#ifndef MSM_SUM_OUTLINED_ADD
+#define MSM_SUM_INLINE_ADD 1
 #endif
 __global__ void __launch_bounds__(128, MSM_SUM_MINBLOCKS) k_msm_bucket_sum(msm_ws ws, msm_plan p, const uint8_t* __restrict__ points64, size_t n) {
     const uint32_t lane = threadIdx.x & 31;
@@ -295,7 +309,9 @@ __global__ void __launch_bounds__(128, MSM_SUM_MINBLOCKS) k_msm_bucket_sum(msm_w
     bool have = false;
     uint32_t e = 0, eend = 0, dst = 0;
     gej acc;
+    ge nxt;                                                       // the point of entry e, loaded one iteration ahead of its addition
     gej_set_infinity(acc);
+    nxt.inf = 1;
     while (true) {
         const uint32_t mask = __ballot_sync(0xffffffffu, !have);
         if (!have) {
@@ -304,6 +320,9 @@ __global__ void __launch_bounds__(128, MSM_SUM_MINBLOCKS) k_msm_bucket_sum(msm_w
                 const uint4 d = *reinterpret_cast<const uint4*>(ws.units + my);
                 e = d.x; eend = d.x + d.y; dst = d.z;
                 gej_set_infinity(acc);
+                const uint32_t v = ws.entries[e];
+                msm_load_point(nxt, points64, n, ws.gpoint, v & 0x7FFFFFFFu);
+                if (v >> 31) fe_neg(nxt.y, nxt.y);
                 have = true;
             }
         }
@@ -311,10 +330,12 @@ __global__ void __launch_bounds__(128, MSM_SUM_MINBLOCKS) k_msm_bucket_sum(msm_w
         if (next > uend) next = uend;
         if (!__any_sync(0xffffffffu, have)) break;
         if (have) {
-            uint32_t v = ws.entries[e];
-            ge pt;
-            msm_load_point(pt, points64, n, ws.gpoint, v & 0x7FFFFFFFu);
-            if (v >> 31) fe_neg(pt.y, pt.y);
+            const ge pt = nxt;
+            if (e + 1 < eend) {                                   // issue the next gather now; the addition below hides its latency
+                const uint32_t v = ws.entries[e + 1];
+                msm_load_point(nxt, points64, n, ws.gpoint, v & 0x7FFFFFFFu);
+                if (v >> 31) fe_neg(nxt.y, nxt.y);
+            }
             gej t;
 #ifdef MSM_SUM_INLINE_ADD
             gej_add_ge_t<true>(t, acc, pt, nullptr);      // field multiplications inlined: this loop is the whole kernel, the body fits the I-cache
@@ -432,7 +453,22 @@ __global__ void __launch_bounds__(256) k_msm_r2(msm_ws ws, msm_plan p) {
         }
         block_sum_gej(acc, scratch);
     }
-    if (threadIdx.x == 0) store_gej_vec(ws.T + (size_t)blockIdx.x, acc);   // unused slots hold infinity
+    // the blocks of one sum leave their partial results in T[sum][part]; the last one to finish adds them into T[sum][0]
+    const uint32_t nparts = (s <= nbits) ? (count + MSM_R2_ELEMS - 1) / MSM_R2_ELEMS : 0;
+    if (threadIdx.x == 0 && part < (nparts ? nparts : 1)) {
+        gej_store* slot = ws.T + (size_t)ws_i * MSM_R2_PARTS;
+        if (nparts <= 1) { store_gej_vec(slot, acc); return; }
+        store_gej_vec(slot + part, acc);
+        __threadfence();
+        if (atomicAdd(&ws.counters[4 + ws_i], 1u) == nparts - 1) {
+            __threadfence();
+            gej tot;
+            gej_set_infinity(tot);
+#pragma unroll 1
+            for (uint32_t k = 0; k < nparts; k++) { gej o, t; load_gej_cg(o, slot + k); gej_add(t, tot, o); tot = t; }
+            store_gej_vec(slot, tot);
+        }
+    }
 }
 
 // ---- (7) tail: window sums, Horner, join, output ------------------------------------------------------------------------------
@@ -455,7 +491,7 @@ __global__ void __launch_bounds__(256) k_msm_tail(uint8_t* out, int mode, msm_ws
         msm_win w;
         msm_window_by_index(w, p, wic);
         gej r;
-        msm_window_from_sums(r, ws.T + (size_t)wic * MSM_MAX_SUMS * MSM_R2_PARTS, msm_ilog2(w.Bw / MSM_CHUNK), maxbits);
+        msm_window_from_sums(r, ws.T + (size_t)wic * MSM_MAX_SUMS * MSM_R2_PARTS, MSM_R2_PARTS, msm_ilog2(w.Bw / MSM_CHUNK), maxbits);
         if (valid && l == 0) W[wi] = r;
     }
     __syncthreads();
@@ -525,7 +561,7 @@ cudaError_t launch_msm(uint8_t* out, int out_mode, const uint8_t* g_scalar32, co
     msm_ws ws;
     if (carve(&ws, workspace, p) > workspace_bytes) return cudaErrorInvalidValue;
     const msm_caps caps = caps_of(p);
-    cudaError_t err = cudaMemsetAsync(ws.hist, 0, (size_t)((uint8_t*)ws.counters - (uint8_t*)ws.hist) + 16, s);
+    cudaError_t err = cudaMemsetAsync(ws.hist, 0, (size_t)((uint8_t*)ws.counters - (uint8_t*)ws.hist) + 16 + (size_t)2 * p.nw * MSM_MAX_SUMS * 4, s);
     if (err != cudaSuccess) return err;
     err = cudaMemsetAsync(ws.buckets, 0, (size_t)p.TB * sizeof(gej_store), s);
     if (err != cudaSuccess) return err;

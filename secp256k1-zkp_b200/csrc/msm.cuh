@@ -223,7 +223,7 @@ HD uint32_t msm_bit_index(uint32_t k, uint32_t j) { return ((k >> j) << (j + 1))
 // arguments, all loops with warp-uniform trip counts); compiled for the host they are plain single-thread code.
 // window sum from its plain sum T[0] = sum_q L_q and bit sums T[1 + j] = sum_{q: bit j} A_q:
 //   W = T[0] + 8 * sum_j 2^j T[1 + j]
-HD void msm_window_from_sums(gej& W, const gej_store* T /* [1 + bits][MSM_R2_PARTS] */, uint32_t nbits, uint32_t maxbits) {
+HD void msm_window_from_sums(gej& W, const gej_store* T /* [1 + bits] sums, `stride` slots apart */, uint32_t stride, uint32_t nbits, uint32_t maxbits) {
     gej acc;
     gej_set_infinity(acc);
 #pragma unroll 1
@@ -233,12 +233,9 @@ HD void msm_window_from_sums(gej& W, const gej_store* T /* [1 + bits][MSM_R2_PAR
 #pragma unroll 1
             for (int k = 0; k < 3; k++) { gej t; gej_double_g4(t, acc); acc = t; }
         } else { gej t; gej_double_g4(t, acc); acc = t; }
-#pragma unroll 1
-        for (int part = 0; part < MSM_R2_PARTS; part++) {
-            gej s, t;
-            if (slot <= (int)nbits) msm_load_gej(s, T[slot * MSM_R2_PARTS + part]); else gej_set_infinity(s);
-            gej_add_g4(t, acc, s); acc = t;
-        }
+        gej s, t;
+        if (slot <= (int)nbits) msm_load_gej(s, T[(size_t)slot * stride]); else gej_set_infinity(s);
+        gej_add_g4(t, acc, s); acc = t;
     }
     W = acc;
 }

@@ -208,14 +208,18 @@ int emu_msm2(uint8_t* out64, const uint8_t* g_sc32, const uint8_t* scalars32, co
     for (uint32_t wi = 0; wi < 2 * p.nw; wi++) {                          // k_msm_r2 + first phase of k_msm_tail
         msm_win w; msm_window_by_index(w, p, wi);
         uint32_t Q = w.Bw / MSM_CHUNK, nbits = msm_ilog2(Q), cb = w.base / MSM_CHUNK;
-        for (uint32_t s = 0; s <= nbits; s++) for (uint32_t part = 0; part < MSM_R2_PARTS; part++) {
-            gej acc; gej_set_infinity(acc);
-            uint32_t count = s == 0 ? Q : Q / 2, lo = part * MSM_R2_ELEMS, hi = lo + MSM_R2_ELEMS < count ? lo + MSM_R2_ELEMS : count;
-            for (uint32_t k = lo; k < hi; k++) { gej o, t; msm_load_gej(o, s == 0 ? Lq[cb + k] : Aq[cb + msm_bit_index(k, s - 1)]); gej_add(t, acc, o); acc = t; }
-            msm_store_gej(T[((size_t)wi * MSM_MAX_SUMS + s) * MSM_R2_PARTS + part], acc);
+        for (uint32_t s = 0; s <= nbits; s++) {
+            gej tot; gej_set_infinity(tot);
+            for (uint32_t part = 0; part < MSM_R2_PARTS; part++) {                 // the blocks of one sum, then the last block's combine
+                gej acc; gej_set_infinity(acc);
+                uint32_t count = s == 0 ? Q : Q / 2, lo = part * MSM_R2_ELEMS, hi = lo + MSM_R2_ELEMS < count ? lo + MSM_R2_ELEMS : count;
+                for (uint32_t k = lo; k < hi; k++) { gej o, t; msm_load_gej(o, s == 0 ? Lq[cb + k] : Aq[cb + msm_bit_index(k, s - 1)]); gej_add(t, acc, o); acc = t; }
+                gej t; gej_add(t, tot, acc); tot = t;
+            }
+            msm_store_gej(T[((size_t)wi * MSM_MAX_SUMS + s) * MSM_R2_PARTS], tot);
         }
         uint32_t maxbits = msm_ilog2((p.B > p.Btop ? p.B : p.Btop) / MSM_CHUNK);
-        msm_window_from_sums(W[wi], T.data() + (size_t)wi * MSM_MAX_SUMS * MSM_R2_PARTS, nbits, maxbits);
+        msm_window_from_sums(W[wi], T.data() + (size_t)wi * MSM_MAX_SUMS * MSM_R2_PARTS, MSM_R2_PARTS, nbits, maxbits);
     }
     gej H[2], r;
     msm_horner_half(H[0], W.data(), p);
