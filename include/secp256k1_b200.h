@@ -62,6 +62,9 @@ typedef struct secp256k1_b200_engine secp256k1_b200_engine;
 #define SECP256K1_B200_FE_INV  5
 #define SECP256K1_B200_FE_SQRT 6
 #define SECP256K1_B200_FE_NEG  7
+#define SECP256K1_B200_FE_INV_FERMAT 8      /* a^(p-2): the round-1 inversion, kept as a cross-check of FE_INV (division steps, csrc/modinv.cuh) */
+#define SECP256K1_B200_FE_IS_SQUARE 9       /* out = 1 / 0: Jacobi symbol (secp256k1_fe_is_square_var, src/field_5x52_impl.h:501) */
+#define SECP256K1_B200_FE_IS_SQUARE_SQRT 10 /* the same through a full square root (round-1 form, cross-check) */
 #define SECP256K1_B200_FE_MUL_PORTABLE 16 /* same op through the portable (non-PTX) limb code: on-device A/B self test */
 #define SECP256K1_B200_FE_SQR_PORTABLE 17
 

@@ -267,9 +267,9 @@ HD void fe_pow_chain(fe& x2, fe& x22, fe& x223, const fe& a) {
     fe_sqr_n(t, x220, 3); fe_mul(x223, t, x3);
 }
 
-// r = a^(p-2)  (a = 0 -> 0).  Any exact inverse gives the reference's fe_inv_var value
-// (field_5x52_impl.h:491 uses safegcd; results are unique mod p).
-HDNI void fe_inv(fe& r, const fe& a) {
+// r = a^(p-2)  (a = 0 -> 0).  Any exact inverse gives the reference's fe_inv_var value (field_5x52_impl.h:491 uses safegcd; results are
+// unique mod p).  Round-1 form, kept as the cross-check of fe_inv (modinv.cuh), which is what the kernels call now.
+HDNI void fe_inv_fermat(fe& r, const fe& a) {
     fe x2, x22, x223, t;
     fe_pow_chain(x2, x22, x223, a);
     // p - 2 = (2^223-1) << 33 | 2^32... : bits: 223 ones, 0, 22 ones, 0000, 1, 0, 11, 0, 1  (binary of p-2 tail ...FFFFFC2D)
@@ -291,8 +291,8 @@ HDNI int fe_sqrt(fe& r, const fe& a) {
     return fe_equal(chk, a);
 }
 
-// Legendre symbol via Euler's criterion is not needed: is_square(a) <=> sqrt succeeds.
-HD int fe_is_square(const fe& a) {
+// is_square(a) <=> sqrt succeeds (round-1 form; fe_is_square in modinv.cuh computes the Jacobi symbol instead)
+HD int fe_is_square_sqrt(const fe& a) {
     fe r;
     return fe_sqrt(r, a);
 }

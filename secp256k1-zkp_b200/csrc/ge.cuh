@@ -5,7 +5,7 @@
 // adversarial verification inputs can reach those branches.  Formulas are the textbook a=0 Jacobian
 // ones; only serialized results have to match the reference bit for bit, and those are unique.
 #pragma once
-#include "fe.cuh"
+#include "modinv.cuh"
 
 namespace B200_NS {
 

@@ -1,7 +1,7 @@
 // k_fe_impl.cuh -- batched field-op kernel body; included by k_fe.cu (PTX limb code) and by
 // k_fe_portable.cu (compiled with -DB200_PORTABLE_BN -DB200_NS=b200_portable) so that both limb
 // implementations exist in one library and can be compared ON THE DEVICE.
-#include "fe.cuh"
+#include "modinv.cuh"
 #include "launch.h"
 
 namespace B200_NS {
@@ -51,6 +51,9 @@ __global__ void __launch_bounds__(256) k_fe_op(uint8_t* __restrict__ out, const 
         else if (OP == 5) { fe t; fe_inv(t, r); r = t; }
         else if (OP == 6) { fe t; fe_sqrt(t, r); r = t; }
         else if (OP == 7) fe_neg(r, r);
+        else if (OP == 8) { fe t; fe_inv_fermat(t, r); r = t; }
+        else if (OP == 9) fe_set_int(r, (uint32_t)fe_is_square(r));
+        else if (OP == 10) fe_set_int(r, (uint32_t)fe_is_square_sqrt(r));
     }
     fe_store_be32_global(out + 32 * i, r);
 }
@@ -67,9 +70,12 @@ static cudaError_t launch_fe_op_impl(int op, uint8_t* out, const uint8_t* a, con
         case 5: k_fe_op<5><<<grid, block, 0, s>>>(out, a, b, n, iters); break;
         case 6: k_fe_op<6><<<grid, block, 0, s>>>(out, a, b, n, iters); break;
         case 7: k_fe_op<7><<<grid, block, 0, s>>>(out, a, b, n, iters); break;
+        case 8: k_fe_op<8><<<grid, block, 0, s>>>(out, a, b, n, iters); break;
+        case 9: k_fe_op<9><<<grid, block, 0, s>>>(out, a, b, n, iters); break;
+        case 10: k_fe_op<10><<<grid, block, 0, s>>>(out, a, b, n, iters); break;
         default: return cudaErrorInvalidValue;
     }
-    if (launches) *launches += 1;
+    if (launches) __atomic_fetch_add(launches, (uint64_t)1, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }
 

@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(128, MSM_SUM_MINBLOCKS) k_msm_bucket_sum(msm_w
     uint32_t e = 0, eend = 0, dst = 0;
     gej acc;
     ge nxt;                                                       // the point of entry e, loaded one iteration ahead of its addition
+    uint32_t nxt_neg = 0;                                         // its sign, applied when it is consumed (nothing waits on the load before that)
     gej_set_infinity(acc);
     nxt.inf = 1;
     while (true) {
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(128, MSM_SUM_MINBLOCKS) k_msm_bucket_sum(msm_w
                 gej_set_infinity(acc);
                 const uint32_t v = ws.entries[e];
                 msm_load_point(nxt, points64, n, ws.gpoint, v & 0x7FFFFFFFu);
-                if (v >> 31) fe_neg(nxt.y, nxt.y);
+                nxt_neg = v >> 31;
                 have = true;
             }
         }
@@ -330,11 +331,12 @@ __global__ void __launch_bounds__(128, MSM_SUM_MINBLOCKS) k_msm_bucket_sum(msm_w
         if (next > uend) next = uend;
         if (!__any_sync(0xffffffffu, have)) break;
         if (have) {
-            const ge pt = nxt;
+            ge pt = nxt;
+            if (nxt_neg) fe_neg(pt.y, pt.y);
             if (e + 1 < eend) {                                   // issue the next gather now; the addition below hides its latency
                 const uint32_t v = ws.entries[e + 1];
                 msm_load_point(nxt, points64, n, ws.gpoint, v & 0x7FFFFFFFu);
-                if (v >> 31) fe_neg(nxt.y, nxt.y);
+                nxt_neg = v >> 31;
             }
             gej t;
 #ifdef MSM_SUM_INLINE_ADD
@@ -409,8 +411,9 @@ __global__ void __launch_bounds__(128) k_msm_combine_small(msm_ws ws, msm_plan p
 }
 
 // ---- (5) running sums over chunks of 8 buckets --------------------------------------------------------------------------------
+// (thread form: 158 registers unbounded = 3 blocks per SM and 1.3 waves of blocks at c = 16; bounded to 128 registers: 4 blocks, one wave)
 template <bool G4>
-__global__ void __launch_bounds__(128) k_msm_r1(msm_ws ws, msm_plan p) {
+__global__ void __launch_bounds__(128, G4 ? 1 : 4) k_msm_r1(msm_ws ws, msm_plan p) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t nchunks = p.TB / MSM_CHUNK;
     uint32_t q = G4 ? (t >> 2) : t;
@@ -432,7 +435,7 @@ __global__ void __launch_bounds__(128) k_msm_r1(msm_ws ws, msm_plan p) {
 }
 
 // ---- (6) per window: plain sum of the L's, bit sums of the A's; <= MSM_R2_ELEMS chunk sums per block ----------------------------
-__global__ void __launch_bounds__(256) k_msm_r2(msm_ws ws, msm_plan p) {
+__global__ void __launch_bounds__(256, 2) k_msm_r2(msm_ws ws, msm_plan p) {      // 2 blocks per SM (unbounded: 146 registers = 1 block, 3 waves)
     __shared__ gej_store scratch[8];
     const uint32_t part = blockIdx.x % MSM_R2_PARTS, ws_i = blockIdx.x / MSM_R2_PARTS;
     const uint32_t wi = ws_i / MSM_MAX_SUMS, s = ws_i % MSM_MAX_SUMS;

@@ -1,0 +1,269 @@
+// modinv.cuh -- modular inverse and Jacobi symbol by the Bernstein-Yang "safegcd" division steps, for the field prime p and the group order n.
+//
+// Replaces, on the B200, what the reference computes with secp256k1_modinv64_var / secp256k1_jacobi64_maybe_var (modinv64_impl.h:637-719,
+// :721; the 32-bit restatement of the same algorithm is modinv32_impl.h) behind secp256k1_fe_inv_var (field_5x52_impl.h:491-499),
+// secp256k1_fe_is_square_var (:501-522) and secp256k1_scalar_inverse_var (scalar_4x64_impl.h:1162).  Round 1 used Fermat chains for all
+// three (~270 dependent field multiplications on the integer-multiply pipe, 0.08 ms for one thread); a division-step inverse is ~10^4
+// mostly ALU-pipe instructions, a quarter of the latency, and the Jacobi symbol replaces a whole square root (253 squarings).
+//
+// Re-designed rather than translated:
+//  * 9 signed limbs of 30 bits held in registers with a FIXED length (the reference shrinks the working length as f and g shrink; a
+//    variable length would turn the register arrays into local memory on a GPU);
+//  * no 128-entry inverse table: the multiple of f that clears the low bits of g comes from two Newton steps (-1/f mod 2^8);
+//  * the modulus is a template parameter (constant limbs folded into the instruction stream).
+// Values are unique (an inverse is an inverse, a Jacobi symbol is a Jacobi symbol), so results are bit-identical to the reference's.
+#pragma once
+#include "fe.cuh"
+#include "sc.cuh"
+
+namespace B200_NS {
+
+struct mi30 { int32_t v[9]; };            // value = sum v[i] * 2^(30 i)
+struct mi_mat { int32_t u, v, q, r; };    // 30 division steps: [f'; g'] = [u v; q r] [f; g] / 2^30
+#define MI_M30 0x3FFFFFFF
+
+struct mi_mod_p {   // p = 2^256 - 2^32 - 977
+    HD static int32_t limb(int i) { const int32_t m[9] = {0x3FFFFC2F, 0x3FFFFFFB, 0x3FFFFFFF, 0x3FFFFFFF, 0x3FFFFFFF, 0x3FFFFFFF, 0x3FFFFFFF, 0x3FFFFFFF, 0xFFFF}; return m[i]; }
+    HD static uint32_t inv30() { return 0x2DDACACFu; }            // p^-1 mod 2^30
+};
+struct mi_mod_n {   // group order
+    HD static int32_t limb(int i) { const int32_t m[9] = {0x10364141, 0x3F497A33, 0x348A03BB, 0x2BB739AB, 0x3FFFFEBA, 0x3FFFFFFF, 0x3FFFFFFF, 0x3FFFFFFF, 0xFFFF}; return m[i]; }
+    HD static uint32_t inv30() { return 0x2A774EC1u; }
+};
+
+HD int mi_ctz(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+// 8 x 32-bit limbs (canonical, < modulus) <-> 9 x 30-bit limbs
+HD void mi_from_words(mi30& r, const uint32_t* a) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const int bit = 30 * i, w = bit >> 5, o = bit & 31;
+        uint32_t x = a[w] >> o;
+        if (o > 2 && w + 1 < 8) x |= a[w + 1] << (32 - o);
+        r.v[i] = (int32_t)(x & MI_M30);
+    }
+}
+HD void mi_to_words(uint32_t* a, const mi30& r) {       // limbs in [0, 2^30), value < 2^256
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const int bit = 30 * i, w = bit >> 5, o = bit & 31;
+        const uint32_t x = (uint32_t)r.v[i];
+        a[w] |= x << o;
+        if (o > 2 && w + 1 < 8) a[w + 1] |= x >> (32 - o);
+    }
+}
+
+// 30 division steps on the low words of f (odd) and g; eta = -delta.  Returns the new eta and the transition matrix.
+HD int32_t mi_divsteps30(int32_t eta, uint32_t f0, uint32_t g0, mi_mat& t) {
+    uint32_t u = 1, v = 0, q = 0, r = 1, f = f0, g = g0;
+    int i = 30;
+    for (;;) {
+        const int z = mi_ctz(g | (0xFFFFFFFFu << i));          // as many plain halvings of g as there are (at most the i steps left)
+        g >>= z; u <<= z; v <<= z; eta -= z; i -= z;
+        if (i == 0) break;
+        if (eta < 0) {                                         // delta > 0 with g odd: (f, g) <- (g, -f)
+            uint32_t tmp;
+            eta = -eta;
+            tmp = f; f = g; g = 0u - tmp;
+            tmp = u; u = q; q = 0u - tmp;
+            tmp = v; v = r; r = 0u - tmp;
+        }
+        // now eta >= 0: up to min(eta + 1, i, 8) low bits of g can be cleared at once by adding a multiple of f
+        const int limit = (eta + 1 > i) ? i : eta + 1;
+        const uint32_t m = (0xFFFFFFFFu >> (32 - limit)) & 255u;
+        uint32_t x = f;                                        // x = 1/f mod 2^3 (f odd), two Newton steps: mod 2^6, mod 2^12
+        x *= 2u - f * x;
+        x *= 2u - f * x;
+        const uint32_t w = (g * (0u - x)) & m;
+        g += f * w; q += u * w; r += v * w;
+    }
+    t.u = (int32_t)u; t.v = (int32_t)v; t.q = (int32_t)q; t.r = (int32_t)r;
+    return eta;
+}
+// the same for the Jacobi symbol: f and g stay positive ((f, g) <- (g, f) without the negation), bit 0 of jac flips whenever the symbol
+// changes sign.  f0, g0 are f, g mod 2^32 (the symbol rules look at f mod 8).
+HD int32_t mi_posdivsteps30(int32_t eta, uint32_t f0, uint32_t g0, mi_mat& t, uint32_t& jac) {
+    uint32_t u = 1, v = 0, q = 0, r = 1, f = f0, g = g0;
+    int i = 30;
+    for (;;) {
+        const int z = mi_ctz(g | (0xFFFFFFFFu << i));
+        g >>= z; u <<= z; v <<= z; eta -= z; i -= z;
+        jac ^= ((uint32_t)z & ((f >> 1) ^ (f >> 2)));         // (2 | f) = -1 for f = 3, 5 mod 8: flips once per odd number of halvings
+        if (i == 0) break;
+        if (eta < 0) {
+            uint32_t tmp;
+            eta = -eta;
+            jac ^= ((f & g) >> 1);                             // reciprocity: the swap flips the sign iff f = g = 3 mod 4
+            tmp = f; f = g; g = tmp;
+            tmp = u; u = q; q = tmp;
+            tmp = v; v = r; r = tmp;
+        }
+        const int limit = (eta + 1 > i) ? i : eta + 1;
+        const uint32_t m = (0xFFFFFFFFu >> (32 - limit)) & 255u;
+        uint32_t x = f;
+        x *= 2u - f * x;
+        x *= 2u - f * x;
+        const uint32_t w = (g * (0u - x)) & m;
+        g += f * w; q += u * w; r += v * w;
+    }
+    t.u = (int32_t)u; t.v = (int32_t)v; t.q = (int32_t)q; t.r = (int32_t)r;
+    return eta;
+}
+
+// (f, g) <- t (f, g) / 2^30 (exact)
+HD void mi_update_fg(mi30& f, mi30& g, const mi_mat& t) {
+    const int64_t u = t.u, v = t.v, q = t.q, r = t.r;
+    int64_t cf = u * f.v[0] + v * g.v[0];
+    int64_t cg = q * f.v[0] + r * g.v[0];
+    cf >>= 30; cg >>= 30;                                      // the low 30 bits are zero by construction
+#pragma unroll
+    for (int i = 1; i < 9; i++) {
+        cf += u * f.v[i] + v * g.v[i];
+        cg += q * f.v[i] + r * g.v[i];
+        f.v[i - 1] = (int32_t)(cf & MI_M30); cf >>= 30;
+        g.v[i - 1] = (int32_t)(cg & MI_M30); cg >>= 30;
+    }
+    f.v[8] = (int32_t)cf;
+    g.v[8] = (int32_t)cg;
+}
+// (d, e) <- t (d, e) / 2^30 mod M, d and e in (-2M, M)
+template <class M>
+HD void mi_update_de(mi30& d, mi30& e, const mi_mat& t) {
+    const int64_t u = t.u, v = t.v, q = t.q, r = t.r;
+    const int32_t sd = d.v[8] >> 31, se = e.v[8] >> 31;
+    int32_t md = (t.u & sd) + (t.v & se), me = (t.q & sd) + (t.r & se);     // multiples of M that make negative d, e non-negative
+    int64_t cd = u * d.v[0] + v * e.v[0];
+    int64_t ce = q * d.v[0] + r * e.v[0];
+    // ... and the multiples that make the low 30 bits vanish
+    md -= (int32_t)((M::inv30() * (uint32_t)cd + (uint32_t)md) & MI_M30);
+    me -= (int32_t)((M::inv30() * (uint32_t)ce + (uint32_t)me) & MI_M30);
+    cd += (int64_t)M::limb(0) * md;
+    ce += (int64_t)M::limb(0) * me;
+    cd >>= 30; ce >>= 30;
+#pragma unroll
+    for (int i = 1; i < 9; i++) {
+        cd += u * d.v[i] + v * e.v[i] + (int64_t)M::limb(i) * md;
+        ce += q * d.v[i] + r * e.v[i] + (int64_t)M::limb(i) * me;
+        d.v[i - 1] = (int32_t)(cd & MI_M30); cd >>= 30;
+        e.v[i - 1] = (int32_t)(ce & MI_M30); ce >>= 30;
+    }
+    d.v[8] = (int32_t)cd;
+    e.v[8] = (int32_t)ce;
+}
+// carry propagation: limbs 0..7 into [0, 2^30), the sign stays in limb 8
+HD void mi_carry(mi30& a) {
+    int32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { int32_t x = a.v[i] + c; a.v[i] = x & MI_M30; c = x >> 30; }
+    a.v[8] += c;
+}
+template <class M>
+HD void mi_add_mod_if(mi30& a, int32_t mask /* 0 or -1 */) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) a.v[i] += M::limb(i) & mask;
+    mi_carry(a);
+}
+// d in (-2M, M), optionally negated, -> [0, M)
+template <class M>
+HD void mi_normalize(mi30& d, int32_t negate) {
+    mi_carry(d);
+    mi_add_mod_if<M>(d, d.v[8] >> 31);                         // (-2M, M) -> (-M, M)
+    if (negate) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) d.v[i] = -d.v[i];
+        mi_carry(d);
+    }
+    mi_add_mod_if<M>(d, d.v[8] >> 31);                         // (-M, M) -> [0, M)
+}
+
+// x <- x^-1 mod M (x in [0, M); 0 -> 0)
+template <class M>
+HD void mi_inverse(mi30& x) {
+    mi30 d, e, f, g = x;
+#pragma unroll
+    for (int i = 0; i < 9; i++) { d.v[i] = 0; e.v[i] = 0; f.v[i] = M::limb(i); }
+    e.v[0] = 1;
+    int32_t eta = -1;
+#pragma unroll 1
+    for (int it = 0; it < 32; it++) {                          // 256-bit inputs finish within 25 rounds of 30 steps
+        mi_mat t;
+        eta = mi_divsteps30(eta, (uint32_t)f.v[0], (uint32_t)g.v[0], t);
+        mi_update_de<M>(d, e, t);
+        mi_update_fg(f, g, t);
+        int32_t z = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) z |= g.v[i];
+        if (z == 0) break;
+    }
+    // g = 0, f = +-1 (or f = M when x was 0, with d = 0): d = +-x^-1
+    mi30 fc = f;
+    mi_carry(fc);
+    mi_normalize<M>(d, fc.v[8] < 0);
+    x = d;
+}
+
+// Jacobi symbol (x | M) for x in (0, M) coprime to M: +1 / -1, or 0 when the iteration limit is hit (caller falls back)
+template <class M>
+HD int mi_jacobi(const mi30& x) {
+    mi30 f, g = x;
+#pragma unroll
+    for (int i = 0; i < 9; i++) f.v[i] = M::limb(i);
+    int32_t eta = -1;
+    uint32_t jac = 0;
+#pragma unroll 1
+    for (int it = 0; it < 50; it++) {
+        mi_mat t;
+        eta = mi_posdivsteps30(eta, (uint32_t)f.v[0] | ((uint32_t)f.v[1] << 30), (uint32_t)g.v[0] | ((uint32_t)g.v[1] << 30), t, jac);
+        mi_update_fg(f, g, t);
+        if (f.v[0] == 1) {
+            int32_t z = 0;
+#pragma unroll
+            for (int i = 1; i < 9; i++) z |= f.v[i];
+            if (z == 0) return 1 - 2 * (int)(jac & 1u);
+        }
+    }
+    return 0;
+}
+
+// ---- field / scalar front ends --------------------------------------------------------------------------------------------------
+// r = a^-1 mod p (0 -> 0): the value secp256k1_fe_inv_var returns
+HD void fe_inv_safegcd(fe& r, const fe& a) {
+    fe t = a;
+    fe_normalize(t);
+    mi30 x;
+    mi_from_words(x, t.v);
+    mi_inverse<mi_mod_p>(x);
+    mi_to_words(r.v, x);
+}
+// is a a square mod p?  (secp256k1_fe_is_square_var, field_5x52_impl.h:501-522: Jacobi symbol, square root only if that gives up)
+HD int fe_is_square_jacobi(const fe& a) {
+    fe t = a;
+    fe_normalize(t);
+    if (bn_is_zero8(t.v)) return 1;
+    mi30 x;
+    mi_from_words(x, t.v);
+    int j = mi_jacobi<mi_mod_p>(x);
+    if (j == 0) { fe s; return fe_sqrt(s, t); }
+    return j > 0;
+}
+// r = a^-1 mod n (0 -> 0): the value secp256k1_scalar_inverse_var returns
+HD void sc_inverse_safegcd(sc& r, const sc& a) {
+    mi30 x;
+    mi_from_words(x, a.v);
+    mi_inverse<mi_mod_n>(x);
+    mi_to_words(r.v, x);
+}
+
+// what the kernels call (outlined: one body per kernel)
+HDNI void fe_inv(fe& r, const fe& a) { fe t; fe_inv_safegcd(t, a); r = t; }
+HDNI int fe_is_square(const fe& a) { return fe_is_square_jacobi(a); }
+HDNI void sc_inverse(sc& r, const sc& a) { sc t; sc_inverse_safegcd(t, a); r = t; }
+
+}  // namespace B200_NS

@@ -160,7 +160,7 @@ HD void sc_split_lambda(sc& r1, sc& r2, const sc& k) {
 // indexed local table, one sm_100a build of k_bppp_norm_verify computed a wrong inverse deterministically (no sanitizer
 // finding; inlining this function, or any unrelated change to the kernel, made it disappear -- A/B libraries on the GPU,
 // round 1).  Inlined, the table lives in the kernel's own frame like every other local array.
-HD void sc_inverse(sc& r, const sc& a) {
+HD void sc_inverse_fermat(sc& r, const sc& a) {
     // a^(n-2) without any table (r1g: the former 16-entry window table -- a dynamically indexed local array -- was the common factor of two
     // wrong-result builds: the outlined copy in k_bppp_norm_verify (see above) and, inlined into k_rangeproof_rewind, a build whose
     // 512-byte table shared its stack slot with the first 512 bytes of a live 4 KB array of the caller; both clean under

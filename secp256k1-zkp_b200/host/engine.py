@@ -13,6 +13,7 @@ import numpy as np
 PK_OPAQUE64, PK_XONLY32, PK_COMPRESSED33 = 0, 1, 2
 SIG_OPAQUE64, SIG_COMPACT64 = 0, 1
 FE_MUL, FE_SQR, FE_ADD, FE_SUB, FE_HALF, FE_INV, FE_SQRT, FE_NEG = range(8)
+FE_INV_FERMAT, FE_IS_SQUARE, FE_IS_SQUARE_SQRT = 8, 9, 10
 FE_MUL_PORTABLE, FE_SQR_PORTABLE = 16, 17
 
 _PKLEN = {PK_OPAQUE64: 64, PK_XONLY32: 32, PK_COMPRESSED33: 33}

@@ -2,7 +2,7 @@
 // as plain C++ when __CUDACC__ is undefined, using the portable big-number path).
 // Lets the CPU-only test tier check the group law / ecmult / verify LOGIC against the oracle
 // without a GPU.  Never linked into, nor loaded by, the product library.
-#include "../../secp256k1-zkp_b200/csrc/fe.cuh"
+#include "../../secp256k1-zkp_b200/csrc/modinv.cuh"
 using namespace b200;
 extern "C" {
 void emu_fe_mul(uint8_t* r, const uint8_t* a, const uint8_t* b) { fe x, y, z; fe_set_b32(x, a); fe_set_b32(y, b); fe_mul(z, x, y); fe_get_b32(r, z); }
@@ -15,6 +15,14 @@ void emu_fe_mul_small(uint8_t* r, const uint8_t* a, uint32_t k) { fe x, z; fe_se
 void emu_fe_inv(uint8_t* r, const uint8_t* a) { fe x, z; fe_set_b32(x, a); fe_inv(z, x); fe_get_b32(r, z); }
 int emu_fe_sqrt(uint8_t* r, const uint8_t* a) { fe x, z; fe_set_b32(x, a); int ok = fe_sqrt(z, x); fe_get_b32(r, z); return ok; }
 int emu_fe_is_zero(const uint8_t* a) { fe x; fe_set_b32(x, a); return fe_is_zero(x); }
+}
+
+// ---- safegcd inverse / Jacobi symbol (modinv.cuh) ---------------------------------------------------
+#include "../../secp256k1-zkp_b200/csrc/modinv.cuh"
+extern "C" {
+void emu_fe_inv_safegcd(uint8_t* r, const uint8_t* a, size_t n) { for (size_t i = 0; i < n; i++) { fe x, z; fe_set_b32(x, a + 32 * i); fe_inv_safegcd(z, x); fe_get_b32(r + 32 * i, z); } }
+void emu_fe_is_square_jacobi(uint8_t* r, const uint8_t* a, size_t n) { for (size_t i = 0; i < n; i++) { fe x; fe_set_b32(x, a + 32 * i); r[i] = (uint8_t)fe_is_square_jacobi(x); } }
+void emu_sc_inverse_safegcd(uint8_t* r, const uint8_t* a, size_t n) { for (size_t i = 0; i < n; i++) { sc x, z; sc_set_b32(x, a + 32 * i); sc_inverse_safegcd(z, x); sc_get_b32(r + 32 * i, z); } }
 }
 
 // ---- scalar / group / ecmult / verify logic -------------------------------

@@ -293,3 +293,24 @@ def test_offcurve_key_does_not_poison_its_block(engine, ref):
     out = engine.ecmult(bad, na, na)
     mask = np.ones(n, dtype=bool); mask[[7, 129, 400]] = False
     assert np.array_equal(out[mask], clean[mask])
+
+
+# ---- division-step inverse / Jacobi symbol on the device (csrc/modinv.cuh) ------------------------------------------------------------
+def test_safegcd_inverse_and_jacobi_gpu(engine, ref):
+    import secp256k1_zkp_b200 as b200
+    rnd = random.Random(31)
+    edge = [0, 1, 2, 3, P - 1, P - 2, P, P + 1, 2**256 - 1, 2**255, 2**128, 2**30, 2**30 - 1, 2**60, 2**240, (P + 1) // 2, (P - 1) // 2, 977, 2**32 + 977]
+    vals = edge + [rnd.getrandbits(256) for _ in range(30000)] + [rnd.getrandbits(k) for k in range(1, 256) for _ in range(8)]
+    A = b"".join(b32(v) for v in vals)
+    inv = [int.from_bytes(bytes(r), "big") for r in engine.fe_op(b200.FE_INV, A)]
+    assert inv == [pow(v % P, P - 2, P) for v in vals]
+    fer = engine.fe_op(b200.FE_INV_FERMAT, A)
+    assert [int.from_bytes(bytes(r), "big") for r in fer] == inv
+    sq = engine.fe_op(b200.FE_IS_SQUARE, A)[:, 31]
+    exp = np.array([1 if (v % P == 0 or pow(v % P, (P - 1) // 2, P) == 1) else 0 for v in vals], dtype=np.uint8)
+    assert np.array_equal(sq, exp)
+    assert np.array_equal(engine.fe_op(b200.FE_IS_SQUARE_SQRT, A)[:, 31], exp)
+    # the reference's own fe_inv_var / fe_is_square_var on a sample
+    for v in vals[:200]:
+        assert ref.fe1("ref_fe_inv", b32(v))[0] == b32(pow(v % P, P - 2, P))
+        assert ref.lib.ref_fe_is_square(b32(v)) == int(exp[vals.index(v)])
