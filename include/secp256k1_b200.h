@@ -278,6 +278,40 @@ SECP256K1_B200_API int secp256k1_b200_rangeproof_rewind_batch_dev(secp256k1_b200
         const unsigned char *d_gen64, size_t gen_stride, const unsigned char *d_extra, size_t extra_stride, const uint32_t *d_extra_len, size_t n,
         void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* ---- one process, several GPUs -------------------------------------------------------------------------------------------
+ * The reference has no counterpart (it is a single-threaded library); this is the C-level form of north_star's multi-GPU plan:
+ * _multi_create makes one engine per listed device (devices = NULL: devices 0 .. n_devices-1; n_devices <= 0: every device of the box),
+ * device 0 builds the generator table, ncclCommInitAll + ONE ncclBroadcast replicate it (NCCL is bound at run time from libnccl.so.2 and is
+ * only needed for more than one device).  Every *_batch call below has the semantics of its single-engine namesake: the host arrays are cut
+ * into contiguous index ranges, one per device, processed concurrently (one host thread and one stream pair per device), results written
+ * straight into the caller's arrays.  _multi_ecmult_multi shards the terms, gathers the per-device Jacobian partial sums with ONE
+ * ncclAllGather (96 bytes per device) and adds them on device 0.  A multi engine may be used from several host threads (calls serialize).
+ * _multi_engine exposes the per-device engines for the device-pointer (_dev) entry points; do not run a sharded call concurrently with
+ * host-buffer calls on those engines. */
+typedef struct secp256k1_b200_multi secp256k1_b200_multi;
+SECP256K1_B200_API int secp256k1_b200_multi_create(secp256k1_b200_multi **out, const int *devices, int n_devices, int gen_window_bits);
+SECP256K1_B200_API void secp256k1_b200_multi_destroy(secp256k1_b200_multi *m);
+SECP256K1_B200_API int secp256k1_b200_multi_device_count(const secp256k1_b200_multi *m);
+SECP256K1_B200_API int secp256k1_b200_multi_nccl_version(const secp256k1_b200_multi *m);   /* e.g. 22809; 0 with a single device */
+SECP256K1_B200_API secp256k1_b200_engine *secp256k1_b200_multi_engine(secp256k1_b200_multi *m, int index);
+SECP256K1_B200_API uint64_t secp256k1_b200_multi_launch_count(const secp256k1_b200_multi *m);
+SECP256K1_B200_API int secp256k1_b200_multi_schnorrsig_verify_batch(secp256k1_b200_multi *m, unsigned char *ok, const unsigned char *sig64,
+        const unsigned char *msg, size_t msglen, const unsigned char *pk, int pkfmt, size_t n);
+SECP256K1_B200_API int secp256k1_b200_multi_ecdsa_verify_batch(secp256k1_b200_multi *m, unsigned char *ok, const unsigned char *sig64, int sigfmt,
+        const unsigned char *msghash32, const unsigned char *pk, int pkfmt, size_t n);
+SECP256K1_B200_API int secp256k1_b200_multi_ecmult_batch(secp256k1_b200_multi *m, unsigned char *out64, const unsigned char *a64,
+        const unsigned char *na32, const unsigned char *ng32, size_t n);
+SECP256K1_B200_API int secp256k1_b200_multi_pedersen_commit_batch(secp256k1_b200_multi *m, unsigned char *ok, unsigned char *commit33,
+        const unsigned char *blind32, const uint64_t *value, const unsigned char *gen64, size_t gen_stride, size_t n);
+SECP256K1_B200_API int secp256k1_b200_multi_rangeproof_verify_batch(secp256k1_b200_multi *m, unsigned char *ok, uint64_t *min_value, uint64_t *max_value,
+        const unsigned char *commit33, const unsigned char *proofs, size_t proof_stride, const uint32_t *plen, const unsigned char *gen64, size_t gen_stride,
+        const unsigned char *extra, size_t extra_stride, const uint32_t *extra_len, size_t n);
+SECP256K1_B200_API int secp256k1_b200_multi_bppp_norm_verify_batch(secp256k1_b200_multi *m, unsigned char *ok, const unsigned char *proofs, size_t proof_stride,
+        const uint32_t *plen, const unsigned char *transcripts104, const unsigned char *rho32, const unsigned char *gens64, size_t g_len,
+        const unsigned char *c_vec32, size_t h_len, const unsigned char *commits64, size_t n);
+SECP256K1_B200_API int secp256k1_b200_multi_ecmult_multi(secp256k1_b200_multi *m, unsigned char *out64, const unsigned char *g_scalar32,
+        const unsigned char *scalars32, const unsigned char *points64, size_t n);
+
 /* ---- synthetic inputs for tests and benchmarks (NOT constant time; never use with real secrets) ---- */
 /* BIP-340 signatures exactly as secp256k1_schnorrsig_sign_custom(ctx, sig, msg, msglen, keypair, NULL) emits them
  * (src/modules/schnorrsig/main_impl.h:125-190), plus the x-only public keys; sk must be in [1, n-1]. */

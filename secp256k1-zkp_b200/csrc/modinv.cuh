@@ -261,9 +261,36 @@ HD void sc_inverse_safegcd(sc& r, const sc& a) {
     mi_to_words(r.v, x);
 }
 
-// what the kernels call (outlined: one body per kernel)
-HDNI void fe_inv(fe& r, const fe& a) { fe t; fe_inv_safegcd(t, a); r = t; }
-HDNI int fe_is_square(const fe& a) { return fe_is_square_jacobi(a); }
-HDNI void sc_inverse(sc& r, const sc& a) { sc t; sc_inverse_safegcd(t, a); r = t; }
+// What the kernels call.  On the device: one outlined body per kernel, operands and results BY VALUE in registers like fe_mul_nv -- never
+// a pointer into the caller's frame.  (Round 1 met two builds in which an outlined inverse taking `sc&` / holding a local table computed
+// wrong values inside kernels with large stack frames, k_bppp_norm_verify and k_rangeproof_rewind; r2d met a third: the first version of
+// these wrappers took references and k_bppp_norm_verify rejected the reference's valid vectors while every other kernel was right.
+// -DB200_INLINE_MODINV inlines them instead.)
+#if defined(__CUDACC__) && !defined(B200_INLINE_MODINV)
+static __device__ __noinline__ fe fe_inv_nv(fe a) { fe r; fe_inv_safegcd(r, a); return r; }
+static __device__ __noinline__ int fe_is_square_nv(fe a) { return fe_is_square_jacobi(a); }
+static __device__ __noinline__ sc sc_inverse_nv(sc a) { sc r; sc_inverse_safegcd(r, a); return r; }
+#endif
+HD void fe_inv(fe& r, const fe& a) {
+#if defined(__CUDA_ARCH__) && !defined(B200_INLINE_MODINV)
+    r = fe_inv_nv(a);
+#else
+    fe t; fe_inv_safegcd(t, a); r = t;
+#endif
+}
+HD int fe_is_square(const fe& a) {
+#if defined(__CUDA_ARCH__) && !defined(B200_INLINE_MODINV)
+    return fe_is_square_nv(a);
+#else
+    return fe_is_square_jacobi(a);
+#endif
+}
+HD void sc_inverse(sc& r, const sc& a) {
+#if defined(__CUDA_ARCH__) && !defined(B200_INLINE_MODINV)
+    r = sc_inverse_nv(a);
+#else
+    sc t; sc_inverse_safegcd(t, a); r = t;
+#endif
+}
 
 }  // namespace B200_NS

@@ -74,9 +74,17 @@ HD void msm_make_plan_c(msm_plan& p, size_t N, uint32_t c) {
 // On the GPU wide windows win much earlier than on a CPU: more buckets = more parallel lanes, and the bucket reduction is parallel
 // too.  Measured (tools/msm_bench.py --sweep, profiles/r2*_msm_sweep.jsonl); below 2^12 terms the MSM is latency bound (a ~128-doubling
 // chain whatever c is) and a narrow window keeps the reduction short.
+//   terms      8     88    1024  4096  16384 32768 65536 131072 262144 2^20      (ms per MSM, profiles/r2d_msm_sweep.jsonl)
+//   c = 8    0.50  0.53   0.58  0.60  0.96  1.49  1.83  2.43   3.49   7.35
+//   c = 10   0.50  0.54   0.59  0.60  0.72  0.79  1.91  3.41   4.52   8.31
+//   c = 11   0.51  0.56   0.63  0.65  0.74  0.79  0.97  2.96   5.89  10.02
+//   c = 12   0.51  0.62   0.70  0.70  0.82  0.87  1.06  1.29   4.96  11.90
+//   c = 16   0.59  0.72   0.89  0.99  1.03  1.07  1.16  1.34   1.71   3.85
 HD uint32_t msm_choose_c(size_t N) {
-    if (N < ((size_t)1 << 12)) return 8;
-    if (N < ((size_t)1 << 16)) return 13;
+    if (N < ((size_t)1 << 13)) return 8;
+    if (N < ((size_t)1 << 15)) return 10;
+    if (N < ((size_t)1 << 17)) return 11;
+    if (N < ((size_t)1 << 18)) return 12;
     return 16;
 }
 

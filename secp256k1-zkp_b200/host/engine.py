@@ -432,3 +432,123 @@ class Engine:
 
     def ecdsa_verify_dev(self, d_ok, d_sig64, sigfmt, d_msg32, d_pk, pkfmt, n, stream=0):
         self._ck(self._lib.secp256k1_b200_ecdsa_verify_batch_dev(self._h, d_ok, d_sig64, sigfmt, d_msg32, d_pk, pkfmt, n, stream))
+
+
+class MultiEngine:
+    """One process, several GPUs: ctypes mirror of the secp256k1_b200_multi_* calls (include/secp256k1_b200.h).  Host arrays are sharded by
+    contiguous index ranges over the devices inside the C library; results have the semantics of the single-engine calls."""
+
+    def __init__(self, devices=None, n_devices=0, gen_window_bits=0):
+        self._lib = load_library()
+        L, vp, sz, ci = self._lib, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+        L.secp256k1_b200_multi_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(ci), ci, ci]
+        L.secp256k1_b200_multi_destroy.argtypes = [vp]
+        L.secp256k1_b200_multi_destroy.restype = None
+        L.secp256k1_b200_multi_device_count.argtypes = [vp]
+        L.secp256k1_b200_multi_nccl_version.argtypes = [vp]
+        L.secp256k1_b200_multi_engine.argtypes = [vp, ci]
+        L.secp256k1_b200_multi_engine.restype = vp
+        L.secp256k1_b200_multi_launch_count.argtypes = [vp]
+        L.secp256k1_b200_multi_launch_count.restype = ctypes.c_uint64
+        L.secp256k1_b200_multi_schnorrsig_verify_batch.argtypes = [vp, vp, vp, vp, sz, vp, ci, sz]
+        L.secp256k1_b200_multi_ecdsa_verify_batch.argtypes = [vp, vp, vp, ci, vp, vp, ci, sz]
+        L.secp256k1_b200_multi_ecmult_batch.argtypes = [vp, vp, vp, vp, vp, sz]
+        L.secp256k1_b200_multi_pedersen_commit_batch.argtypes = [vp, vp, vp, vp, vp, vp, sz, sz]
+        L.secp256k1_b200_multi_rangeproof_verify_batch.argtypes = [vp, vp, vp, vp, vp, vp, sz, vp, vp, sz, vp, sz, vp, sz]
+        L.secp256k1_b200_multi_bppp_norm_verify_batch.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, sz, vp, sz, vp, sz]
+        L.secp256k1_b200_multi_ecmult_multi.argtypes = [vp, vp, vp, vp, vp, sz]
+        h = vp()
+        if devices is not None:
+            arr = (ci * len(devices))(*devices)
+            ok = L.secp256k1_b200_multi_create(ctypes.byref(h), arr, len(devices), gen_window_bits)
+        else:
+            ok = L.secp256k1_b200_multi_create(ctypes.byref(h), None, n_devices, gen_window_bits)
+        if not ok:
+            raise B200Error(L.secp256k1_b200_last_error().decode())
+        self._h = h
+
+    def _ck(self, ok):
+        if not ok:
+            raise B200Error(self._lib.secp256k1_b200_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.secp256k1_b200_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device_count(self):
+        return self._lib.secp256k1_b200_multi_device_count(self._h)
+
+    @property
+    def nccl_version(self):
+        return self._lib.secp256k1_b200_multi_nccl_version(self._h)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.secp256k1_b200_multi_launch_count(self._h))
+
+    def schnorrsig_verify(self, sig64, msg, pk, pkfmt=PK_XONLY32, msglen=32, out=None):
+        sig = _u8(sig64, len(sig64) if not hasattr(sig64, "size") else sig64.size, "sig64")
+        n = sig.size // 64
+        m = _u8(msg, msglen * n, "msg") if msglen else np.zeros(1, dtype=np.uint8)
+        p = _u8(pk, _PKLEN[pkfmt] * n, "pk")
+        ok = out if out is not None else np.empty(n, dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_multi_schnorrsig_verify_batch(self._h, _p(ok), _p(sig), _p(m), msglen, _p(p), pkfmt, n))
+        return ok
+
+    def ecdsa_verify(self, sig64, msghash32, pk, sigfmt=SIG_COMPACT64, pkfmt=PK_COMPRESSED33):
+        sig = _u8(sig64, len(sig64) if not hasattr(sig64, "size") else sig64.size, "sig64")
+        n = sig.size // 64
+        m = _u8(msghash32, 32 * n, "msghash32")
+        p = _u8(pk, _PKLEN[pkfmt] * n, "pk")
+        ok = np.empty(n, dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_multi_ecdsa_verify_batch(self._h, _p(ok), _p(sig), sigfmt, _p(m), _p(p), pkfmt, n))
+        return ok
+
+    def ecmult(self, a64, na32, ng32=None):
+        na = _u8(na32, len(na32) if not hasattr(na32, "size") else na32.size, "na32")
+        n = na.size // 32
+        a = _u8(a64, 64 * n, "a64")
+        ng = _u8(ng32, 32 * n, "ng32") if ng32 is not None else None
+        out = np.empty(64 * n, dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_multi_ecmult_batch(self._h, _p(out), _p(a), _p(na), _p(ng), n))
+        return out.reshape(n, 64)
+
+    def pedersen_commit(self, blind32, values, gen64):
+        b = _u8(blind32, len(blind32) if not hasattr(blind32, "size") else blind32.size, "blind32")
+        n = b.size // 32
+        v = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1)
+        g = _u8(gen64, len(gen64) if not hasattr(gen64, "size") else gen64.size, "gen64")
+        ok = np.empty(n, dtype=np.uint8)
+        out = np.zeros(33 * n, dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_multi_pedersen_commit_batch(self._h, _p(ok), _p(out), _p(b), _p(v), _p(g), 0 if g.size == 64 else 64, n))
+        return ok, out.reshape(n, 33)
+
+    def rangeproof_verify(self, commit33, proofs, plen, gen64):
+        pr = np.ascontiguousarray(proofs, dtype=np.uint8)
+        n, stride = pr.shape
+        c = _u8(commit33, 33 * n, "commit33")
+        pl = np.ascontiguousarray(plen, dtype=np.uint32).reshape(-1)
+        g = _u8(gen64, len(gen64) if not hasattr(gen64, "size") else gen64.size, "gen64")
+        ok = np.empty(n, dtype=np.uint8)
+        mn = np.zeros(n, dtype=np.uint64)
+        mx = np.zeros(n, dtype=np.uint64)
+        self._ck(self._lib.secp256k1_b200_multi_rangeproof_verify_batch(self._h, _p(ok), _p(mn), _p(mx), _p(c), _p(pr), stride, _p(pl), _p(g),
+                                                                        0 if g.size == 64 else 64, None, 0, None, n))
+        return ok, mn, mx
+
+    def ecmult_multi(self, scalars32, points64, g_scalar32=None):
+        sc = _u8(scalars32, len(scalars32) if not hasattr(scalars32, "size") else scalars32.size, "scalars32")
+        n = sc.size // 32
+        pt = _u8(points64, 64 * n, "points64")
+        g = _u8(g_scalar32, 32, "g_scalar32") if g_scalar32 is not None else None
+        out = np.zeros(64, dtype=np.uint8)
+        self._ck(self._lib.secp256k1_b200_multi_ecmult_multi(self._h, _p(out), _p(g), _p(sc) if n else None, _p(pt) if n else None, n))
+        return out.tobytes()
