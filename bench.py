@@ -341,7 +341,8 @@ def make_bppp(ref, n, seed, hi_info):
     gens = np.frombuffer(gxy.raw, dtype=np.uint8).reshape(g + h, 64).copy()
 
     def cpu_verify(lo, hi):
-        for i in range(lo, hi):
+        for j in range(lo, hi):
+            i = j % n                                                # the CPU sample may be longer than the batch
             L.ref_bppp_norm_verify(ref.ctx, proofs[i].tobytes(), ctypes.c_size_t(324), cms[i].tobytes(), rhos[i].tobytes(), gs, ctypes.c_size_t(g), cvs[i].tobytes(), ctypes.c_size_t(h))
     return proofs, rhos, cvs, cms, gens, cpu_verify
 
