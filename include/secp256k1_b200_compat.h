@@ -128,6 +128,17 @@ SECP256K1_B200_API int secp256k1_pedersen_verify_tally(const secp256k1_context *
 SECP256K1_B200_API secp256k1_b200_engine *secp256k1_b200_global_engine(void);
 SECP256K1_B200_API void secp256k1_b200_global_engine_shutdown(void);
 
+/* Opt-in coalescing of concurrent single calls (no reference counterpart).  A reference-named verification call is a batch of one on the
+ * GPU and is latency bound (~1 ms, profiles/r2_single_call_latency.md); a multi-threaded caller gets throughput instead when coalescing is
+ * on: concurrent secp256k1_schnorrsig_verify (32-byte messages), secp256k1_ecdsa_verify and secp256k1_rangeproof_verify calls are queued, the
+ * first caller that finds no flush in progress waits up to window_us microseconds (or until max_batch calls have gathered) and runs ONE
+ * batch launch for all of them; every caller gets exactly the result and callback behaviour of the direct path.  window_us = 0 turns it off
+ * (the default); max_batch = 0 keeps the current value (default 4096).  The environment variables SECP256K1_B200_COALESCE_US /
+ * SECP256K1_B200_COALESCE_MAX set the same values for programs that cannot be changed. */
+SECP256K1_B200_API int secp256k1_b200_coalesce_configure(unsigned window_us, size_t max_batch);
+/* test hook: the next `count` GPU calls issued by the reference-named functions report an engine failure (exercises the error callback) */
+SECP256K1_B200_API void secp256k1_b200_test_fail_next_gpu_calls(int count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,73 @@ void b200_set_error(const char* what) { g_last_error = what; }
 static void set_error(const char* what, cudaError_t err) { b200_set_error(what, err); }
 static void set_error(const char* what) { b200_set_error(what); }
 
+// ---- host-buffer calls: chunked, double-buffered pipeline -------------------------------------------------------------------------------
+// Every per-item batch call with host buffers runs through run_chunked(): the items are cut into chunks, chunk k uses stream (k & 1), so the
+// H2D copies of chunk k+1 overlap the kernel of chunk k and the D2H copies of chunk k-1; with pinned host buffers the call costs about one
+// kernel time plus one chunk of transfer.  Results bound for pageable host memory are staged in the engine's pinned buffer (a D2H copy into
+// pageable memory would block the host and serialize the pipeline) and copied out once at the end; pinned destinations are written directly.
+namespace {
+struct h_in { const void* host; size_t item; };          // one input array, `item` bytes per item (host == nullptr: absent)
+struct h_out { void* host; size_t item; };
+static bool host_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+// launch(lo, m, din, dout, stream): enqueue the kernels for items [lo, lo + m); din[i] / dout[i] point at item lo of array i (nullptr if absent)
+template <class Launch>
+static int run_chunked(secp256k1_b200_engine* e, carver& c, const h_in* ins, int nin, const h_out* outs, int nout, size_t n, Launch launch) {
+    size_t oin[8], oout[8], stage_off[8], in_bytes = 0, stage_total = 0;
+    bool staged[8];
+    for (int i = 0; i < nin; i++) { oin[i] = c.add(ins[i].item * n + 16); in_bytes += ins[i].host ? ins[i].item : 0; }
+    for (int i = 0; i < nout; i++) {
+        oout[i] = c.add(outs[i].item * n + 16);
+        staged[i] = !host_pinned(outs[i].host);
+        stage_off[i] = stage_total;
+        if (staged[i]) stage_total += (outs[i].item * n + 63) & ~(size_t)63;
+    }
+    if (!c.commit()) return 0;
+    if (stage_total > e->pinned_bytes) {
+        if (e->h_pinned) cudaFreeHost(e->h_pinned);
+        e->h_pinned = nullptr; e->pinned_bytes = 0;
+        CK(cudaHostAlloc((void**)&e->h_pinned, stage_total + (stage_total >> 2), cudaHostAllocDefault));
+        e->pinned_bytes = stage_total + (stage_total >> 2);
+    }
+    size_t chunk = ((size_t)16 << 20) / (in_bytes ? in_bytes : 1);          // ~16 MiB of input per chunk ...
+    if (n >= 65536 && chunk > (n + 3) / 4) chunk = (n + 3) / 4;             // ... but at least four chunks of a large batch (something to overlap)
+    chunk = (chunk + 255) & ~(size_t)255;                                   // multiples of 256 items keep every sub-array 16-byte aligned
+    if (chunk < 1024) chunk = 1024;
+    if (chunk > n) chunk = n;
+    cudaStream_t st[2] = {e->stream, e->stream2};
+    int k = 0;
+    for (size_t lo = 0; lo < n; lo += chunk, k ^= 1) {
+        const size_t m = n - lo < chunk ? n - lo : chunk;
+        cudaStream_t sk = st[k];
+        uint8_t* din[8]; uint8_t* dout[8];
+        for (int i = 0; i < nin; i++) {
+            din[i] = ins[i].host ? c.at(oin[i]) + ins[i].item * lo : nullptr;
+            if (ins[i].host) CK(cudaMemcpyAsync(din[i], (const uint8_t*)ins[i].host + ins[i].item * lo, ins[i].item * m, cudaMemcpyHostToDevice, sk));
+        }
+        for (int i = 0; i < nout; i++) dout[i] = c.at(oout[i]) + outs[i].item * lo;
+        if (!launch(lo, m, din, dout, sk)) return 0;
+        for (int i = 0; i < nout; i++) {
+            uint8_t* dst = staged[i] ? e->h_pinned + stage_off[i] + outs[i].item * lo : (uint8_t*)outs[i].host + outs[i].item * lo;
+            CK(cudaMemcpyAsync(dst, dout[i], outs[i].item * m, cudaMemcpyDeviceToHost, sk));
+        }
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaStreamSynchronize(e->stream2));
+    for (int i = 0; i < nout; i++) if (staged[i]) memcpy(outs[i].host, e->h_pinned + stage_off[i], outs[i].item * n);
+    return 1;
+}
+// small inputs shared by the whole batch (a generator, ...): copied once, visible to both streams
+static int upload_shared(secp256k1_b200_engine* e, uint8_t* dst, const void* src, size_t bytes) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 1;
+}
+}  // namespace
+
 extern "C" {
 
 const char* secp256k1_b200_last_error(void) { return g_last_error.c_str(); }
@@ -177,15 +244,11 @@ int secp256k1_b200_ecmult_batch(secp256k1_b200_engine* e, unsigned char* out64, 
     std::lock_guard<std::mutex> lock(e->mu);
     device_guard guard(e->device);
     carver c(e);
-    size_t oa = c.add(64 * n), ona = c.add(32 * n), ong = c.add(32 * n), oo = c.add(64 * n);
-    if (!c.commit()) return 0;
-    CK(cudaMemcpyAsync(c.at(oa), a64, 64 * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(c.at(ona), na32, 32 * n, cudaMemcpyHostToDevice, e->stream));
-    if (ng32) CK(cudaMemcpyAsync(c.at(ong), ng32, 32 * n, cudaMemcpyHostToDevice, e->stream));
-    if (!secp256k1_b200_ecmult_batch_dev(e, c.at(oo), c.at(oa), c.at(ona), ng32 ? c.at(ong) : nullptr, n, e->stream)) return 0;
-    CK(cudaMemcpyAsync(out64, c.at(oo), 64 * n, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    return 1;
+    const h_in ins[3] = {{a64, 64}, {na32, 32}, {ng32, 32}};
+    const h_out outs[1] = {{out64, 64}};
+    return run_chunked(e, c, ins, 3, outs, 1, n, [&](size_t, size_t m, uint8_t* const* din, uint8_t* const* dout, cudaStream_t s) {
+        return secp256k1_b200_ecmult_batch_dev(e, dout[0], din[0], din[1], din[2], m, s);
+    });
 }
 
 /* ---- Schnorr --------------------------------------------------------------------------------------- */
@@ -209,33 +272,14 @@ int secp256k1_b200_schnorrsig_verify_batch(secp256k1_b200_engine* e, unsigned ch
     std::lock_guard<std::mutex> lock(e->mu);
     device_guard guard(e->device);
     carver c(e);
-    size_t pl = pk_len(pkfmt);
-    size_t os = c.add(64 * n), om = c.add(msglen * n + 16), op = c.add(pl * n), oo = c.add(n);
-    if (!c.commit()) return 0;
-    // chunked + double-buffered: the copies of chunk k+1 (stream B) overlap the kernel of chunk k (stream A); with pinned
-    // host buffers the whole call costs ~one kernel time + one chunk of transfer instead of kernel + full transfer
-    if (n > e->pinned_bytes) {
-        if (e->h_pinned) cudaFreeHost(e->h_pinned);
-        e->h_pinned = nullptr; e->pinned_bytes = 0;
-        CK(cudaHostAlloc((void**)&e->h_pinned, n + (n >> 2), cudaHostAllocDefault));
-        e->pinned_bytes = n + (n >> 2);
-    }
-    const size_t chunk = n > (1u << 17) ? ((size_t)1 << 17) : n;
-    cudaStream_t st[2] = {e->stream, e->stream2};
-    int k = 0;
-    for (size_t lo = 0; lo < n; lo += chunk, k ^= 1) {
-        size_t m = n - lo < chunk ? n - lo : chunk;
-        cudaStream_t s = st[k];
-        CK(cudaMemcpyAsync(c.at(os) + 64 * lo, sig64 + 64 * lo, 64 * m, cudaMemcpyHostToDevice, s));
-        if (msglen) CK(cudaMemcpyAsync(c.at(om) + msglen * lo, msg + msglen * lo, msglen * m, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(c.at(op) + pl * lo, pk + pl * lo, pl * m, cudaMemcpyHostToDevice, s));
-        if (!secp256k1_b200_schnorrsig_verify_batch_dev(e, c.at(oo) + lo, c.at(os) + 64 * lo, c.at(om) + msglen * lo, msglen, c.at(op) + pl * lo, pkfmt, m, s)) return 0;
-        CK(cudaMemcpyAsync(e->h_pinned + lo, c.at(oo) + lo, m, cudaMemcpyDeviceToHost, s));
-    }
-    CK(cudaStreamSynchronize(e->stream));
-    CK(cudaStreamSynchronize(e->stream2));
-    memcpy(ok, e->h_pinned, n);
-    return 1;
+    const h_in ins[3] = {{sig64, 64}, {msglen ? msg : nullptr, msglen}, {pk, pk_len(pkfmt)}};
+    const h_out outs[1] = {{ok, 1}};
+    uint8_t* dummy = nullptr;                                  // msglen = 0: the kernel still wants a valid message pointer
+    size_t od = c.add(16);
+    return run_chunked(e, c, ins, 3, outs, 1, n, [&](size_t, size_t m, uint8_t* const* din, uint8_t* const* dout, cudaStream_t s) {
+        dummy = c.at(od);
+        return secp256k1_b200_schnorrsig_verify_batch_dev(e, dout[0], din[0], din[1] ? din[1] : dummy, msglen, din[2], pkfmt, m, s);
+    });
 }
 
 /* ---- synthetic inputs (tests / benchmarks only) ---------------------------------------------------- */
@@ -295,16 +339,11 @@ int secp256k1_b200_ecdsa_verify_batch(secp256k1_b200_engine* e, unsigned char* o
     std::lock_guard<std::mutex> lock(e->mu);
     device_guard guard(e->device);
     carver c(e);
-    size_t pl = pk_len(pkfmt);
-    size_t os = c.add(64 * n), om = c.add(32 * n), op = c.add(pl * n), oo = c.add(n);
-    if (!c.commit()) return 0;
-    CK(cudaMemcpyAsync(c.at(os), sig64, 64 * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(c.at(om), msghash32, 32 * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(c.at(op), pk, pl * n, cudaMemcpyHostToDevice, e->stream));
-    if (!secp256k1_b200_ecdsa_verify_batch_dev(e, c.at(oo), c.at(os), sigfmt, c.at(om), c.at(op), pkfmt, n, e->stream)) return 0;
-    CK(cudaMemcpyAsync(ok, c.at(oo), n, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    return 1;
+    const h_in ins[3] = {{sig64, 64}, {msghash32, 32}, {pk, pk_len(pkfmt)}};
+    const h_out outs[1] = {{ok, 1}};
+    return run_chunked(e, c, ins, 3, outs, 1, n, [&](size_t, size_t m, uint8_t* const* din, uint8_t* const* dout, cudaStream_t s) {
+        return secp256k1_b200_ecdsa_verify_batch_dev(e, dout[0], din[0], sigfmt, din[1], din[2], pkfmt, m, s);
+    });
 }
 
 int secp256k1_b200_ecdsa_recover_batch_dev(secp256k1_b200_engine* e, unsigned char* d_ok, unsigned char* d_pubkey64, const unsigned char* d_sig64,
@@ -321,16 +360,11 @@ int secp256k1_b200_ecdsa_recover_batch(secp256k1_b200_engine* e, unsigned char* 
     std::lock_guard<std::mutex> lock(e->mu);
     device_guard guard(e->device);
     carver c(e);
-    size_t os = c.add(64 * n), om = c.add(32 * n), orr = c.add(n), oo = c.add(n), op = c.add(64 * n);
-    if (!c.commit()) return 0;
-    CK(cudaMemcpyAsync(c.at(os), sig64, 64 * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(c.at(om), msghash32, 32 * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(c.at(orr), recid, n, cudaMemcpyHostToDevice, e->stream));
-    if (!secp256k1_b200_ecdsa_recover_batch_dev(e, c.at(oo), c.at(op), c.at(os), c.at(orr), c.at(om), n, e->stream)) return 0;
-    CK(cudaMemcpyAsync(ok, c.at(oo), n, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaMemcpyAsync(pubkey64, c.at(op), 64 * n, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    return 1;
+    const h_in ins[3] = {{sig64, 64}, {msghash32, 32}, {recid, 1}};
+    const h_out outs[2] = {{ok, 1}, {pubkey64, 64}};
+    return run_chunked(e, c, ins, 3, outs, 2, n, [&](size_t, size_t m, uint8_t* const* din, uint8_t* const* dout, cudaStream_t s) {
+        return secp256k1_b200_ecdsa_recover_batch_dev(e, dout[0], dout[1], din[0], din[2], din[1], m, s);
+    });
 }
 
 /* ---- multi-scalar multiplication (Pippenger) ------------------------------------------------------------ */
@@ -615,17 +649,14 @@ int secp256k1_b200_pedersen_commit_batch(secp256k1_b200_engine* e, unsigned char
     std::lock_guard<std::mutex> lock(e->mu);
     device_guard guard(e->device);
     carver c(e);
-    size_t gbytes = gen_stride ? gen_stride * n : 64;
-    size_t ob = c.add(32 * n), ov = c.add(8 * n), og = c.add(gbytes), ook = c.add(n), oc = c.add(33 * n);
-    if (!c.commit()) return 0;
-    CK(cudaMemcpyAsync(c.at(ob), blind32, 32 * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(c.at(ov), value, 8 * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(c.at(og), gen64, gbytes, cudaMemcpyHostToDevice, e->stream));
-    if (!secp256k1_b200_pedersen_commit_batch_dev(e, c.at(ook), c.at(oc), c.at(ob), (const uint64_t*)c.at(ov), c.at(og), gen_stride, n, e->stream)) return 0;
-    CK(cudaMemcpyAsync(ok, c.at(ook), n, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaMemcpyAsync(commit33, c.at(oc), 33 * n, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    return 1;
+    const size_t og = c.add(64);
+    const h_in ins[3] = {{blind32, 32}, {value, 8}, {gen_stride ? gen64 : nullptr, gen_stride}};
+    const h_out outs[2] = {{ok, 1}, {commit33, 33}};
+    bool shared_up = false;
+    return run_chunked(e, c, ins, 3, outs, 2, n, [&](size_t, size_t m, uint8_t* const* din, uint8_t* const* dout, cudaStream_t s) {
+        if (!gen_stride && !shared_up) { if (!upload_shared(e, c.at(og), gen64, 64)) return 0; shared_up = true; }
+        return secp256k1_b200_pedersen_commit_batch_dev(e, dout[0], dout[1], din[0], (const uint64_t*)din[1], gen_stride ? din[2] : c.at(og), gen_stride, m, s);
+    });
 }
 
 int secp256k1_b200_rangeproof_verify_batch_dev(secp256k1_b200_engine* e, unsigned char* d_ok, uint64_t* d_min_value, uint64_t* d_max_value,
@@ -653,28 +684,17 @@ int secp256k1_b200_rangeproof_verify_batch(secp256k1_b200_engine* e, unsigned ch
     std::lock_guard<std::mutex> lock(e->mu);
     device_guard guard(e->device);
     carver c(e);
-    size_t gbytes = gen_stride ? gen_stride * n : 64;
-    bool has_extra = extra && extra_len && extra_stride;
-    size_t oc = c.add(33 * n), op = c.add(proof_stride * n), ol = c.add(4 * n), og = c.add(gbytes);
-    size_t oe = c.add(has_extra ? extra_stride * n : 16), oel = c.add(4 * n);
-    size_t ook = c.add(n), omn = c.add(8 * n), omx = c.add(8 * n);
-    if (!c.commit()) return 0;
-    CK(cudaMemcpyAsync(c.at(oc), commit33, 33 * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(c.at(op), proofs, proof_stride * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(c.at(ol), plen, 4 * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(c.at(og), gen64, gbytes, cudaMemcpyHostToDevice, e->stream));
-    if (has_extra) {
-        CK(cudaMemcpyAsync(c.at(oe), extra, extra_stride * n, cudaMemcpyHostToDevice, e->stream));
-        CK(cudaMemcpyAsync(c.at(oel), extra_len, 4 * n, cudaMemcpyHostToDevice, e->stream));
-    }
-    if (!secp256k1_b200_rangeproof_verify_batch_dev(e, c.at(ook), (uint64_t*)c.at(omn), (uint64_t*)c.at(omx), c.at(oc), c.at(op), proof_stride,
-                                                    (const uint32_t*)c.at(ol), c.at(og), gen_stride, has_extra ? c.at(oe) : nullptr, extra_stride,
-                                                    has_extra ? (const uint32_t*)c.at(oel) : nullptr, n, e->stream)) return 0;
-    CK(cudaMemcpyAsync(ok, c.at(ook), n, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaMemcpyAsync(min_value, c.at(omn), 8 * n, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaMemcpyAsync(max_value, c.at(omx), 8 * n, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    return 1;
+    const bool has_extra = extra && extra_len && extra_stride;
+    const size_t og = c.add(64);
+    const h_in ins[6] = {{commit33, 33}, {proofs, proof_stride}, {plen, 4}, {gen_stride ? gen64 : nullptr, gen_stride},
+                         {has_extra ? extra : nullptr, extra_stride}, {has_extra ? extra_len : nullptr, 4}};
+    const h_out outs[3] = {{ok, 1}, {min_value, 8}, {max_value, 8}};
+    bool shared_up = false;
+    return run_chunked(e, c, ins, 6, outs, 3, n, [&](size_t, size_t m, uint8_t* const* din, uint8_t* const* dout, cudaStream_t s) {
+        if (!gen_stride && !shared_up) { if (!upload_shared(e, c.at(og), gen64, 64)) return 0; shared_up = true; }
+        return secp256k1_b200_rangeproof_verify_batch_dev(e, dout[0], (uint64_t*)dout[1], (uint64_t*)dout[2], din[0], din[1], proof_stride, (const uint32_t*)din[2],
+                                                          gen_stride ? din[3] : c.at(og), gen_stride, din[4], extra_stride, (const uint32_t*)din[5], m, s);
+    });
 }
 
 /* ---- range-proof rewinding: verify (one warp per proof, challenges kept) + replay (one thread per proof) ---- */
