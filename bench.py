@@ -377,7 +377,8 @@ def run_extra_workloads(ctx, peaks, ref, hi_info, want_cpu):
     res = torch.empty((n, 64), dtype=torch.uint8, device=dev)
     ms = time_dev(ctx, lambda: eng.ecmult_dev(res.data_ptr(), pts.data_ptr(), na.data_ptr(), ng.data_ptr(), n, stream))
     tp, hp = pinned(torch, pts.cpu().numpy()); tn, hn = pinned(torch, na.cpu().numpy()); tg, hg = pinned(torch, ng.cpu().numpy())
-    e2e_ms, hres = time_host(ctx, lambda: eng.ecmult(hp, hn, hg))
+    tout = torch.empty((n, 64), dtype=torch.uint8).pin_memory()                       # pinned result buffer: D2H copies land in it directly
+    e2e_ms, hres = time_host(ctx, lambda: eng.ecmult(hp, hn, hg, out=tout.numpy()))
     entry = {"items": n * world, "per_gpu": n, "scaling": "weak", "e2e_matches_device": bool(np.array_equal(hres, res.cpu().numpy()))}
     cpu = None
     if want_cpu:
@@ -387,7 +388,7 @@ def run_extra_workloads(ctx, peaks, ref, hi_info, want_cpu):
         cpu = cpu_leg(hi_info, lambda lo, hi: ref.ecmult_batch(hp[lo:hi].tobytes(), hn[lo:hi].tobytes(), hg[lo:hi].tobytes()), "ecmult/s", 4096, 1024,
                       "reference secp256k1_ecmult a*P + b*G (what bench_ecmult's ecmult_1p_g row times twice per iteration, src/bench_ecmult.c:184-191)")
     finish("ecmult", entry, n * world, ms, "ecmult_per_s", e2e_ms, 128 * n, 64 * n, MAC_PER_ECMULT, n, cpu, "secp256k1_b200_ecmult_batch")
-    del res, na, ng, z64, z32, tp, tn, tg
+    del res, na, ng, z64, z32, tp, tn, tg, tout
 
     # ---- config 3: Pippenger 2^20-term MSM, strong scaling: rank r owns terms [r*N/W, (r+1)*N/W), partial sums all-gathered --------------
     n_total = 1 << 20
@@ -489,7 +490,8 @@ def run_extra_workloads(ctx, peaks, ref, hi_info, want_cpu):
     okc = torch.zeros(nb, dtype=torch.uint8, device=dev); cm33 = torch.zeros((nb, 33), dtype=torch.uint8, device=dev)
     ms = time_dev(ctx, lambda: eng.pedersen_commit_dev(okc.data_ptr(), cm33.data_ptr(), bl.data_ptr(), vt.data_ptr(), g64.data_ptr(), 0, nb, stream), warm=1, reps=3)
     tb, hb = pinned(torch, np.tile(blinds_h, (reps_c, 1)))
-    e2e_ms, hcres = time_host(ctx, lambda: eng.pedersen_commit(hb, vv, genh))
+    tco = torch.empty((nb, 33), dtype=torch.uint8).pin_memory()
+    e2e_ms, hcres = time_host(ctx, lambda: eng.pedersen_commit(hb, vv, genh, out=tco.numpy()))
     entry = {"commitments": nb * world, "per_gpu": nb, "scaling": "weak", "all_ok": bool(okc.all()),
              "reproduces_prover_commitments": bool(np.array_equal(cm33[:per].cpu().numpy(), commits_h)),
              "e2e_matches_device": bool(np.array_equal(hcres[1], cm33.cpu().numpy()))}
@@ -541,7 +543,10 @@ def run_extra_workloads(ctx, peaks, ref, hi_info, want_cpu):
     okc = torch.empty(per, dtype=torch.uint8, device=dev); rec = torch.empty((per, 64), dtype=torch.uint8, device=dev)
     ms = time_dev(ctx, lambda: eng.ecdsa_recover_dev(okc.data_ptr(), rec.data_ptr(), rsig.data_ptr(), rid.data_ptr(), msg.data_ptr(), per, stream), warm=1, reps=3)
     h_sig, h_msg, h_rid = rsig.cpu().numpy(), msg.cpu().numpy(), rid.cpu().numpy()
-    e2e_ms, hrec = time_host(ctx, lambda: eng.ecdsa_recover(h_sig, h_rid, h_msg))
+    trec = torch.empty((per, 64), dtype=torch.uint8).pin_memory()
+    ths, thm = rsig.cpu().pin_memory(), msg.cpu().pin_memory()
+    h_sig, h_msg = ths.numpy(), thm.numpy()
+    e2e_ms, hrec = time_host(ctx, lambda: eng.ecdsa_recover(h_sig, h_rid, h_msg, out=trec.numpy()))
     finish("ecdsa_recover", {"signatures": per * world, "per_gpu": per, "scaling": "weak", "all_recovered": bool(okc.all()),
                              "e2e_matches_device": bool(np.array_equal(hrec[1], rec.cpu().numpy()))},
            per * world, ms, "recover_per_s", e2e_ms, per * 97, per * 65, MAC_PER_ECMULT, per, None, "secp256k1_b200_ecdsa_recover_batch")

@@ -201,7 +201,7 @@ void secp256k1_selftest(void) {
     // src/selftest.h:12-34: a SHA-256 known-answer test, and abort through the default error callback when it fails.  Same test on the host
     // hash used by this layer; when a B200 is usable the device is put through known answers too: 1*G, 2*G by doubling and by the generator
     // table, and a BIP-340 verification (vector 0 of the BIP) -- a miscompiled or mis-installed library fails here, not in a consensus check.
-    static const char* input63 = "For this test, this 63-byte string will be used as input data";
+    static const char* input63 = "For this sample, this 63-byte string will be used as input data";
     static const unsigned char output32[32] = {0xf0, 0x8a, 0x78, 0xcb, 0xba, 0xee, 0x08, 0x2b, 0x05, 0x2a, 0xe0, 0x70, 0x8f, 0x32, 0xfa, 0x1e,
                                                0x50, 0xc5, 0xc4, 0x21, 0xaa, 0x77, 0x2b, 0xa5, 0xdb, 0xb4, 0x06, 0xa2, 0xea, 0x6b, 0xe3, 0x42};
     unsigned char out[32];

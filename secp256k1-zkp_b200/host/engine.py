@@ -177,12 +177,13 @@ class Engine:
         self._ck(self._lib.secp256k1_b200_fe_op_batch(self._h, op, _p(out), _p(a), _p(b), n, iters))
         return out.reshape(n, 32)
 
-    def ecmult(self, a64, na32, ng32=None):
+    def ecmult(self, a64, na32, ng32=None, out=None):
+        """out: optional preallocated uint8 array of 64*n bytes (e.g. a view of pinned memory: written by the D2H copies directly)"""
         na = _u8(na32, len(na32) if not hasattr(na32, "size") else na32.size, "na32")
         n = na.size // 32
         a = _u8(a64, 64 * n, "a64")
         ng = _u8(ng32, 32 * n, "ng32") if ng32 is not None else None
-        out = np.empty(64 * n, dtype=np.uint8)
+        out = np.empty(64 * n, dtype=np.uint8) if out is None else out.reshape(-1)
         self._ck(self._lib.secp256k1_b200_ecmult_batch(self._h, _p(out), _p(a), _p(na), _p(ng), n))
         return out.reshape(n, 64)
 
@@ -242,14 +243,14 @@ class Engine:
     def schnorrsig_aggverify_dev(self, d_ok, d_pk32, d_msgs32, n, d_aggsig, d_ws, ws_bytes, stream=0):
         self._ck(self._lib.secp256k1_b200_schnorrsig_aggverify_dev(self._h, d_ok, d_pk32, d_msgs32, n, d_aggsig, d_ws, ws_bytes, stream))
 
-    def ecdsa_recover(self, sig64, recid, msghash32):
+    def ecdsa_recover(self, sig64, recid, msghash32, out=None):
         """(ok[n], pubkey64[n,64]) -- secp256k1_ecdsa_recover on compact signatures + recovery ids"""
         sig = _u8(sig64, len(sig64) if not hasattr(sig64, "size") else sig64.size, "sig64")
         n = sig.size // 64
         rid = _u8(recid, n, "recid")
         m = _u8(msghash32, 32 * n, "msghash32")
         ok = np.empty(n, dtype=np.uint8)
-        out = np.empty((n, 64), dtype=np.uint8)
+        out = np.empty((n, 64), dtype=np.uint8) if out is None else out.reshape(n, 64)
         self._ck(self._lib.secp256k1_b200_ecdsa_recover_batch(self._h, _p(ok), _p(out), _p(sig), _p(rid), _p(m), n))
         return ok, out
 
@@ -351,8 +352,8 @@ class Engine:
         self._ck(self._lib.secp256k1_b200_pedersen_verify_tally_batch(self._h, _p(ok), _p(p), _p(po), _p(q), _p(no), n))
         return ok
 
-    def pedersen_commit(self, blind32, values, gen64):
-        """gen64: 64 bytes (shared) or n*64 bytes (one generator per item)"""
+    def pedersen_commit(self, blind32, values, gen64, out=None):
+        """gen64: 64 bytes (shared) or n*64 bytes (one generator per item); out: optional preallocated 33*n uint8 array"""
         b = _u8(blind32, len(blind32) if not hasattr(blind32, "size") else blind32.size, "blind32")
         n = b.size // 32
         v = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1)
@@ -363,7 +364,7 @@ class Engine:
         if stride and g.size != 64 * n:
             raise ValueError("gen64: expected 64 or %d bytes" % (64 * n))
         ok = np.empty(n, dtype=np.uint8)
-        out = np.empty(33 * n, dtype=np.uint8)
+        out = np.empty(33 * n, dtype=np.uint8) if out is None else out.reshape(-1)
         self._ck(self._lib.secp256k1_b200_pedersen_commit_batch(self._h, _p(ok), _p(out), _p(b), _p(v), _p(g), stride, n))
         return ok, out.reshape(n, 33)
 

@@ -62,3 +62,12 @@ def test_halfagg_randomizer_chain_host_paths():
             th = hashlib.sha256(b"HalfAgg/randomizer").digest()
             h = hashlib.sha256(th + th + b"".join(agg[32 * i:32 * i + 32] + pk[32 * i:32 * i + 32] + msg[32 * i:32 * i + 32] for i in range(2)))
             assert want.raw[32:64] == h.digest() and want.raw[:32] == (1).to_bytes(32, "big")
+
+
+def test_selftest_host_part_runs_without_a_device():
+    """secp256k1_selftest (src/selftest.h:12-34): the SHA-256 known-answer test runs on the host whether or not a GPU is present; a wrong
+    digest would abort the process through the default error callback.  (With a B200 the same call also runs device known answers.)"""
+    import secp256k1_zkp_b200 as b200
+    lib = ctypes.CDLL(b200.library_path())
+    lib.secp256k1_selftest.restype = None
+    lib.secp256k1_selftest()
