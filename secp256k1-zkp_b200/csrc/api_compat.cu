@@ -4,6 +4,7 @@
 // code is reused.
 #include "../../include/secp256k1_b200_compat.h"
 #include "sha256.cuh"
+#include "rp_getheader.cuh"
 
 #include <chrono>
 #include <condition_variable>
@@ -682,36 +683,8 @@ int secp256k1_rangeproof_info(const secp256k1_context* ctx, int* exp, int* manti
     ARG_CHECK(min_value != NULL);
     ARG_CHECK(max_value != NULL);
     ARG_CHECK(proof != NULL);
-    // header decoding is byte parsing only (rangeproof_impl.h:487-538): restated here for the host
-    size_t offset = 0;
-    if (plen < 65 || (proof[0] & 128) != 0) return 0;
-    int has_nz_range = proof[0] & 64, has_min = proof[0] & 32;
-    *exp = -1;
-    *mantissa = 0;
-    if (has_nz_range) {
-        *exp = proof[0] & 31;
-        offset += 1;
-        if (*exp > 18) return 0;
-        *mantissa = proof[offset] + 1;
-        if (*mantissa > 64) return 0;
-        *max_value = UINT64_MAX >> (64 - *mantissa);
-    } else {
-        *max_value = 0;
-    }
-    offset += 1;
-    for (int i = 0; i < *exp; i++) {
-        if (*max_value > UINT64_MAX / 10) return 0;
-        *max_value *= 10;
-    }
-    *min_value = 0;
-    if (has_min) {
-        if (plen - offset < 8) return 0;
-        for (int i = 0; i < 8; i++) *min_value = (*min_value << 8) | proof[offset + i];
-        offset += 8;
-    }
-    if (*max_value > UINT64_MAX - *min_value) return 0;
-    *max_value += *min_value;
-    return 1;
+    size_t offset; uint64_t scale;
+    return rp_getheader(offset, *exp, *mantissa, scale, *min_value, *max_value, proof, plen);   // the decoder the kernels use (rp_getheader.cuh)
 }
 int secp256k1_rangeproof_verify(const secp256k1_context* ctx, uint64_t* min_value, uint64_t* max_value, const secp256k1_pedersen_commitment* commit,
                                 const unsigned char* proof, size_t plen, const unsigned char* extra_commit, size_t extra_commit_len, const secp256k1_generator* gen) {

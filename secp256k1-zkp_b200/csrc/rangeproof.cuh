@@ -15,6 +15,7 @@
 //   P5  lane 0 hashes the 32 ring results and compares with e0
 // The pieces are HD functions so that the CPU tier can run the identical logic lane by lane.
 #pragma once
+#include "rp_getheader.cuh"
 #include "ecmult.cuh"
 #include "sha256.cuh"
 
@@ -35,35 +36,8 @@ struct rp_header {
 // rangeproof_impl.h:487-538 + ring layout / length / padding checks (:566-603, :634-646 length part).
 // min/max are written exactly when the reference writes them (also on later failure).
 HD int rp_parse_header(rp_header& h, uint64_t& min_value, uint64_t& max_value, const uint8_t* proof, size_t plen) {
-    size_t offset = 0;
-    if (plen < 65 || (proof[0] & 128) != 0) return 0;
-    int has_nz_range = proof[0] & 64, has_min = proof[0] & 32;
-    h.exp = -1; h.mantissa = 0;
-    if (has_nz_range) {
-        h.exp = proof[0] & 31;
-        offset += 1;
-        if (h.exp > 18) return 0;
-        h.mantissa = proof[offset] + 1;
-        if (h.mantissa > 64) return 0;
-        max_value = UINT64_MAX >> (64 - h.mantissa);
-    } else {
-        max_value = 0;
-    }
-    offset += 1;
-    h.scale = 1;
-    for (int i = 0; i < h.exp; i++) {
-        if (max_value > UINT64_MAX / 10) return 0;
-        max_value *= 10;
-        h.scale *= 10;
-    }
-    min_value = 0;
-    if (has_min) {
-        if (plen - offset < 8) return 0;
-        for (int i = 0; i < 8; i++) min_value = (min_value << 8) | proof[offset + i];
-        offset += 8;
-    }
-    if (max_value > UINT64_MAX - min_value) return 0;
-    max_value += min_value;
+    size_t offset;
+    if (!rp_getheader(offset, h.exp, h.mantissa, h.scale, min_value, max_value, proof, plen)) return 0;
     h.min_value = min_value; h.max_value = max_value;
     h.rings = 1; h.last_rsize = 1; h.npub = 1;
     if (h.mantissa != 0) {

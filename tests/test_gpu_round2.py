@@ -295,6 +295,126 @@ def test_offcurve_key_does_not_poison_its_block(engine, ref):
     assert np.array_equal(out[mask], clean[mask])
 
 
+# ---- range proofs: every mantissa, and a large batch of DISTINCT 64-bit proofs, item by item against the reference ---------------------
+def _threaded(fn, n, threads=16):
+    import threading
+    per = (n + threads - 1) // threads
+    ts = [threading.Thread(target=fn, args=(t * per, min(n, (t + 1) * per))) for t in range(threads) if t * per < n]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+
+
+def test_rangeproof_every_mantissa_and_4096_distinct(engine, ref):
+    gen = ref.generator_h()
+    # (a) mantissa 1..64 (ring counts 1..32, odd mantissas end in a 2-member ring), 8 proofs each, half of them damaged
+    proofs, plens, commits = [], [], []
+    for m in range(1, 65):
+        blinds = b"".join(hashlib.sha256(b"mant-b%d-%d" % (m, i)).digest() for i in range(8))
+        vals = [int.from_bytes(hashlib.sha256(b"mant-v%d-%d" % (m, i)).digest()[:8], "little") % (1 << m) for i in range(8)]
+        p, pl, c = ref.rangeproof_make(blinds, vals, gen, min_bits=m)
+        proofs.append(p); plens.append(pl); commits.append(c)
+    proofs = np.concatenate(proofs); plens = np.concatenate(plens); commits = np.concatenate(commits)
+    n = proofs.shape[0]
+    for i in range(1, n, 2):
+        off = int.from_bytes(hashlib.sha256(b"mant-flip%d" % i).digest()[:4], "big") % (8 * int(plens[i]))
+        proofs[i, off // 8] ^= 1 << (off % 8)
+    ok, mn, mx = engine.rangeproof_verify(commits, proofs, plens, gen)
+    eok, emn, emx = ref.rangeproof_verify(commits, proofs, plens, gen)
+    hdr_ok = np.array([(int(p[0]) & 128) == 0 for p in proofs])           # a rejected header leaves min / max unspecified in the reference
+    assert np.array_equal(ok, eok)
+    assert np.array_equal(mn[hdr_ok & (eok == 1)], emn[hdr_ok & (eok == 1)]) and np.array_equal(mx[hdr_ok & (eok == 1)], emx[hdr_ok & (eok == 1)])
+    assert int(eok[0::2].sum()) == n // 2 and len(set(int(x) for x in plens)) >= 32
+    # (b) 4096 distinct 64-bit proofs (SURVEY 8d config 4 at one sixteenth), 1/8 with one flipped bit
+    n = 4096
+    blinds = [hashlib.sha256(b"rp-b" + i.to_bytes(4, "little")).digest() for i in range(n)]
+    vals = [int.from_bytes(hashlib.sha256(b"rp-v" + i.to_bytes(4, "little")).digest()[:8], "little") for i in range(n)]
+    P_ = np.zeros((n, 5126), dtype=np.uint8); C_ = np.zeros((n, 33), dtype=np.uint8)
+
+    def sign(lo, hi):
+        p, pl, c = ref.rangeproof_make(b"".join(blinds[lo:hi]), vals[lo:hi], gen, stride=5126)
+        P_[lo:hi] = p; C_[lo:hi] = c
+    _threaded(sign, n)
+    for i in range(3, n, 8):
+        off = int.from_bytes(hashlib.sha256(b"%d" % i).digest()[:4], "big") % (8 * 5126)
+        P_[i, off // 8] ^= 1 << (off % 8)
+    pl = np.full(n, 5126, dtype=np.uint64)
+    ok, mn, mx = engine.rangeproof_verify(C_, P_, pl, gen)
+    eok = np.zeros(n, dtype=np.uint8); emx = np.zeros(n, dtype=np.uint64)
+
+    def check(lo, hi):
+        a, _, c = ref.rangeproof_verify(C_[lo:hi], P_[lo:hi], pl[lo:hi], gen)
+        eok[lo:hi] = a; emx[lo:hi] = c
+    _threaded(check, n)
+    assert np.array_equal(ok, eok) and int(eok.sum()) >= n - len(range(3, n, 8)) - 2 and int(eok.sum()) < n
+    assert np.array_equal(mx[eok == 1], emx[eok == 1])
+    okc, cg = engine.pedersen_commit(b"".join(blinds), vals, gen)          # the same (blind, value) pairs through the batched commit
+    assert okc.all() and np.array_equal(cg, C_)
+
+
+# ---- batched parsing / serialization: every format of secp256k1_b200_point_codec_batch at scale -----------------------
+def test_point_codec_batch_all_formats_vs_reference_parsers(engine, ref):
+    import ctypes
+    L = ref.lib
+    n = 100000
+    rnd = random.Random(41)
+    ks = [rnd.getrandbits(256) % N or 1 for _ in range(4096)]
+    pool = _points(ref, ks)                                            # valid affine points
+    idx = np.array([rnd.randrange(4096) for _ in range(n)])
+    xs = pool[idx, :32].copy(); ys = pool[idx, 32:].copy()
+    parity = (ys[:, 31] & 1).astype(np.uint8)
+    bad_kind = np.array([i % 10 for i in range(n)])                    # 0: x not on the curve, 1: x >= p, 2: bad tag, rest valid
+    for i in range(n):
+        if bad_kind[i] == 0:
+            xs[i] = np.frombuffer(hashlib.sha256(b"codec%d" % i).digest(), dtype=np.uint8)      # ~half of these have no y
+        elif bad_kind[i] == 1:
+            xs[i] = np.frombuffer((P + (i % 977)).to_bytes(32, "big"), dtype=np.uint8)
+
+    def ref_loop(fn, recs, inlen, out_len=64):
+        ok = np.zeros(n, dtype=np.uint8); out = np.zeros((n, 64), dtype=np.uint8)
+        buf = ctypes.create_string_buffer(64)
+        for i in range(n):
+            ok[i] = fn(ref.ctx, buf, recs[i].tobytes()[:inlen], *([ctypes.c_size_t(inlen)] if fn is L.secp256k1_ec_pubkey_parse else []))
+            if ok[i]:
+                out[i, :out_len] = np.frombuffer(buf.raw[:out_len], dtype=np.uint8)
+        return ok, out
+    # format 1: 32-byte x-only keys -> opaque secp256k1_xonly_pubkey
+    ok, out = engine.point_codec(xs.tobytes(), 32, 1)
+    rok, rout = ref_loop(L.secp256k1_xonly_pubkey_parse, xs, 32)
+    assert np.array_equal(ok, rok) and np.array_equal(out[ok == 1], rout[rok == 1]) and 0 < int(ok.sum()) < n
+    # format 2: SEC1 compressed (33) and uncompressed (65) keys -> opaque secp256k1_pubkey
+    tag = (2 + parity).astype(np.uint8); tag[bad_kind == 2] = 5
+    c33 = np.concatenate([tag[:, None], xs], axis=1)
+    ok, out = engine.point_codec(c33.tobytes(), 33, 2)
+    rok, rout = ref_loop(L.secp256k1_ec_pubkey_parse, c33, 33)
+    assert np.array_equal(ok, rok) and np.array_equal(out[ok == 1], rout[rok == 1])
+    t65 = np.full(n, 4, dtype=np.uint8); t65[bad_kind == 2] = 1; t65[bad_kind == 3] = 6 + parity[bad_kind == 3]     # hybrid encodings are legal
+    u65 = np.concatenate([t65[:, None], xs, ys], axis=1)
+    ok, out = engine.point_codec(u65.tobytes(), 65, 2)
+    rok, rout = ref_loop(L.secp256k1_ec_pubkey_parse, u65, 65)
+    assert np.array_equal(ok, rok) and np.array_equal(out[ok == 1], rout[rok == 1]) and 0 < int(ok.sum()) < n
+    # format 4: 33-byte generators (tags 10 / 11 = y is a square / is not) -> 64-byte secp256k1_generator; format 5 = serialize back
+    gtag = np.array([10 + (i & 1) for i in range(n)], dtype=np.uint8); gtag[bad_kind == 2] = 9
+    g33 = np.concatenate([gtag[:, None], xs], axis=1)
+    ok, out = engine.point_codec(g33.tobytes(), 33, 4)
+    rok, rout = ref_loop(L.secp256k1_generator_parse, g33, 33)
+    assert np.array_equal(ok, rok) and np.array_equal(out[ok == 1], rout[rok == 1]) and 0 < int(ok.sum()) < n
+    good = out[ok == 1]
+    ok5, ser = engine.point_codec(good.tobytes(), 64, 5)
+    assert ok5.all() and np.array_equal(ser[:, :33], g33[ok == 1])
+    # format 3: 33-byte commitments (tags 8 / 9) -> validity + affine point; the reference's parser accepts exactly the same encodings
+    ctag = np.array([8 + (i & 1) for i in range(n)], dtype=np.uint8); ctag[bad_kind == 2] = 10
+    c33 = np.concatenate([ctag[:, None], xs], axis=1)
+    ok, out = engine.point_codec(c33.tobytes(), 33, 3)
+    rok, _ = ref_loop(L.secp256k1_pedersen_commitment_parse, c33, 33, out_len=33)
+    assert np.array_equal(ok, rok) and 0 < int(ok.sum()) < n
+    for i in np.nonzero(ok)[0][::97]:
+        x = int.from_bytes(bytes(out[i, :32]), "big"); y = int.from_bytes(bytes(out[i, 32:]), "big")
+        assert x == int.from_bytes(bytes(xs[i]), "big") and (y * y - x * x * x - 7) % P == 0
+        assert (pow(y, (P - 1) // 2, P) == 1) == (ctag[i] == 8)          # tag 8: y is the square root that is itself a square (:266-273)
+
+
 # ---- division-step inverse / Jacobi symbol on the device (csrc/modinv.cuh) ------------------------------------------------------------
 def test_safegcd_inverse_and_jacobi_gpu(engine, ref):
     import secp256k1_zkp_b200 as b200
