@@ -39,45 +39,91 @@ namespace B200_NS {
 
 #if BN_PTX
 // acc[0..8] += (a0 + a1*2^64 + a2*2^128 + a3*2^192) * b   (a_i, b 32-bit; four aligned 64-bit products)
+// CO = false: the caller knows acc[7] is still zero (a fresh limb), so the top word  hi(a3*b) + carry <= 2^32 - 1  cannot overflow and the
+// carry-out into acc[8] is omitted (one instruction -- a SEL or an IMAD.X on the multiply pipe -- and one zero-initialised register less).
+template <bool CO = true>
 __device__ __forceinline__ void bn_cmad4(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
-    asm("mad.lo.cc.u32  %0, %9,  %13, %0;\n\t"
-        "madc.hi.cc.u32 %1, %9,  %13, %1;\n\t"
-        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
-        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
-        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
-        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
-        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
-        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
-        "addc.u32       %8, %8, 0;\n\t"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
-        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+    if (CO) {
+        asm("mad.lo.cc.u32  %0, %9,  %13, %0;\n\t"
+            "madc.hi.cc.u32 %1, %9,  %13, %1;\n\t"
+            "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+            "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+            "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+            "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+            "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32       %8, %8, 0;\n\t"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
+            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+    } else {
+        asm("mad.lo.cc.u32  %0, %8,  %12, %0;\n\t"
+            "madc.hi.cc.u32 %1, %8,  %12, %1;\n\t"
+            "madc.lo.cc.u32 %2, %9,  %12, %2;\n\t"
+            "madc.hi.cc.u32 %3, %9,  %12, %3;\n\t"
+            "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+            "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+            "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+            "madc.hi.u32    %7, %11, %12, %7;\n\t"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+    }
 }
+template <bool CO = true>
 __device__ __forceinline__ void bn_cmad3(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b) {
-    asm("mad.lo.cc.u32  %0, %7, %10, %0;\n\t"
-        "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
-        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
-        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
-        "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
-        "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
-        "addc.u32       %6, %6, 0;\n\t"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
-        : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+    if (CO) {
+        asm("mad.lo.cc.u32  %0, %7, %10, %0;\n\t"
+            "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+            "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+            "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+            "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+            "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+            "addc.u32       %6, %6, 0;\n\t"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
+            : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+    } else {
+        asm("mad.lo.cc.u32  %0, %6, %9, %0;\n\t"
+            "madc.hi.cc.u32 %1, %6, %9, %1;\n\t"
+            "madc.lo.cc.u32 %2, %7, %9, %2;\n\t"
+            "madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+            "madc.lo.cc.u32 %4, %8, %9, %4;\n\t"
+            "madc.hi.u32    %5, %8, %9, %5;\n\t"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5])
+            : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+    }
 }
+template <bool CO = true>
 __device__ __forceinline__ void bn_cmad2(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t b) {
-    asm("mad.lo.cc.u32  %0, %5, %7, %0;\n\t"
-        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
-        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
-        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
-        "addc.u32       %4, %4, 0;\n\t"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4])
-        : "r"(a0), "r"(a1), "r"(b));
+    if (CO) {
+        asm("mad.lo.cc.u32  %0, %5, %7, %0;\n\t"
+            "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+            "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+            "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+            "addc.u32       %4, %4, 0;\n\t"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4])
+            : "r"(a0), "r"(a1), "r"(b));
+    } else {
+        asm("mad.lo.cc.u32  %0, %4, %6, %0;\n\t"
+            "madc.hi.cc.u32 %1, %4, %6, %1;\n\t"
+            "madc.lo.cc.u32 %2, %5, %6, %2;\n\t"
+            "madc.hi.u32    %3, %5, %6, %3;\n\t"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3])
+            : "r"(a0), "r"(a1), "r"(b));
+    }
 }
+template <bool CO = true>
 __device__ __forceinline__ void bn_cmad1(uint32_t* acc, uint32_t a0, uint32_t b) {
-    asm("mad.lo.cc.u32  %0, %3, %4, %0;\n\t"
-        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
-        "addc.u32       %2, %2, 0;\n\t"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2])
-        : "r"(a0), "r"(b));
+    if (CO) {
+        asm("mad.lo.cc.u32  %0, %3, %4, %0;\n\t"
+            "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+            "addc.u32       %2, %2, 0;\n\t"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2])
+            : "r"(a0), "r"(b));
+    } else {
+        asm("mad.lo.cc.u32  %0, %2, %3, %0;\n\t"
+            "madc.hi.u32    %1, %2, %3, %1;\n\t"
+            : "+r"(acc[0]), "+r"(acc[1])
+            : "r"(a0), "r"(b));
+    }
 }
 #endif
 
@@ -130,12 +176,16 @@ HD void bn_mul_wide(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 #pragma unroll
     for (int i = 0; i < 17; i++) { e[i] = 0; o[i] = 0; }
     // e[k] holds weight 2^(32k) for products whose column is even, o[k] weight 2^(32(k+1)) for odd columns
+    // Carry-outs that cannot happen are not emitted (r2): a chain whose top target limb has never been written ends in  hi + carry  of a
+    // fresh zero, which fits 32 bits.  That is the case for the very first chain on e, for every first chain of a pair on o (o[i+7] is fresh:
+    // the previous pair reached o[i+5] and put its carries into o[i+6]) and for every second chain on e (e[i+9] is fresh): 9 of the 16 chains.
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {
-        bn_cmad4(e + i, a[0], a[2], a[4], a[6], b[i]);          // columns i+0,2,4,6   (even)
-        bn_cmad4(o + i, a[1], a[3], a[5], a[7], b[i]);          // columns i+1,3,5,7   (odd)
-        bn_cmad4(o + i, a[0], a[2], a[4], a[6], b[i + 1]);      // columns i+1+0,2,..  (odd)
-        bn_cmad4(e + i + 2, a[1], a[3], a[5], a[7], b[i + 1]);  // columns i+2,4,..    (even)
+        if (i == 0) bn_cmad4<false>(e + i, a[0], a[2], a[4], a[6], b[i]);   // columns i+0,2,4,6   (even)
+        else bn_cmad4<true>(e + i, a[0], a[2], a[4], a[6], b[i]);
+        bn_cmad4<false>(o + i, a[1], a[3], a[5], a[7], b[i]);               // columns i+1,3,5,7   (odd)
+        bn_cmad4<true>(o + i, a[0], a[2], a[4], a[6], b[i + 1]);            // columns i+1+0,2,..  (odd)
+        bn_cmad4<false>(e + i + 2, a[1], a[3], a[5], a[7], b[i + 1]);       // columns i+2,4,..    (even)
     }
     r[0] = e[0];
     uint32_t cmid, cdummy;
@@ -193,13 +243,14 @@ HD void bn_sqr_wide(uint32_t* r, const uint32_t* a) {
     uint32_t e[17], o[17];
 #pragma unroll
     for (int i = 0; i < 17; i++) { e[i] = 0; o[i] = 0; }
-    bn_cmad3(e + 2, a[2], a[4], a[6], a[0]);   bn_cmad4(o + 0, a[1], a[3], a[5], a[7], a[0]);
-    bn_cmad3(e + 4, a[3], a[5], a[7], a[1]);   bn_cmad3(o + 2, a[2], a[4], a[6], a[1]);
-    bn_cmad2(e + 6, a[4], a[6], a[2]);         bn_cmad3(o + 4, a[3], a[5], a[7], a[2]);
-    bn_cmad2(e + 8, a[5], a[7], a[3]);         bn_cmad2(o + 6, a[4], a[6], a[3]);
-    bn_cmad1(e + 10, a[6], a[4]);              bn_cmad2(o + 8, a[5], a[7], a[4]);
-    bn_cmad1(e + 12, a[7], a[5]);              bn_cmad1(o + 10, a[6], a[5]);
-    bn_cmad1(o + 12, a[7], a[6]);
+    // <false>: the chain's top target limb has never been written, so no carry can leave it (see bn_mul_wide)
+    bn_cmad3<false>(e + 2, a[2], a[4], a[6], a[0]);   bn_cmad4<false>(o + 0, a[1], a[3], a[5], a[7], a[0]);
+    bn_cmad3<false>(e + 4, a[3], a[5], a[7], a[1]);   bn_cmad3<true>(o + 2, a[2], a[4], a[6], a[1]);
+    bn_cmad2<true>(e + 6, a[4], a[6], a[2]);          bn_cmad3<false>(o + 4, a[3], a[5], a[7], a[2]);
+    bn_cmad2<false>(e + 8, a[5], a[7], a[3]);         bn_cmad2<true>(o + 6, a[4], a[6], a[3]);
+    bn_cmad1<true>(e + 10, a[6], a[4]);               bn_cmad2<false>(o + 8, a[5], a[7], a[4]);
+    bn_cmad1<false>(e + 12, a[7], a[5]);              bn_cmad1<true>(o + 10, a[6], a[5]);
+    bn_cmad1<false>(o + 12, a[7], a[6]);
     // s = e + (o << 32)   (s[0] = s[1]... e[0], e[1] are zero by construction)
     uint32_t s[16], cmid, cdummy;
     s[0] = 0;

@@ -37,7 +37,7 @@ HD void fe_reduce512(fe& r, const uint32_t* t) {
     const uint32_t* h = t + 8;
     // lo[0..9] = t_lo + hi*977 + (hi << 32)      (< 2^289, so lo[9] <= 1)
     bn_cmad4(lo, h[0], h[2], h[4], h[6], 977u);
-    bn_cmad4(lo + 1, h[1], h[3], h[5], h[7], 977u);
+    bn_cmad4<false>(lo + 1, h[1], h[3], h[5], h[7], 977u);      // top word: lo[8] (0/1) + hi(h7*977) (< 977) + carry: cannot overflow
     asm("add.cc.u32  %0, %0, %9;\n\t"
         "addc.cc.u32 %1, %1, %10;\n\t"
         "addc.cc.u32 %2, %2, %11;\n\t"
