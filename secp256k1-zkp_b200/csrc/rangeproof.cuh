@@ -132,14 +132,50 @@ HD void rp_ring_base(gej& base, const ge& genp, int exp, uint32_t ring) {
     for (uint32_t k = 0; k < 2 * ring; k++) { gej t; gej_double(t, base); base = t; }
 }
 
-// borromean_hash (borromean_impl.h:23-37): SHA256(e || m || be32(ring) || be32(idx)) -> scalar; returns overflow flag
+// borromean_hash (borromean_impl.h:23-37): SHA256(e || m || be32(ring) || be32(idx)) -> scalar; returns overflow flag.
+// e is e0 (32 bytes) or a serialized point (33 bytes): one full block plus 8 or 9 bytes.  Both layouts are assembled as big-endian words
+// straight from the inputs -- no byte buffer, no generic write loop: this hash runs 128 times per 64-bit proof in every lane (r2m: the
+// byte-oriented form was 10 % of k_rangeproof_verify's instructions and 46 % of its code size).
+HD uint32_t rp_be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3]; }
 HD int rp_borromean_challenge(sc& ens, const uint8_t* e, uint32_t elen, const uint8_t* m32, uint32_t ring, uint32_t idx) {
-    sha256 s;
-    uint8_t out[32], w[8] = {(uint8_t)(ring >> 24), (uint8_t)(ring >> 16), (uint8_t)(ring >> 8), (uint8_t)ring,
-                             (uint8_t)(idx >> 24), (uint8_t)(idx >> 16), (uint8_t)(idx >> 8), (uint8_t)idx};
-    sha256_init(s);
-    sha256_write(s, e, elen); sha256_write(s, m32, 32); sha256_write(s, w, 8);
-    sha256_finalize(s, out);
+    uint8_t out[32];
+    if (elen == 32 || elen == 33) {
+        uint32_t st[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+        uint32_t w[16];
+#pragma unroll
+        for (int k = 0; k < 8; k++) w[k] = rp_be32(e + 4 * k);
+        if (elen == 32) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) w[8 + k] = rp_be32(m32 + 4 * k);
+        } else {                                                    // the stream is m shifted by one byte
+            w[8] = ((uint32_t)e[32] << 24) | ((uint32_t)m32[0] << 16) | ((uint32_t)m32[1] << 8) | (uint32_t)m32[2];
+#pragma unroll
+            for (int k = 1; k < 8; k++) w[8 + k] = rp_be32(m32 + 4 * k - 1);
+        }
+        sha256_compress(st, w);
+#pragma unroll
+        for (int k = 0; k < 16; k++) w[k] = 0;
+        if (elen == 32) {
+            w[0] = ring; w[1] = idx; w[2] = 0x80000000u;
+        } else {
+            w[0] = ((uint32_t)m32[31] << 24) | (ring >> 8);
+            w[1] = (ring << 24) | (idx >> 8);
+            w[2] = (idx << 24) | 0x00800000u;
+        }
+        w[15] = (elen + 40) * 8;
+        sha256_compress(st, w);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            out[4 * k] = (uint8_t)(st[k] >> 24); out[4 * k + 1] = (uint8_t)(st[k] >> 16); out[4 * k + 2] = (uint8_t)(st[k] >> 8); out[4 * k + 3] = (uint8_t)st[k];
+        }
+    } else {
+        sha256 s;
+        uint8_t w[8] = {(uint8_t)(ring >> 24), (uint8_t)(ring >> 16), (uint8_t)(ring >> 8), (uint8_t)ring,
+                        (uint8_t)(idx >> 24), (uint8_t)(idx >> 16), (uint8_t)(idx >> 8), (uint8_t)idx};
+        sha256_init(s);
+        sha256_write(s, e, elen); sha256_write(s, m32, 32); sha256_write(s, w, 8);
+        sha256_finalize(s, out);
+    }
     return sc_set_b32(ens, out);
 }
 
