@@ -498,13 +498,14 @@ __global__ void __launch_bounds__(256) k_msm_tail(uint8_t* out, int mode, msm_ws
         if (valid && l == 0) W[wi] = r;
     }
     __syncthreads();
-    if (threadIdx.x >= 32) return;                                      // the rest is one warp's work
-    {
+    const uint32_t warp = threadIdx.x >> 5;
+    if (warp < 2) {                                                     // warp 0 / warp 1: the two halves, side by side
         gej r;
-        msm_horner_half(r, W + (g & 1) * p.nw, p);                     // groups 0 / 1 own the halves, the other six recompute them
-        if (g < 2 && l == 0) H[g] = r;
+        msm_horner_half(r, W + warp * p.nw, p);
+        if ((threadIdx.x & 31) == 0) H[warp] = r;
     }
-    __syncwarp();
+    __syncthreads();
+    if (threadIdx.x >= 32) return;                                      // the rest is one warp's work
     gej r, a = H[0], b = H[1];
     msm_join_halves(r, a, b);
     if (threadIdx.x == 0) write_result(out, r, mode);

@@ -25,6 +25,7 @@
 #pragma once
 #include "gtable.cuh"
 #include "ge_g4.cuh"
+#include "ge_w10.cuh"
 #include "sc.cuh"
 
 namespace B200_NS {
@@ -248,14 +249,15 @@ HD void msm_window_from_sums(gej& W, const gej_store* T /* [1 + bits] sums, `str
     W = acc;
 }
 
-// Horner over the nw windows of one half: sum_w 2^(c w) W[w]
+// Horner over the nw windows of one half: sum_w 2^(c w) W[w].  One WHOLE WARP per half, converged (the doublings are warp-wide, the additions
+// run redundantly in its 8 groups of 4 lanes).
 HD void msm_horner_half(gej& out, const gej* W, const msm_plan& p) {
     gej acc;
     gej_set_infinity(acc);
 #pragma unroll 1
     for (int w = (int)p.nw - 1; w >= 0; w--) {
 #pragma unroll 1
-        for (uint32_t k = 0; k < p.c; k++) { gej t; gej_double_g4(t, acc); acc = t; }      // doubling infinity is free of branches
+        { gej t; gej_double_n_w10(t, acc, p.c); acc = t; }         // the whole warp works on this one chain (ge_w10.cuh)
         gej t, ww = W[w];
         gej_add_g4(t, acc, ww); acc = t;
     }

@@ -18,7 +18,7 @@ LAMBDA = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
 G64 = bytes.fromhex("79BE667EF9DCBBAC55A06295CE870B07029BFCDB2DCE28D959F2815B16F81798"
                     "483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8")
 U_SC_MUL, U_SC_ADD, U_SC_NEG, U_SC_INV, U_SC_SPLIT, U_SC_RED = 0, 1, 2, 3, 4, 5
-U_DBL, U_ADD, U_ADD_GE, U_DBL_G4, U_ADD_G4, U_ADD_GE_G4 = 8, 9, 10, 24, 25, 26
+U_DBL, U_ADD, U_ADD_GE, U_DBL_G4, U_ADD_G4, U_ADD_GE_G4, U_DBL_W10, U_DBL16_W10 = 8, 9, 10, 24, 25, 26, 27, 28
 
 
 def b32(x):
@@ -123,6 +123,17 @@ def test_unit_group_ops_vs_reference(engine, ref):
     # sanity of the expectation itself: the a == -b items really are infinity, the a == b items are the doubling
     e = exp_add.reshape(n, 64)
     assert not e[4].any() and np.array_equal(e[0], exp_dbl.reshape(n, 64)[0])
+    # the warp-wide doubling chain (ge_w10.cuh: one 26-bit limb per lane): 2 a, and 2^16 a against 16 reference doublings
+    m = 20000
+    Aw = A[:m].copy()
+    Aw[0, 64:] = np.frombuffer(b32(P - 1), dtype=np.uint8); Aw[1, 64:] = np.frombuffer(b32(1), dtype=np.uint8)
+    assert np.array_equal(engine.unit_op(U_DBL_W10, Aw.tobytes()), ref.unit_op(U_DBL, Aw.tobytes()))
+    cur = Aw.copy()
+    for _ in range(16):
+        d = ref.unit_op(U_DBL, cur.tobytes()).reshape(m, 64)
+        cur[:, :64] = d
+        cur[:, 64:] = 0                                   # s = 0 is taken as 1
+    assert np.array_equal(engine.unit_op(U_DBL16_W10, Aw.tobytes()).reshape(m, 64), cur[:, :64])
 
 
 # ---- MSM ------------------------------------------------------------------------------------------------------------------------
