@@ -115,6 +115,7 @@ SECP256K1_B200_API int secp256k1_b200_fe_op_batch_dev(secp256k1_b200_engine *e, 
 #define SECP256K1_B200_UNIT_GEJ_ADD_GE_G4   26
 #define SECP256K1_B200_UNIT_GEJ_DOUBLE_W10  27  /* the warp-wide doubling chain of the MSM tail (ge_w10.cuh), 1 doubling */
 #define SECP256K1_B200_UNIT_GEJ_DOUBLE16_W10 28 /* 16 doublings */
+#define SECP256K1_B200_UNIT_GEJ_ADD_W10     29  /* the warp-wide addition (complete: infinity, a = b, a = -b) */
 SECP256K1_B200_API int secp256k1_b200_unit_op_batch(secp256k1_b200_engine *e, int op, unsigned char *out,
         const unsigned char *a, const unsigned char *b, size_t n);
 

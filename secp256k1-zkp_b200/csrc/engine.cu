@@ -203,7 +203,7 @@ int secp256k1_b200_fe_op_batch(secp256k1_b200_engine* e, int op, unsigned char* 
 /* unit kernels of the scalar / group primitives (parity hardening; k_unit.cu) */
 int secp256k1_b200_unit_op_batch(secp256k1_b200_engine* e, int op, unsigned char* out, const unsigned char* a, const unsigned char* b, size_t n) {
     if (!e) { set_error("engine is NULL"); return 0; }
-    const bool scalar = op >= 0 && op <= 5, group = (op >= 8 && op <= 10) || (op >= 24 && op <= 28);
+    const bool scalar = op >= 0 && op <= 5, group = (op >= 8 && op <= 10) || (op >= 24 && op <= 29);
     if (!scalar && !group) { set_error("unit_op: unknown op"); return 0; }
     if (n == 0) return 1;
     const size_t in_sz = scalar ? 32 : 96, out_sz = (scalar && op != 4) ? 32 : 64;

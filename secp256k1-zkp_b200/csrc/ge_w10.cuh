@@ -129,37 +129,104 @@ __device__ __forceinline__ uint32_t w10_mul(uint32_t a, uint32_t b, const w10_la
     return l2 + (L.k == 0 ? cp * 0x3D1u : cp) + (L.k == 1 ? c9 * 0x40u : 0u);
 }
 
-// r = 2^n a
-static __device__ __forceinline__ void gej_double_n_w10(gej& r, const gej& a, uint32_t n) {
-    if (a.inf || n == 0) { r = a; return; }                            // uniform
-    const w10_lane L = w10_lane_init();
-    const int r0 = L.k, r1 = 10 + L.k, r2 = 20 + L.k;                 // the lanes that hold limb k of group 0 / 1 / 2's product
-    uint32_t X = w10_from_fe(a.x, L), Y = w10_from_fe(a.y, L), Z = w10_from_fe(a.z, L);
+// A point in lane form: lane k of each group holds limb k of X, Y, Z (all three groups hold the same values); inf is uniform.
+// Invariant between operations: X, Y magnitude 1, Z magnitude <= 2.
+struct gej_w10 { uint32_t x, y, z; int inf; };
+
+__device__ __forceinline__ void w10_set_gej(gej_w10& P, const gej& a, const w10_lane& L) {
+    P.x = w10_from_fe(a.x, L); P.y = w10_from_fe(a.y, L); P.z = w10_from_fe(a.z, L); P.inf = a.inf;
+}
+__device__ __forceinline__ void w10_set_infinity(gej_w10& P) { P.x = 0; P.y = 0; P.z = 0; P.inf = 1; }
+__device__ __forceinline__ void w10_get_gej(gej& r, const gej_w10& P) {
+    if (P.inf) { gej_set_infinity(r); return; }                        // uniform
+    r.x = w10_to_fe(P.x); r.y = w10_to_fe(P.y); r.z = w10_to_fe(P.z); r.inf = 0;
+}
+// the three products of one step, each group's result copied to every group
+#define W10_MUL3(o0, o1, o2, p, q)                                                   \
+    { const uint32_t o_ = w10_mul(p, q, L);                                         \
+      o0 = __shfl_sync(W10_FULL, o_, L.k); o1 = __shfl_sync(W10_FULL, o_, 10 + L.k); o2 = __shfl_sync(W10_FULL, o_, 20 + L.k); }
+#define W10_SEL(a0, a1, a2) (L.g == 0 ? (a0) : (L.g == 1 ? (a1) : (a2)))
+
+// P = 2^n P
+static __device__ __forceinline__ void w10_double_n(gej_w10& P, uint32_t n, const w10_lane& L) {
+    if (P.inf) return;                                                  // uniform
+    uint32_t X = P.x, Y = P.y, Z = P.z;
 #pragma unroll 1
     for (uint32_t it = 0; it < n; it++) {
-        // step 1: X*X | Y*Y | Y*Z
-        uint32_t o = w10_mul(L.g == 0 ? X : Y, L.g == 0 ? X : (L.g == 1 ? Y : Z), L);
-        const uint32_t A = __shfl_sync(W10_FULL, o, r0), B = __shfl_sync(W10_FULL, o, r1), YZ = __shfl_sync(W10_FULL, o, r2);
-        // step 2: X*B | B*B | A*A
-        o = w10_mul(L.g == 0 ? X : (L.g == 1 ? B : A), L.g == 2 ? A : B, L);
-        const uint32_t XB = __shfl_sync(W10_FULL, o, r0), C = __shfl_sync(W10_FULL, o, r1), A2 = __shfl_sync(W10_FULL, o, r2);
+        uint32_t A, B, YZ, XB, C, A2;
+        W10_MUL3(A, B, YZ, W10_SEL(X, Y, Y), W10_SEL(X, Y, Z));         // step 1: X*X | Y*Y | Y*Z
+        W10_MUL3(XB, C, A2, W10_SEL(X, B, A), W10_SEL(B, B, A));        // step 2: X*B | B*B | A*A
         X = w10_norm(9u * A2 + L.p16 - 8u * XB, L);
         const uint32_t N = w10_norm(12u * XB + L.p16 - 9u * A2, L);
-        // step 3: (3 A) * N in every group
-        o = w10_mul(3u * A, N, L);
-        Y = w10_norm(o + L.p16 - 8u * C, L);
+        const uint32_t M = w10_mul(3u * A, N, L);                       // step 3: (3 A) * N in every group
+        Y = w10_norm(M + L.p16 - 8u * C, L);
         Z = 2u * YZ;
     }
-    r.x = w10_to_fe(X); r.y = w10_to_fe(Y); r.z = w10_to_fe(Z);
-    r.inf = 0;
+    P.x = X; P.y = Y; P.z = Z;
 }
 
-#else   // host build: the plain function, n times
+// P = P + Q (complete: infinity on either side, Q = P, Q = -P).  add-2007-bl without the doubling shortcuts:
+//   step 1  Z2^2 | Z1^2 | Z1 Z2        step 2  U1 = X1 Z2^2 | U2 = X2 Z1^2 | Z2^3        H = U2 - U1
+//   step 3  Z1^3 | S1 = Y1 Z2^3 | H^2   step 4  S2 = Y2 Z1^3 | H^3 | V = U1 H^2          R = S2 - S1
+//   step 5  R^2 | S1 H^3 | Z3 = Z1 Z2 H      X3 = R^2 - H^3 - 2V      step 6  R (V - X3)      Y3 = R (V - X3) - S1 H^3
+static __device__ __forceinline__ void w10_add(gej_w10& P, const gej_w10& Q, const w10_lane& L) {
+    if (Q.inf) return;                                                  // uniform branches: all lanes hold the same points
+    if (P.inf) { P = Q; return; }
+    uint32_t z22, z12, zab, u1, u2, t1, t2, S1, HH, S2, HHH, V, RR, S1H, Z3;
+    W10_MUL3(z22, z12, zab, W10_SEL(Q.z, P.z, P.z), W10_SEL(Q.z, P.z, Q.z));
+    W10_MUL3(u1, u2, t1, W10_SEL(P.x, Q.x, Q.z), W10_SEL(z22, z12, z22));
+    const uint32_t H = w10_norm(u2 + L.p16 - u1, L);
+    W10_MUL3(t2, S1, HH, W10_SEL(P.z, P.y, H), W10_SEL(z12, t1, H));
+    W10_MUL3(S2, HHH, V, W10_SEL(Q.y, H, u1), W10_SEL(t2, HH, HH));
+    const uint32_t R = w10_norm(S2 + L.p16 - S1, L);
+    const fe hf = w10_to_fe(H), rf = w10_to_fe(R);                      // exact zero tests on the 8 x 32 form
+    if (fe_is_zero(hf)) {                                               // same x: Q = P or Q = -P (uniform)
+        if (fe_is_zero(rf)) w10_double_n(P, 1, L); else P.inf = 1;
+        return;
+    }
+    W10_MUL3(RR, S1H, Z3, W10_SEL(R, S1, zab), W10_SEL(R, HHH, H));
+    const uint32_t X3 = w10_norm(RR + L.p16 - HHH - 2u * V, L);
+    const uint32_t D = w10_norm(V + L.p16 - X3, L);
+    const uint32_t M = w10_mul(R, D, L);
+    P.x = X3; P.y = w10_norm(M + L.p16 - S1H, L); P.z = Z3;
+}
+
+// r = 2^n a on uniform operands (all lanes pass and receive the same point)
+static __device__ __forceinline__ void gej_double_n_w10(gej& r, const gej& a, uint32_t n) {
+    if (a.inf || n == 0) { r = a; return; }
+    const w10_lane L = w10_lane_init();
+    gej_w10 P;
+    w10_set_gej(P, a, L);
+    w10_double_n(P, n, L);
+    w10_get_gej(r, P);
+}
+// r = a + b on uniform operands
+static __device__ __forceinline__ void gej_add_w10(gej& r, const gej& a, const gej& b) {
+    const w10_lane L = w10_lane_init();
+    gej_w10 P, Q;
+    w10_set_gej(P, a, L); w10_set_gej(Q, b, L);
+    w10_add(P, Q, L);
+    if (P.inf) gej_set_infinity(r); else w10_get_gej(r, P);
+}
+
+#else   // host build (tests/hostemu): the same names on plain points
+struct w10_lane { int unused; };
+struct gej_w10 { gej g; int inf; };
+inline w10_lane w10_lane_init() { return w10_lane{0}; }
+inline void w10_set_gej(gej_w10& P, const gej& a, const w10_lane&) { P.g = a; P.inf = a.inf; }
+inline void w10_set_infinity(gej_w10& P) { gej_set_infinity(P.g); P.inf = 1; }
+inline void w10_get_gej(gej& r, const gej_w10& P) { r = P.g; }
+inline void w10_double_n(gej_w10& P, uint32_t n, const w10_lane&) {
+    for (uint32_t i = 0; i < n; i++) { gej u; gej_double(u, P.g); P.g = u; }
+    P.inf = P.g.inf;
+}
+inline void w10_add(gej_w10& P, const gej_w10& Q, const w10_lane&) { gej u; gej_add(u, P.g, Q.g); P.g = u; P.inf = u.inf; }
 inline void gej_double_n_w10(gej& r, const gej& a, uint32_t n) {
     gej t = a;
     for (uint32_t i = 0; i < n; i++) { gej u; gej_double(u, t); t = u; }
     r = t;
 }
+inline void gej_add_w10(gej& r, const gej& a, const gej& b) { gej_add(r, a, b); }
 #endif
 
 }  // namespace B200_NS

@@ -482,23 +482,21 @@ __device__ void write_result(uint8_t* out, const gej& r, int mode) {
     ge a; ge_set_gej(a, r);
     fe_get_b32(out, a.x); fe_get_b32(out + 32, a.y);
 }
-__global__ void __launch_bounds__(256) k_msm_tail(uint8_t* out, int mode, msm_ws ws, msm_plan p) {
+// Every chain in here is run by a whole warp on the lane form of ge_w10.cuh: one warp per window for the window sums (16 of them for
+// 16-bit windows: 512 threads = one round), one warp per GLV half for the Horner chains, warp 0 for the join and the inversion.
+#define MSM_TAIL_THREADS 512
+__global__ void __launch_bounds__(MSM_TAIL_THREADS) k_msm_tail(uint8_t* out, int mode, msm_ws ws, msm_plan p) {
     __shared__ gej W[2 * 32];
     __shared__ gej H[2];
-    const uint32_t g = threadIdx.x >> 2, l = threadIdx.x & 3, ngroups = blockDim.x >> 2;
-    const uint32_t maxbits = msm_ilog2((p.B > p.Btop ? p.B : p.Btop) / MSM_CHUNK);
-    for (uint32_t base = 0; base < 2 * p.nw; base += ngroups) {        // every warp runs every round (4-lane operations need whole warps)
-        const uint32_t wi = base + g;
-        const bool valid = wi < 2 * p.nw;
-        const uint32_t wic = valid ? wi : 0;
+    const uint32_t warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (uint32_t wi = warp; wi < 2 * p.nw; wi += nwarps) {
         msm_win w;
-        msm_window_by_index(w, p, wic);
+        msm_window_by_index(w, p, wi);
         gej r;
-        msm_window_from_sums(r, ws.T + (size_t)wic * MSM_MAX_SUMS * MSM_R2_PARTS, MSM_R2_PARTS, msm_ilog2(w.Bw / MSM_CHUNK), maxbits);
-        if (valid && l == 0) W[wi] = r;
+        msm_window_from_sums(r, ws.T + (size_t)wi * MSM_MAX_SUMS * MSM_R2_PARTS, MSM_R2_PARTS, msm_ilog2(w.Bw / MSM_CHUNK));
+        if ((threadIdx.x & 31) == 0) W[wi] = r;
     }
     __syncthreads();
-    const uint32_t warp = threadIdx.x >> 5;
     if (warp < 2) {                                                     // warp 0 / warp 1: the two halves, side by side
         gej r;
         msm_horner_half(r, W + warp * p.nw, p);
@@ -587,7 +585,7 @@ cudaError_t launch_msm(uint8_t* out, int out_mode, const uint8_t* g_scalar32, co
     if (chunks <= 40960) k_msm_r1<true><<<(unsigned)((chunks * 4 + 127) / 128), 128, 0, s>>>(ws, p);
     else k_msm_r1<false><<<(unsigned)((chunks + 127) / 128), 128, 0, s>>>(ws, p);
     k_msm_r2<<<2 * p.nw * MSM_MAX_SUMS * MSM_R2_PARTS, 256, 0, s>>>(ws, p);
-    k_msm_tail<<<1, 256, 0, s>>>(out, out_mode, ws, p);
+    k_msm_tail<<<1, MSM_TAIL_THREADS, 0, s>>>(out, out_mode, ws, p);
     if (launches) __atomic_fetch_add(launches, (uint64_t)11, __ATOMIC_RELAXED);
     return cudaGetLastError();
 }

@@ -29,7 +29,7 @@ __device__ void unit_store_gej(uint8_t* out64, const gej& r) {
 
 __global__ void __launch_bounds__(128) k_unit_op(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool g4 = op >= 24;                     // lane-parallel forms: 4 lanes per item (24-26), a whole warp per item (27, 28)
+    const bool g4 = op >= 24;                     // lane-parallel forms: 4 lanes per item (24-26), a whole warp per item (27-29)
     const int lanes_log2 = op >= 27 ? 5 : 2;
     size_t i = g4 ? (t >> lanes_log2) : t;
     const bool valid = i < n;
@@ -65,14 +65,15 @@ __global__ void __launch_bounds__(128) k_unit_op(int op, uint8_t* __restrict__ o
     case 25: gej_add_g4(R, A, B); break;
     case 26: gej_add_ge_g4(R, A, Ba); break;
     case 27: gej_double_n_w10(R, A, 1); break;
-    default: gej_double_n_w10(R, A, 16); break;
+    case 28: gej_double_n_w10(R, A, 16); break;
+    default: gej_add_w10(R, A, B); break;
     }
     if (valid && (!g4 || (threadIdx.x & ((1u << lanes_log2) - 1)) == 0)) unit_store_gej(out + 64 * i, R);
 }
 
 cudaError_t launch_unit_op(int op, uint8_t* out, const uint8_t* a, const uint8_t* b, size_t n, cudaStream_t s, uint64_t* launches) {
     if (n == 0) return cudaSuccess;
-    const bool ok = (op >= 0 && op <= 5) || (op >= 8 && op <= 10) || (op >= 24 && op <= 28);
+    const bool ok = (op >= 0 && op <= 5) || (op >= 8 && op <= 10) || (op >= 24 && op <= 29);
     if (!ok) return cudaErrorInvalidValue;
     size_t threads = op >= 27 ? 32 * n : op >= 24 ? 4 * n : n;
     k_unit_op<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(op, out, a, b, n);

@@ -66,7 +66,10 @@ HD void msm_make_plan_c(msm_plan& p, size_t N, uint32_t c) {
     // piece size: small enough that the pieces outnumber the GPU's lanes several times over (~2^19 pieces when there is that much
     // work) and that no lane walks a long bucket alone -- the top window of a half holds only ~0.6 * 2^t distinct digits, so its
     // buckets are several times fuller than the others -- but not smaller than 16 entries (every extra piece costs a Jacobian addition).
-    uint64_t e = ((uint64_t)2 * p.nw * N) >> 19;
+#ifndef MSM_PIECE_SHIFT
+#define MSM_PIECE_SHIFT 19
+#endif
+    uint64_t e = ((uint64_t)2 * p.nw * N) >> MSM_PIECE_SHIFT;
     uint32_t tp = MSM_PIECE_MIN;
     while (tp * 2 <= e && tp < MSM_PIECE_MAX) tp <<= 1;
     p.Tp = tp;
@@ -228,47 +231,46 @@ HD void msm_chunk_r1(gej& L, gej& A, const gej_store* s8) {
 // element k of bit-sum j over Q chunk sums: the k-th index q in [0, Q) whose bit j is set
 HD uint32_t msm_bit_index(uint32_t k, uint32_t j) { return ((k >> j) << (j + 1)) | (1u << j) | (k & ((1u << j) - 1u)); }
 
-// The three functions below run on GROUPS OF 4 LANES on the device (ge_g4.cuh: a whole warp calls together, every group with its own
-// arguments, all loops with warp-uniform trip counts); compiled for the host they are plain single-thread code.
+// The three functions below are serial chains of doublings and additions.  On the device each is run by ONE WHOLE WARP, converged, with the
+// running point in lane form (ge_w10.cuh: one 26-bit limb of every coordinate per lane); compiled for the host they are plain code.
 // window sum from its plain sum T[0] = sum_q L_q and bit sums T[1 + j] = sum_{q: bit j} A_q:
 //   W = T[0] + 8 * sum_j 2^j T[1 + j]
-HD void msm_window_from_sums(gej& W, const gej_store* T /* [1 + bits] sums, `stride` slots apart */, uint32_t stride, uint32_t nbits, uint32_t maxbits) {
-    gej acc;
-    gej_set_infinity(acc);
+HD void msm_window_from_sums(gej& W, const gej_store* T /* [1 + bits] sums, `stride` slots apart */, uint32_t stride, uint32_t nbits) {
+    const w10_lane L = w10_lane_init();
+    gej_w10 acc;
+    w10_set_infinity(acc);
 #pragma unroll 1
-    for (int j = (int)maxbits - 1; j >= -1; j--) {                // j = -1: the plain sum, after the multiplication by 8
-        const int slot = j + 1;
-        if (j == -1) {
-#pragma unroll 1
-            for (int k = 0; k < 3; k++) { gej t; gej_double_g4(t, acc); acc = t; }
-        } else { gej t; gej_double_g4(t, acc); acc = t; }
-        gej s, t;
-        if (slot <= (int)nbits) msm_load_gej(s, T[(size_t)slot * stride]); else gej_set_infinity(s);
-        gej_add_g4(t, acc, s); acc = t;
+    for (int j = (int)nbits - 1; j >= -1; j--) {                  // j = -1: the plain sum, after the multiplication by 8
+        w10_double_n(acc, j == -1 ? 3u : 1u, L);
+        gej s;
+        msm_load_gej(s, T[(size_t)(j + 1) * stride]);
+        gej_w10 q;
+        w10_set_gej(q, s, L);
+        w10_add(acc, q, L);
     }
-    W = acc;
+    w10_get_gej(W, acc);
 }
 
-// Horner over the nw windows of one half: sum_w 2^(c w) W[w].  One WHOLE WARP per half, converged (the doublings are warp-wide, the additions
-// run redundantly in its 8 groups of 4 lanes).
+// Horner over the nw windows of one half: sum_w 2^(c w) W[w]
 HD void msm_horner_half(gej& out, const gej* W, const msm_plan& p) {
-    gej acc;
-    gej_set_infinity(acc);
+    const w10_lane L = w10_lane_init();
+    gej_w10 acc;
+    w10_set_infinity(acc);
 #pragma unroll 1
     for (int w = (int)p.nw - 1; w >= 0; w--) {
-#pragma unroll 1
-        { gej t; gej_double_n_w10(t, acc, p.c); acc = t; }         // the whole warp works on this one chain (ge_w10.cuh)
-        gej t, ww = W[w];
-        gej_add_g4(t, acc, ww); acc = t;
+        w10_double_n(acc, p.c, L);
+        gej_w10 q;
+        w10_set_gej(q, W[w], L);
+        w10_add(acc, q, L);
     }
-    out = acc;
+    w10_get_gej(out, acc);
 }
 
 // R = A + lambda(B), lambda(X, Y, Z) = (beta X, Y, Z)   (group_impl.h ge_mul_lambda on Jacobian coordinates)
 HD void msm_join_halves(gej& R, const gej& A, const gej& Bh) {
     gej lb = Bh;
     if (!lb.inf) { fe beta; fe_set_beta(beta); fe_mul(lb.x, lb.x, beta); }
-    gej_add_g4(R, A, lb);
+    gej_add_w10(R, A, lb);
 }
 
 }  // namespace B200_NS

@@ -227,7 +227,7 @@ int emu_msm2(uint8_t* out64, const uint8_t* g_sc32, const uint8_t* scalars32, co
             msm_store_gej(T[((size_t)wi * MSM_MAX_SUMS + s) * MSM_R2_PARTS], tot);
         }
         uint32_t maxbits = msm_ilog2((p.B > p.Btop ? p.B : p.Btop) / MSM_CHUNK);
-        msm_window_from_sums(W[wi], T.data() + (size_t)wi * MSM_MAX_SUMS * MSM_R2_PARTS, MSM_R2_PARTS, nbits, maxbits);
+        msm_window_from_sums(W[wi], T.data() + (size_t)wi * MSM_MAX_SUMS * MSM_R2_PARTS, MSM_R2_PARTS, nbits);
     }
     gej H[2], r;
     msm_horner_half(H[0], W.data(), p);

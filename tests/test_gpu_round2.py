@@ -18,7 +18,7 @@ LAMBDA = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
 G64 = bytes.fromhex("79BE667EF9DCBBAC55A06295CE870B07029BFCDB2DCE28D959F2815B16F81798"
                     "483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8")
 U_SC_MUL, U_SC_ADD, U_SC_NEG, U_SC_INV, U_SC_SPLIT, U_SC_RED = 0, 1, 2, 3, 4, 5
-U_DBL, U_ADD, U_ADD_GE, U_DBL_G4, U_ADD_G4, U_ADD_GE_G4, U_DBL_W10, U_DBL16_W10 = 8, 9, 10, 24, 25, 26, 27, 28
+U_DBL, U_ADD, U_ADD_GE, U_DBL_G4, U_ADD_G4, U_ADD_GE_G4, U_DBL_W10, U_DBL16_W10, U_ADD_W10 = 8, 9, 10, 24, 25, 26, 27, 28, 29
 
 
 def b32(x):
@@ -134,6 +134,7 @@ def test_unit_group_ops_vs_reference(engine, ref):
         cur[:, :64] = d
         cur[:, 64:] = 0                                   # s = 0 is taken as 1
     assert np.array_equal(engine.unit_op(U_DBL16_W10, Aw.tobytes()).reshape(m, 64), cur[:, :64])
+    assert np.array_equal(engine.unit_op(U_ADD_W10, A[:m].tobytes(), B[:m].tobytes()), exp_add[:64 * m])
 
 
 # ---- MSM ------------------------------------------------------------------------------------------------------------------------
