@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) k_msm_units(msm_ws ws, msm_plan p) {
     d.begin = beg + j * p.Tp;
     d.count = (end - d.begin < p.Tp) ? end - d.begin : p.Tp;
     d.dst = (npieces == 1) ? b : (MSM_DST_PART | (ws.mbase[b] + j));
-    d.bucket = b;
+    d.first = ws.entries[d.begin];
     ws.units[u] = d;
 }
 
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(128, MSM_SUM_MINBLOCKS) k_msm_bucket_sum(msm_w
                 const uint4 d = *reinterpret_cast<const uint4*>(ws.units + my);
                 e = d.x; eend = d.x + d.y; dst = d.z;
                 gej_set_infinity(acc);
-                const uint32_t v = ws.entries[e];
+                const uint32_t v = d.w;                               // = ws.entries[e], copied into the descriptor by k_msm_units
                 msm_load_point(nxt, points64, n, ws.gpoint, v & 0x7FFFFFFFu);
                 nxt_neg = v >> 31;
                 have = true;
@@ -375,9 +375,14 @@ __device__ void block_sum_gej(gej& acc, gej_store* scratch) {
     __syncthreads();
     if (lane == 0) msm_store_gej(scratch[wid], acc);
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (wid == 0) {                                                     // the <= 8 warp sums: a second shuffle tree (3 additions deep, not 7 in a row)
+        if (lane < nw) msm_load_gej(acc, scratch[lane]); else gej_set_infinity(acc);
 #pragma unroll 1
-        for (uint32_t w = 1; w < nw; w++) { gej o, t; msm_load_gej(o, scratch[w]); gej_add(t, acc, o); acc = t; }
+        for (int d = 4; d >= 1; d >>= 1) {
+            gej o, t;
+            gej_shfl_down(o, acc, d);
+            if ((int)lane < d) { gej_add(t, acc, o); acc = t; }
+        }
     }
 }
 __global__ void __launch_bounds__(256) k_msm_combine(msm_ws ws, msm_plan p) {

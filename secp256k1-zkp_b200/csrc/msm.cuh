@@ -156,7 +156,8 @@ HD void msm_load_gej(gej& a, const gej_store& s) {
 }
 
 // a unit of bucket work: <= Tp consecutive sorted entries of one bucket
-struct msm_unit { uint32_t begin, count, dst, bucket; };   // dst: bucket index, or 0x80000000 | index into the parts array
+struct msm_unit { uint32_t begin, count, dst, first; };    // dst: bucket index, or 0x80000000 | index into the parts array; first = entries[begin]
+                                                           // (one dependent load less when a lane of k_msm_bucket_sum starts a piece)
 #define MSM_DST_PART 0x80000000u
 
 // affine point i of the input (x||y big-endian, raw 256-bit values); index n = the generator slot

@@ -201,7 +201,7 @@ int emu_msm2(uint8_t* out64, const uint8_t* g_sc32, const uint8_t* scalars32, co
         uint32_t lo = 0, hi = p.TB;
         while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (pbase[mid] <= u) lo = mid; else hi = mid; }
         uint32_t b = lo, j = u - pbase[b], npieces = pbase[b + 1] - pbase[b];
-        msm_unit d; d.begin = off[b] + j * p.Tp; d.count = off[b + 1] - d.begin < p.Tp ? off[b + 1] - d.begin : p.Tp; d.bucket = b;
+        msm_unit d; d.begin = off[b] + j * p.Tp; d.count = off[b + 1] - d.begin < p.Tp ? off[b + 1] - d.begin : p.Tp; d.first = entries[d.begin];
         d.dst = npieces == 1 ? b : (MSM_DST_PART | (mbase[b] + j));
         gej acc; msm_unit_sum(acc, d, entries.data(), points64, n, gpoint);
         msm_store_gej((d.dst & MSM_DST_PART) ? parts[d.dst & ~MSM_DST_PART] : buckets[d.dst], acc);
