@@ -527,9 +527,21 @@ def run_extra_workloads(ctx, peaks, ref, hi_info, want_cpu):
              "note": "norm-product argument only: this reference snapshot has no full BP++ range proof (SURVEY fact 3); 512 proofs = 0.3 waves of warps, "
                      "the kernel is latency bound at this batch size"}
     cpu = cpu_leg(hi_info, bp_cpu, "verify/s", 256, 16, "reference secp256k1_bppp_rangeproof_norm_product_verify (no reference bench exists)") if want_cpu else None
+    # the same kernel with enough warps to fill the GPU: 8192 DISTINCT arguments per GPU (5.5 waves of warps) -- what the kernel sustains
+    big = 8192
+    bp2, rho2, cv2, cm2, gens2, _ = make_bppp(ref, big, seed + b"big", hi_info)
+    tr2 = eng.bppp_transcripts(cm2, rho2, gens2, 16, cv2, 8, mode="tests")
+    d2 = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in (("p", bp2), ("rho", rho2), ("cv", cv2), ("cm", cm2), ("tr", tr2), ("g", gens2))}
+    pl2 = torch.full((big,), 324, dtype=torch.int32, device=dev)
+    okb2 = torch.zeros(big, dtype=torch.uint8, device=dev)
+    ms2 = time_dev(ctx, lambda: eng._ck(eng._lib.secp256k1_b200_bppp_norm_verify_batch_dev(
+        eng._h, okb2.data_ptr(), d2["p"].data_ptr(), 324, pl2.data_ptr(), d2["tr"].data_ptr(), d2["rho"].data_ptr(), d2["g"].data_ptr(), 16,
+        d2["cv"].data_ptr(), 8, d2["cm"].data_ptr(), big, stream)), warm=1, reps=3)
+    entry["batch_8192"] = {"proofs_per_gpu": big, "all_accepted": bool(okb2.all()), "ms": ms2, "verify_per_s": big * world / ms2 * 1e3,
+                           "roofline": roofline_entry(big, MAC_PER_BPPP, ms2, peaks)}
     finish("bppp_norm_verify_16g8h", entry, per * world, ms, "verify_per_s", e2e_ms, per * (324 + 104 + 32 + 256 + 64 + 4) + 24 * 64, per, MAC_PER_BPPP, per, cpu,
            "secp256k1_b200_bppp_norm_verify_batch")
-    del d
+    del d, d2
 
     # ---- ECDSA verify / recover, 2^18 per GPU: r = x of a BIP-340 nonce point (always liftable), s random ------------------------------
     per = 1 << 18
