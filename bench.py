@@ -420,6 +420,25 @@ def run_extra_workloads(ctx, peaks, ref, hi_info, want_cpu):
         tot = sum(parts) % N_ORD
     exp = eng.ecmult(bytes(64), bytes(32), tot.to_bytes(32, "big"))[0].tobytes()
     entry = {"terms": n_total, "scaling": "strong", "identity_check_ok": got == exp}
+    if world > 1 and n_total % world == 0:
+        # the other sharding: all 2^20 terms resident on EVERY GPU, rank r sums the bucket windows wi with wi % W == r (1/W of the bucket additions
+        # AND of the bucket reduction, which sharding by terms repeats on every GPU); same all-gather of 96-byte partial results
+        full_sc = torch.empty((n_total, 32), dtype=torch.uint8, device=dev); full_pts = torch.empty((n_total, 64), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(full_sc, sc); dist.all_gather_into_tensor(full_pts, mpts)
+        wsb_f = eng.ecmult_multi_workspace_bytes(n_total)
+        ws_f = torch.empty(wsb_f, dtype=torch.uint8, device=dev)
+
+        def msm_step_windows():
+            eng.ecmult_multi_window_shard_dev(part.data_ptr(), None, full_sc.data_ptr(), full_pts.data_ptr(), n_total, rank, world, ws_f.data_ptr(), wsb_f, stream)
+            D.allgather_partials(part, allp)
+            eng.ecmult_multi_combine_dev(final.data_ptr(), allp.data_ptr(), world, stream)
+        ms_w = time_dev(ctx, msm_step_windows)
+        entry["sharding"] = {"by_terms_ms": ms, "by_windows_ms": ms_w, "by_windows_identity_check_ok": final.cpu().numpy().tobytes() == exp,
+                             "reported": "by_windows" if ms_w < ms else "by_terms",
+                             "note": "by_terms: rank r holds terms [rN/W, (r+1)N/W) only; by_windows: all terms resident on every GPU (replicated inputs), "
+                                     "rank r sums the bucket windows wi = r mod W"}
+        ms = min(ms, ms_w)
+        del full_sc, full_pts, ws_f
     tps, hps = pinned(torch, mpts.cpu().numpy()); tss, hss = pinned(torch, sch)
     e2e_ms, hout = time_host(ctx, lambda: eng.ecmult_multi(hss, hps))
     if world == 1:

@@ -36,6 +36,7 @@ struct secp256k1_b200_engine {
     size_t scratch_bytes;
     uint8_t* h_pinned;         // grow-only pinned host staging for results (a D2H copy into pageable memory would block the host
     size_t pinned_bytes;       //  and serialize the chunk pipeline)
+    cudaMemPool_t pool;        // stream-ordered scratch of the _dev calls (release threshold = max: blocks stay cached across synchronisations)
     uint64_t launches;         // updated with atomic adds by the launchers (_dev calls may come from many threads)
     int msm_window;            // 0 = chosen from n (msm_choose_c); otherwise forced (secp256k1_b200_ecmult_multi_set_window)
     std::mutex mu;             // the reference context is usable from many threads (secp256k1.h:42-49): serialize here

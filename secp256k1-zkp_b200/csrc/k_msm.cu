@@ -446,6 +446,7 @@ __global__ void __launch_bounds__(256, 2) k_msm_r2(msm_ws ws, msm_plan p) {     
     __shared__ gej_store scratch[8];
     const uint32_t part = blockIdx.x % MSM_R2_PARTS, ws_i = blockIdx.x / MSM_R2_PARTS;
     const uint32_t wi = ws_i / MSM_MAX_SUMS, s = ws_i % MSM_MAX_SUMS;
+    if (!msm_window_owned(p, wi)) return;                               // window sharding: another launch sums this window (block-uniform)
     msm_win w;
     msm_window_by_index(w, p, wi);
     const uint32_t Q = w.Bw / MSM_CHUNK, nbits = msm_ilog2(Q), cb = w.base / MSM_CHUNK;
@@ -500,7 +501,8 @@ __global__ void __launch_bounds__(MSM_TAIL_THREADS) k_msm_tail(uint8_t* out, int
         msm_win w;
         msm_window_by_index(w, p, wi);
         gej r;
-        msm_window_from_sums(r, ws.T + (size_t)wi * MSM_MAX_SUMS * MSM_R2_PARTS, MSM_R2_PARTS, msm_ilog2(w.Bw / MSM_CHUNK));
+        if (msm_window_owned(p, wi)) msm_window_from_sums(r, ws.T + (size_t)wi * MSM_MAX_SUMS * MSM_R2_PARTS, MSM_R2_PARTS, msm_ilog2(w.Bw / MSM_CHUNK));
+        else gej_set_infinity(r);                                       // warp-uniform
         if ((threadIdx.x & 31) == 0) W[wi] = r;
     }
     __syncthreads();
@@ -559,14 +561,15 @@ static int sum_grid_blocks() {
 }
 
 cudaError_t launch_msm(uint8_t* out, int out_mode, const uint8_t* g_scalar32, const uint8_t* scalars32, const uint8_t* points64, size_t n,
-                       uint8_t* workspace, size_t workspace_bytes, int window_bits, cudaStream_t s, uint64_t* launches) {
+                       uint8_t* workspace, size_t workspace_bytes, int window_bits, cudaStream_t s, uint64_t* launches, uint32_t shard, uint32_t shards) {
     if (n + 1 >= ((size_t)1 << 31)) return cudaErrorInvalidValue;
     if (reinterpret_cast<uintptr_t>(workspace) & 255) return cudaErrorInvalidValue;
+    if (shards == 0 || shard >= shards) return cudaErrorInvalidValue;
     const size_t N = n + 1;
     int c = window_bits ? window_bits : (int)msm_choose_c(N);
     if (!c_allowed(N, c)) return cudaErrorInvalidValue;
     msm_plan p;
-    msm_make_plan_c(p, N, (uint32_t)c);
+    msm_make_plan_c(p, N, (uint32_t)c, shard, shards);
     msm_ws ws;
     if (carve(&ws, workspace, p) > workspace_bytes) return cudaErrorInvalidValue;
     const msm_caps caps = caps_of(p);

@@ -184,7 +184,7 @@ static inline ecmult_gtable to_gt(const gtable_dev& g) { ecmult_gtable t; t.data
 
 cudaError_t launch_rangeproof_verify(uint8_t* ok, uint64_t* minv, uint64_t* maxv, const uint8_t* commit33, const uint8_t* proofs, size_t stride,
                                      const uint32_t* plen, const uint8_t* gen64, size_t gen_stride, const uint8_t* extra, size_t extra_stride,
-                                     const uint32_t* extra_len, size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches, uint8_t* ev_out) {
+                                     const uint32_t* extra_len, size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches, uint8_t* ev_out, cudaMemPool_t pool) {
     if (n == 0) return cudaSuccess;
 #ifdef RP_SMEM_MIN                                                 // development: caps the resident blocks per SM (A/B of wave shapes)
     const int smem = RP_WARPS * RP_WARP_STRIDE > RP_SMEM_MIN ? RP_WARPS * RP_WARP_STRIDE : RP_SMEM_MIN;
@@ -193,8 +193,8 @@ cudaError_t launch_rangeproof_verify(uint8_t* ok, uint64_t* minv, uint64_t* maxv
 #endif
     cudaError_t err = cudaFuncSetAttribute(k_rangeproof_verify, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return err;
-    uint8_t* scratch = nullptr;                                   // stream-ordered: no synchronisation, the pool reuses the block call after call
-    err = cudaMallocAsync((void**)&scratch, RP_SCRATCH_BYTES * n, s);
+    uint8_t* scratch = nullptr;                                   // stream-ordered: no synchronisation; the engine's pool keeps the block cached call after call
+    err = pool ? cudaMallocFromPoolAsync((void**)&scratch, RP_SCRATCH_BYTES * n, pool, s) : cudaMallocAsync((void**)&scratch, RP_SCRATCH_BYTES * n, s);
     if (err != cudaSuccess) return err;
     const unsigned tb = (unsigned)((n + 127) / 128);
     k_rangeproof_prehash<<<tb, 128, 0, s>>>(scratch, commit33, proofs, stride, plen, gen64, gen_stride, extra, extra_stride, extra_len, n);

@@ -35,7 +35,8 @@ cudaError_t launch_schnorr_sign(uint8_t* sig64, uint8_t* pk32, uint8_t* ok, cons
 
 cudaError_t launch_rangeproof_verify(uint8_t* ok, uint64_t* minv, uint64_t* maxv, const uint8_t* commit33, const uint8_t* proofs, size_t stride,
                                      const uint32_t* plen, const uint8_t* gen64, size_t gen_stride, const uint8_t* extra, size_t extra_stride,
-                                     const uint32_t* extra_len, size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches, uint8_t* ev_out = nullptr);
+                                     const uint32_t* extra_len, size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches, uint8_t* ev_out = nullptr,
+                                     cudaMemPool_t pool = nullptr /* scratch of the three launches; nullptr = the device's default pool */);
 cudaError_t launch_rangeproof_rewind(uint8_t* ok, uint8_t* blind32, uint64_t* value, uint8_t* msg, size_t msg_stride, uint32_t* msg_len,
                                      const uint8_t* nonce32, const uint8_t* commit33, const uint8_t* proofs, size_t stride, const uint32_t* plen,
                                      const uint8_t* gen64, size_t gen_stride, const uint8_t* ev, uint8_t* scratch, size_t n, const gtable_dev& gt,
@@ -59,9 +60,10 @@ cudaError_t launch_halfagg_verify(uint8_t* d_ok, const uint8_t* d_pk32, const ui
                                   cudaStream_t s, uint64_t* launches);
 size_t msm_workspace_bytes(size_t n_terms);
 // out_mode 0: out = 64 bytes affine x||y big-endian; 1: out = 96 bytes Jacobian (x, y, z LE limbs, z = 0 <=> infinity) for launch_gej_sum.
-// window_bits 0 = chosen from n (msm_choose_c)
+// window_bits 0 = chosen from n (msm_choose_c).  shards > 1: only the bucket windows wi with wi % shards == shard are summed (window sharding:
+// every shard sees ALL terms; the Jacobian partial results of the shards add up to the MSM)
 cudaError_t launch_msm(uint8_t* out, int out_mode, const uint8_t* g_scalar32, const uint8_t* scalars32, const uint8_t* points64, size_t n,
-                       uint8_t* workspace, size_t workspace_bytes, int window_bits, cudaStream_t s, uint64_t* launches);
+                       uint8_t* workspace, size_t workspace_bytes, int window_bits, cudaStream_t s, uint64_t* launches, uint32_t shard = 0, uint32_t shards = 1);
 cudaError_t launch_unit_op(int op, uint8_t* out, const uint8_t* a, const uint8_t* b, size_t n, cudaStream_t s, uint64_t* launches);
 cudaError_t launch_gej_sum(uint8_t* out64, const uint8_t* partials96, size_t count, cudaStream_t s, uint64_t* launches);
 

@@ -50,12 +50,17 @@ struct msm_plan {
     uint32_t TB;       // total buckets = 2*HB (a multiple of 8)
     uint32_t Tp;       // entries per piece
     uint32_t N;        // terms incl. the generator slot (index N-1)
+    uint32_t shards;   // window sharding: this launch sums the windows wi (0 <= wi < 2 nw) with wi % shards == shard only;
+    uint32_t shard;    // the partial results of all shards add up to the MSM (shards = 1: everything)
 };
 
 HD uint32_t msm_ilog2(uint32_t x) { uint32_t r = 0; while (x > 1) { x >>= 1; r++; } return r; }
+HD bool msm_window_owned(const msm_plan& p, uint32_t wi) { return p.shards <= 1 || wi % p.shards == p.shard; }
 
-HD void msm_make_plan_c(msm_plan& p, size_t N, uint32_t c) {
+HD void msm_make_plan_c(msm_plan& p, size_t N, uint32_t c, uint32_t shard = 0, uint32_t shards = 1) {
     p.c = c;
+    p.shards = shards ? shards : 1;
+    p.shard = shard;
     p.nw = (128 + c - 1) / c;
     uint32_t t = 128 - c * (p.nw - 1);
     p.B = 1u << (c - 1);
@@ -69,7 +74,8 @@ HD void msm_make_plan_c(msm_plan& p, size_t N, uint32_t c) {
 #ifndef MSM_PIECE_SHIFT
 #define MSM_PIECE_SHIFT 19
 #endif
-    uint64_t e = ((uint64_t)2 * p.nw * N) >> MSM_PIECE_SHIFT;
+    const uint64_t own = p.shard < 2 * p.nw ? (2 * p.nw - p.shard + p.shards - 1) / p.shards : 0;      // windows of this shard
+    uint64_t e = ((own ? own : 1) * N) >> MSM_PIECE_SHIFT;
     uint32_t tp = MSM_PIECE_MIN;
     while (tp * 2 <= e && tp < MSM_PIECE_MAX) tp <<= 1;
     p.Tp = tp;
@@ -112,7 +118,7 @@ HD void msm_emit_digits(const msm_plan& p, const uint32_t* mag4, uint32_t neg, u
         uint32_t v = msm_bits128(mag4, pos, nb) + carry;
         uint32_t sgn = neg;
         if (w + 1 < p.nw && v > p.B) { v = (1u << p.c) - v; sgn ^= 1u; carry = 1; } else carry = 0;
-        if (v) emit(base + w * p.B + v - 1, sgn);
+        if (v && msm_window_owned(p, half * p.nw + w)) emit(base + w * p.B + v - 1, sgn);
     }
 }
 

@@ -71,6 +71,7 @@ def load_library():
     lib.secp256k1_b200_ecmult_multi.argtypes = [vp, u8p, u8p, u8p, u8p, sz]
     lib.secp256k1_b200_ecmult_multi_dev.argtypes = [vp, u8p, u8p, u8p, u8p, sz, vp, sz, vp]
     lib.secp256k1_b200_ecmult_multi_partial_dev.argtypes = [vp, u8p, u8p, u8p, u8p, sz, vp, sz, vp]
+    lib.secp256k1_b200_ecmult_multi_window_shard_dev.argtypes = [vp, u8p, u8p, u8p, u8p, sz, ctypes.c_uint, ctypes.c_uint, vp, sz, vp]
     lib.secp256k1_b200_ecmult_multi_combine_dev.argtypes = [vp, u8p, u8p, sz, vp]
     lib.secp256k1_b200_ecmult_multi_set_window.argtypes = [vp, ci]
     lib.secp256k1_b200_unit_op_batch.argtypes = [vp, ci, u8p, u8p, u8p, sz]
@@ -273,6 +274,11 @@ class Engine:
     def ecmult_multi_partial_dev(self, d_out96, d_g_scalar32, d_scalars32, d_points64, n, d_workspace, workspace_bytes, stream=0):
         """one shard of a sharded MSM: 96-byte Jacobian partial sum (no inversion); combine with ecmult_multi_combine_dev"""
         self._ck(self._lib.secp256k1_b200_ecmult_multi_partial_dev(self._h, d_out96, d_g_scalar32, d_scalars32, d_points64, n, d_workspace, workspace_bytes, stream))
+
+    def ecmult_multi_window_shard_dev(self, d_out96, d_g_scalar32, d_scalars32, d_points64, n, shard, shards, d_workspace, workspace_bytes, stream=0):
+        """one WINDOW shard of an MSM over all n terms (bucket windows wi with wi % shards == shard): 96-byte Jacobian partial result"""
+        self._ck(self._lib.secp256k1_b200_ecmult_multi_window_shard_dev(self._h, d_out96, d_g_scalar32, d_scalars32, d_points64, n, shard, shards,
+                                                                        d_workspace, workspace_bytes, stream))
 
     def ecmult_multi_combine_dev(self, d_out64, d_partials96, count, stream=0):
         self._ck(self._lib.secp256k1_b200_ecmult_multi_combine_dev(self._h, d_out64, d_partials96, count, stream))

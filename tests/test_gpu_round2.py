@@ -238,6 +238,36 @@ def test_msm_sharded_partial_and_combine(engine, ref):
     assert not out.cpu().numpy().any()
 
 
+def test_msm_window_shards_add_up(engine, ref):
+    """the other sharding (terms resident everywhere, bucket windows spread over the shards): for every shard count the partial results add up
+    to the reference's MSM -- with the generator term, with every dispatcher window width, also when there are more shards than windows"""
+    import torch
+    rnd = random.Random(59)
+    st = torch.cuda.current_stream().cuda_stream
+    try:
+        for m, c in ((3000, 0), (3000, 4), (5000, 13), (40000, 16), (9, 8)):
+            sc, pts = _msm_inputs(ref, rnd, m)
+            g = b32(rnd.getrandbits(256) % N)
+            ok, exp = ref.ecmult_multi(sc, pts, g, scratch_bytes=64 << 20)
+            assert ok == 1
+            sc_t = torch.frombuffer(bytearray(sc), dtype=torch.uint8).cuda()
+            pt_t = torch.frombuffer(bytearray(pts), dtype=torch.uint8).cuda()
+            g_t = torch.frombuffer(bytearray(g), dtype=torch.uint8).cuda()
+            wsb = engine.ecmult_multi_workspace_bytes(m)
+            ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+            engine.ecmult_multi_set_window(c)
+            for shards in (1, 2, 8, 5, 70):
+                parts = torch.zeros((shards, 96), dtype=torch.uint8, device="cuda")
+                for s in range(shards):
+                    engine.ecmult_multi_window_shard_dev(parts[s].data_ptr(), g_t.data_ptr(), sc_t.data_ptr(), pt_t.data_ptr(), m, s, shards, ws.data_ptr(), wsb, st)
+                out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+                engine.ecmult_multi_combine_dev(out.data_ptr(), parts.data_ptr(), shards, st)
+                torch.cuda.synchronize()
+                assert out.cpu().numpy().tobytes() == exp, (m, c, shards)
+    finally:
+        engine.ecmult_multi_set_window(0)
+
+
 def test_msm_adversarial_skew_time_and_value(engine, ref):
     """2^20 IDENTICAL scalars: every window has ONE bucket holding every term.  Value: k * sum(P_i).  Time: at most 2x the random-scalar
     MSM of the same size (pieces spread a hot bucket over the whole GPU; round 1 put it on one thread)."""
