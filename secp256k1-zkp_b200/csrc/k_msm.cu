@@ -46,7 +46,8 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct msm_caps { size_t emax, cap_multi, cap_parts, cap_units, nblk; };
 static msm_caps caps_of(const msm_plan& p) {
     msm_caps c;
-    c.emax = (size_t)2 * p.nw * p.N;
+    c.emax = (size_t)msm_windows_owned(p) * p.N;              // one entry per term and summed window at most (all 2 nw windows unless sharded)
+    if (c.emax == 0) c.emax = 1;
     c.cap_multi = c.emax / p.Tp + 1;
     c.cap_parts = 2 * (c.emax / p.Tp) + 2;
     c.cap_units = (c.emax < p.TB ? c.emax : p.TB) + c.emax / p.Tp + 1;

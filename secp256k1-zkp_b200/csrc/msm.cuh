@@ -56,6 +56,9 @@ struct msm_plan {
 
 HD uint32_t msm_ilog2(uint32_t x) { uint32_t r = 0; while (x > 1) { x >>= 1; r++; } return r; }
 HD bool msm_window_owned(const msm_plan& p, uint32_t wi) { return p.shards <= 1 || wi % p.shards == p.shard; }
+HD uint32_t msm_windows_owned(const msm_plan& p) {                       // how many of the 2 nw windows this launch sums (needs p.nw)
+    return p.shard < 2 * p.nw ? (2 * p.nw - p.shard + p.shards - 1) / p.shards : 0;
+}
 
 HD void msm_make_plan_c(msm_plan& p, size_t N, uint32_t c, uint32_t shard = 0, uint32_t shards = 1) {
     p.c = c;
@@ -74,7 +77,7 @@ HD void msm_make_plan_c(msm_plan& p, size_t N, uint32_t c, uint32_t shard = 0, u
 #ifndef MSM_PIECE_SHIFT
 #define MSM_PIECE_SHIFT 19
 #endif
-    const uint64_t own = p.shard < 2 * p.nw ? (2 * p.nw - p.shard + p.shards - 1) / p.shards : 0;      // windows of this shard
+    const uint64_t own = msm_windows_owned(p);
     uint64_t e = ((own ? own : 1) * N) >> MSM_PIECE_SHIFT;
     uint32_t tp = MSM_PIECE_MIN;
     while (tp * 2 <= e && tp < MSM_PIECE_MAX) tp <<= 1;

@@ -245,8 +245,13 @@ def test_msm_window_shards_add_up(engine, ref):
     rnd = random.Random(59)
     st = torch.cuda.current_stream().cuda_stream
     try:
-        for m, c in ((3000, 0), (3000, 4), (5000, 13), (40000, 16), (9, 8)):
-            sc, pts = _msm_inputs(ref, rnd, m)
+        for m, c in ((3000, 0), (3000, 4), (5000, 13), (40000, 16), (9, 8), (1 << 18, 0)):
+            if m <= 40000:
+                sc, pts = _msm_inputs(ref, rnd, m)
+            else:                                       # big enough that the piece size (and with it the workspace layout) depends on the shard count
+                _, p4k = _msm_inputs(ref, rnd, 4096)
+                pts = p4k * (m // 4096)
+                sc = b"".join(b32(rnd.getrandbits(256) % N) for _ in range(m))
             g = b32(rnd.getrandbits(256) % N)
             ok, exp = ref.ecmult_multi(sc, pts, g, scratch_bytes=64 << 20)
             assert ok == 1
