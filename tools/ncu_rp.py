@@ -48,6 +48,8 @@ def main():
             per, ["%.2f" % t for t in ts], per / min(ts), ev[0].elapsed_time(ev[1]) / 3, os.environ.get("SECP256K1_B200_LIB", "default")))
         return
 
+    if os.environ.get("RP_ONLY"):
+        return
     n = 1 << 18
     sk = np.frombuffer(b"".join(hashlib.sha256(b"ncu-sk%d" % i).digest() for i in range(4096)), dtype=np.uint8)
     msg = np.frombuffer(b"".join(hashlib.sha256(b"ncu-m%d" % i).digest() for i in range(4096)), dtype=np.uint8)
