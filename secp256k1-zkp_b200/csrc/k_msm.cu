@@ -298,17 +298,33 @@ __device__ __forceinline__ void load_gej_cg(gej& a, const gej_store* src) {     
 #ifndef MSM_SUM_OUTLINED_ADD
 #define MSM_SUM_INLINE_ADD 1
 #endif
+#ifndef MSM_SUM_STATIC_RANGES
+#define MSM_SUM_QUEUE 1            // r2r: 2^17 terms 1.089 -> 1.065 ms, 2^20 terms 3.439 -> 3.422 ms against one contiguous range per warp
+#endif
+#ifndef MSM_SUM_BATCH
+#define MSM_SUM_BATCH 32           // at most this many pieces per take (64: no gain at 2^20, 128: slower everywhere)
+#endif
 // (r2o: an accumulator in XYZZ coordinates -- madd-2008-s, 8M + 2S against 8M + 3S -- was measured and rejected: the fourth coordinate
 // pushes the loop over 128 registers, 3.95 ms against 3.45 ms for the 2^20-term MSM.)
 __global__ void __launch_bounds__(128, MSM_SUM_MINBLOCKS) k_msm_bucket_sum(msm_ws ws, msm_plan p, const uint8_t* __restrict__ points64, size_t n) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t P = ws.pbase[p.TB];
+#ifdef MSM_SUM_QUEUE
+    // the pieces are a global queue (counters[2]) from which a warp takes MSM_SUM_BATCH at a time: warps whose pieces are long (the top window of
+    // a half: several times fuller buckets) simply take fewer batches, and all warps run dry together
+    (void)wid;
+    uint32_t batch = P / (4 * nwarps);                            // small enough that every warp gets several batches
+    batch = batch < 1 ? 1 : (batch > MSM_SUM_BATCH ? MSM_SUM_BATCH : batch);
+    uint32_t next = 0, uend = 0;
+    bool drained = false;
+#else
     const uint32_t R = (P + nwarps - 1) / nwarps;                 // pieces per warp (contiguous range)
     uint64_t first = (uint64_t)wid * R;
     if (first >= P) return;                                       // whole warp
     uint32_t next = (uint32_t)first;
     const uint32_t uend = (first + R < P) ? (uint32_t)(first + R) : P;
+#endif
     bool have = false;
     uint32_t e = 0, eend = 0, dst = 0;
     gej acc;
@@ -317,6 +333,33 @@ __global__ void __launch_bounds__(128, MSM_SUM_MINBLOCKS) k_msm_bucket_sum(msm_w
     uint32_t nxt_neg = 0;                                         // its sign, applied when it is consumed (nothing waits on the load before that)
     nxt.inf = 1;
     while (true) {
+#ifdef MSM_SUM_QUEUE
+        uint32_t mask = __ballot_sync(0xffffffffu, !have);
+        while (mask) {                                                // warp-uniform: serve the lanes without a piece, refilling the batch when it runs dry
+            if (next >= uend) {
+                if (drained) break;
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&ws.counters[2], batch);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= P) { drained = true; break; }
+                next = base;
+                uend = (P - base < batch) ? P : base + batch;
+            }
+            const uint32_t avail = uend - next, rank = __popc(mask & ((1u << lane) - 1u));
+            if (!have && rank < avail) {
+                const uint4 d = *reinterpret_cast<const uint4*>(ws.units + next + rank);
+                e = d.x; eend = d.x + d.y; dst = d.z;
+                gej_set_infinity(acc);
+                const uint32_t v = d.w;                               // = ws.entries[e], copied into the descriptor by k_msm_units
+                msm_load_point(nxt, points64, n, ws.gpoint, v & 0x7FFFFFFFu);
+                nxt_neg = v >> 31;
+                have = true;
+            }
+            const uint32_t need = __popc(mask);
+            next += need < avail ? need : avail;
+            mask = __ballot_sync(0xffffffffu, !have);
+        }
+#else
         const uint32_t mask = __ballot_sync(0xffffffffu, !have);
         if (!have) {
             uint32_t my = next + __popc(mask & ((1u << lane) - 1u));
@@ -332,6 +375,7 @@ __global__ void __launch_bounds__(128, MSM_SUM_MINBLOCKS) k_msm_bucket_sum(msm_w
         }
         next += __popc(mask);
         if (next > uend) next = uend;
+#endif
         if (!__any_sync(0xffffffffu, have)) break;
         if (have) {
             ge pt = nxt;
