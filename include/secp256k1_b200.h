@@ -186,8 +186,8 @@ SECP256K1_B200_API int secp256k1_b200_ecmult_multi_partial_dev(secp256k1_b200_en
         const unsigned char *d_scalars32, const unsigned char *d_points64, size_t n, void *d_workspace, size_t workspace_bytes, void *stream);
 SECP256K1_B200_API int secp256k1_b200_ecmult_multi_combine_dev(secp256k1_b200_engine *e, unsigned char *d_out64, const unsigned char *d_partials96,
         size_t count, void *stream);
-/* The other way to shard an MSM whose terms are resident on EVERY GPU: by bucket windows.  Shard `shard` of `shards` sums the windows wi with
- * wi % shards == shard (of the 2 * ceil(128 / c) windows of the GLV-split scalars) over ALL n terms and leaves a 96-byte partial result like
+/* The other way to shard an MSM whose terms are resident on EVERY GPU: by bucket windows.  Shard `shard` of `shards` sums window j of the first GLV
+ * half and window nw - 1 - j of the second for every j with j % shards == shard (nw = ceil(128 / c) windows per half) over ALL n terms and leaves a 96-byte partial result like
  * _partial_dev; the partial results of all shards go through _combine_dev.  Against sharding by terms each GPU does 1/shards of the bucket
  * additions AND of the bucket reduction (which does not shrink with the number of terms); the price is that every GPU reads all terms. */
 SECP256K1_B200_API int secp256k1_b200_ecmult_multi_window_shard_dev(secp256k1_b200_engine *e, unsigned char *d_out96, const unsigned char *d_g_scalar32,

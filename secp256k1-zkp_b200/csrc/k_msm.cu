@@ -472,6 +472,11 @@ __global__ void __launch_bounds__(128, G4 ? 1 : 4) k_msm_r1(msm_ws ws, msm_plan 
     const bool valid = q < nchunks;
     if (!G4 && !valid) return;
     if (!valid) q = nchunks - 1;                      // G4: the whole warp stays (full-mask shuffles); surplus groups redo the last chunk
+    if (!G4 && p.shards > 1) {                        // window sharding: the chunks of another shard's windows are not summed here (k_msm_r2 skips them too)
+        msm_win cw;
+        msm_window_of_bucket(cw, p, q * MSM_CHUNK);
+        if (!msm_window_owned(p, cw.half * p.nw + cw.w)) return;
+    }
     const gej_store* s8 = ws.buckets + (size_t)q * MSM_CHUNK;
     gej running, acc;
     gej_set_infinity(running);

@@ -60,7 +60,7 @@ cudaError_t launch_halfagg_verify(uint8_t* d_ok, const uint8_t* d_pk32, const ui
                                   cudaStream_t s, uint64_t* launches);
 size_t msm_workspace_bytes(size_t n_terms);
 // out_mode 0: out = 64 bytes affine x||y big-endian; 1: out = 96 bytes Jacobian (x, y, z LE limbs, z = 0 <=> infinity) for launch_gej_sum.
-// window_bits 0 = chosen from n (msm_choose_c).  shards > 1: only the bucket windows wi with wi % shards == shard are summed (window sharding:
+// window_bits 0 = chosen from n (msm_choose_c).  shards > 1: only the bucket windows of shard `shard` are summed (msm_window_owned; window sharding:
 // every shard sees ALL terms; the Jacobian partial results of the shards add up to the MSM)
 cudaError_t launch_msm(uint8_t* out, int out_mode, const uint8_t* g_scalar32, const uint8_t* scalars32, const uint8_t* points64, size_t n,
                        uint8_t* workspace, size_t workspace_bytes, int window_bits, cudaStream_t s, uint64_t* launches, uint32_t shard = 0, uint32_t shards = 1);

@@ -55,9 +55,15 @@ struct msm_plan {
 };
 
 HD uint32_t msm_ilog2(uint32_t x) { uint32_t r = 0; while (x > 1) { x >>= 1; r++; } return r; }
-HD bool msm_window_owned(const msm_plan& p, uint32_t wi) { return p.shards <= 1 || wi % p.shards == p.shard; }
+// Window sharding: shard s sums window j of the first GLV half when j % shards == s, and window nw - 1 - j of the second: the top windows
+// (twice the buckets, the longest Horner chain) of the two halves go to different shards.
+HD bool msm_window_owned(const msm_plan& p, uint32_t wi) {
+    if (p.shards <= 1) return true;
+    const uint32_t j = wi < p.nw ? wi : 2 * p.nw - 1 - wi;
+    return j % p.shards == p.shard;
+}
 HD uint32_t msm_windows_owned(const msm_plan& p) {                       // how many of the 2 nw windows this launch sums (needs p.nw)
-    return p.shard < 2 * p.nw ? (2 * p.nw - p.shard + p.shards - 1) / p.shards : 0;
+    return p.shard < p.nw ? 2 * ((p.nw - p.shard + p.shards - 1) / p.shards) : 0;
 }
 
 HD void msm_make_plan_c(msm_plan& p, size_t N, uint32_t c, uint32_t shard = 0, uint32_t shards = 1) {
