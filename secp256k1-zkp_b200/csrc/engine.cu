@@ -600,7 +600,7 @@ int secp256k1_b200_bppp_norm_verify_batch_dev(secp256k1_b200_engine* e, unsigned
     if (!e) { set_error("engine is NULL"); return 0; }
     device_guard guard(e->device);
     CK(launch_bppp_norm_verify(d_ok, d_proofs, proof_stride, d_plen, d_transcripts104, d_rho32, d_gens64, (uint32_t)g_len, d_c_vec32, (uint32_t)h_len,
-                               d_commits64, n, e->gt(), (cudaStream_t)stream, &e->launches));
+                               d_commits64, n, e->gt(), (cudaStream_t)stream, &e->launches, e->pool));
     return 1;
 }
 int secp256k1_b200_bppp_norm_verify_batch(secp256k1_b200_engine* e, unsigned char* ok, const unsigned char* proofs, size_t proof_stride,

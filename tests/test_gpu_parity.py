@@ -638,6 +638,42 @@ def test_bppp_4096_batch_properties(engine):
     assert np.array_equal(ok, exp)
 
 
+def test_bppp_packed_large_batches_vs_reference(engine, ref):
+    """From 4096 proofs on, k_bppp_norm_verify_packed runs (4 proofs per warp, comb tables for the batch's generators built on the stream):
+    128 distinct reference-made arguments per geometry, 1/4 tampered at random positions (incl. malformed point encodings), tiled to 4224
+    items so that the four proofs of a warp differ and the last warp is ragged; accept bits against the reference's."""
+    L = ref.lib
+    L.secp256k1_bppp_generators_create.restype = ctypes.c_void_p
+    rnd = random.Random(67)
+    for (g, h) in [(16, 8), (8, 16), (32, 32), (1, 1), (64, 2), (2, 64)]:
+        n0 = 128 if g + h <= 32 else 32
+        gs = ctypes.c_void_p(L.secp256k1_bppp_generators_create(ref.ctx, ctypes.c_size_t(g + h)))
+        gxy = ctypes.create_string_buffer(64 * (g + h)); L.ref_bppp_generators_xy(gxy, gs)
+        proofs, rhos, cvs, cms, exp = [], [], [], [], []
+        for i in range(n0):
+            nv = b"".join(b32(rnd.getrandbits(256) % N) for _ in range(g)); lv = b"".join(b32(rnd.getrandbits(256) % N) for _ in range(h))
+            cv = b"".join(b32(rnd.getrandbits(256) % N) for _ in range(h)); rho = b32(rnd.getrandbits(256) % N or 1)
+            proof = ctypes.create_string_buffer(1000); plen = ctypes.c_size_t(1000); cm = ctypes.create_string_buffer(64)
+            assert L.ref_bppp_norm_prove(ref.ctx, proof, ctypes.byref(plen), cm, rho, gs, nv, ctypes.c_size_t(g), lv, cv, ctypes.c_size_t(h)) == 1
+            pr = bytearray(proof.raw[:plen.value])
+            if i % 4 == 1 and len(pr):
+                pr[rnd.randrange(len(pr))] ^= 1 << rnd.randrange(8)
+            if i % 16 == 6 and len(pr) >= 65:
+                pr[0] = 4                                   # malformed sign byte of the first point pair
+            e = L.ref_bppp_norm_verify(ref.ctx, bytes(pr), ctypes.c_size_t(len(pr)), cm.raw, rho, gs, ctypes.c_size_t(g), cv, ctypes.c_size_t(h))
+            proofs.append(bytes(pr)); rhos.append(rho); cvs.append(cv); cms.append(cm.raw); exp.append(e)
+        n = 4224 + 3                                        # >= 4096, not a multiple of 4
+        idx = [i % n0 for i in range(n)]
+        P = np.frombuffer(b"".join(proofs[i] for i in idx), dtype=np.uint8).reshape(n, -1)
+        rh = b"".join(rhos[i] for i in idx); cvv = b"".join(cvs[i] for i in idx); cmm = b"".join(cms[i] for i in idx)
+        tr = engine.bppp_transcripts(cmm, rh, gxy.raw, g, cvv, h, mode="tests")
+        got = engine.bppp_norm_verify(P, [P.shape[1]] * n, tr, rh, gxy.raw, g, cvv, h, cmm)
+        assert list(got) == [exp[i] for i in idx], (g, h)
+        small = engine.bppp_norm_verify(P[:n0], [P.shape[1]] * n0, tr[:n0], rh[:32 * n0], gxy.raw, g, cvv[:32 * h * n0], h, cmm[:64 * n0])
+        assert list(small) == exp, (g, h, "warp-per-proof kernel")
+        assert 0 < sum(exp) < n0
+
+
 def test_rangeproof_header_fuzz_vs_reference(engine, ref):
     """Every value of each of the first 11 proof bytes (header: flags/exp, mantissa, min_value, first sign byte) and
     truncated / extended lengths: accept bit AND min/max outputs must match the reference (SURVEY 8b edge semantics:
