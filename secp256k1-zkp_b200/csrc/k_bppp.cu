@@ -1,4 +1,5 @@
 // k_bppp.cu -- BP++ norm-product argument verification kernel (one warp per proof; see bppp.cuh).
+#include <stdlib.h>
 #include "bppp.cuh"
 #include "gtable.cuh"
 #include "ge_w10.cuh"
@@ -91,8 +92,8 @@ __global__ void __launch_bounds__(BP_WARPS * 32, 3) k_bppp_norm_verify(uint8_t* 
 // BPK_MIN_PROOFS proofs on, the launcher first builds an 8-bit comb table T_i[j][d] = d 2^(8j) P_i per generator on the stream (one warp per
 // generator: 31 x 8 doublings in lane form; then one thread per entry), and the verification kernel packs 4 proofs into a warp: 8 lanes per
 // proof, each with one of the proof's 8 variable points (a full a*P) and three generator terms (32 table additions each, no doublings).
-// r2t: 8192 distinct proofs 7.9 ms -> see profiles/.
-#define BPK_MIN_PROOFS 4096
+// r2t/r2v: 8192 distinct proofs 7.9 -> 4.15 ms; the packed path costs ~2 ms whatever the batch (0.7 ms of table build, then one warp's chain).
+#define BPK_MIN_PROOFS 2048        // r2v: 2048 proofs 1.99 ms packed against 2.48 ms warp-per-proof; 1024 proofs 1.99 against 1.25
 #define BPK_GW 8
 #define BPK_WINDOWS 32
 #define BPK_GEN_WORDS ((size_t)BPK_WINDOWS * 256 * 16)
@@ -226,7 +227,11 @@ cudaError_t launch_bppp_norm_verify(uint8_t* ok, const uint8_t* proofs, size_t s
                                     const uint8_t* rho32, const uint8_t* gens64, uint32_t g_len, const uint8_t* c_vec32, uint32_t h_len,
                                     const uint8_t* commits64, size_t n, const gtable_dev& gt, cudaStream_t s, uint64_t* launches, cudaMemPool_t pool) {
     if (n == 0) return cudaSuccess;
-    if (n >= BPK_MIN_PROOFS && g_len + h_len <= 128 && g_len && h_len) {
+    static const size_t pack_min = [] {                                     // development knob: where the packed kernel takes over
+        const char* v = getenv("SECP256K1_B200_BPPP_PACK_MIN");
+        return v && *v ? (size_t)strtoull(v, nullptr, 10) : (size_t)BPK_MIN_PROOFS;
+    }();
+    if (n >= pack_min && g_len + h_len <= 128 && g_len && h_len) {
         const uint32_t count = g_len + h_len;
         const size_t tab_bytes = (size_t)count * BPK_GEN_WORDS * 4, base_bytes = (size_t)count * BPK_WINDOWS * sizeof(bpk_base);
         uint8_t* mem = nullptr;
