@@ -162,9 +162,9 @@ int emu_pedersen_commit(uint8_t* out33, const uint8_t* blind32, uint64_t value, 
 struct emu_emit_hist { std::vector<uint32_t>* h; void operator()(uint32_t b, uint32_t) { (*h)[b]++; } };
 struct emu_emit_scatter { std::vector<uint32_t>* off; std::vector<uint32_t>* h; std::vector<uint32_t>* ent; uint32_t idx;
     void operator()(uint32_t b, uint32_t sgn) { uint32_t pos = (*off)[b] + ((*h)[b]--) - 1u; (*ent)[pos] = idx | (sgn << 31); } };
-int emu_msm2(uint8_t* out64, const uint8_t* g_sc32, const uint8_t* scalars32, const uint8_t* points64, size_t n, int c, uint32_t tp) {
+static void emu_msm_core(gej& r, const uint8_t* g_sc32, const uint8_t* scalars32, const uint8_t* points64, size_t n, int c, uint32_t tp, uint32_t shard, uint32_t shards) {
     const size_t N = n + 1;
-    msm_plan p; msm_make_plan_c(p, N, c ? (uint32_t)c : msm_choose_c(N));
+    msm_plan p; msm_make_plan_c(p, N, c ? (uint32_t)c : msm_choose_c(N), shard, shards);
     if (tp) p.Tp = tp;
     std::vector<uint32_t> k12(N * 8), hist(p.TB, 0), off(p.TB + 1), pbase(p.TB + 1), mbase(p.TB + 1), multi, entries((size_t)2 * p.nw * N);
     std::vector<uint8_t> flags(N);
@@ -229,11 +229,25 @@ int emu_msm2(uint8_t* out64, const uint8_t* g_sc32, const uint8_t* scalars32, co
         uint32_t maxbits = msm_ilog2((p.B > p.Btop ? p.B : p.Btop) / MSM_CHUNK);
         msm_window_from_sums(W[wi], T.data() + (size_t)wi * MSM_MAX_SUMS * MSM_R2_PARTS, MSM_R2_PARTS, nbits);
     }
-    gej H[2], r;
+    gej H[2];
     msm_horner_half(H[0], W.data(), p);
     msm_horner_half(H[1], W.data() + p.nw, p);
     msm_join_halves(r, H[0], H[1]);
+}
+int emu_msm2(uint8_t* out64, const uint8_t* g_sc32, const uint8_t* scalars32, const uint8_t* points64, size_t n, int c, uint32_t tp) {
+    gej r;
+    emu_msm_core(r, g_sc32, scalars32, points64, n, c, tp, 0, 1);
     return gej_to_xy64(out64, r);
+}
+// window sharding (secp256k1_b200_ecmult_multi_window_shard_dev): every shard over all terms, the partial results added
+int emu_msm_window_shards(uint8_t* out64, const uint8_t* g_sc32, const uint8_t* scalars32, const uint8_t* points64, size_t n, int c, uint32_t shards) {
+    gej tot; gej_set_infinity(tot);
+    for (uint32_t s = 0; s < shards; s++) {
+        gej r, t;
+        emu_msm_core(r, g_sc32, scalars32, points64, n, c, 0, s, shards);
+        gej_add(t, tot, r); tot = t;
+    }
+    return gej_to_xy64(out64, tot);
 }
 int emu_msm(uint8_t* out64, const uint8_t* g_sc32, const uint8_t* scalars32, const uint8_t* points64, size_t n) { return emu_msm2(out64, g_sc32, scalars32, points64, n, 0, 0); }
 int emu_msm_choose_c(size_t N) { return (int)msm_choose_c(N); }

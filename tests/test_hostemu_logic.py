@@ -287,6 +287,16 @@ def test_msm_pipeline_logic(emu, ref):
             emu.emu_msm2(out, g, sc if m else None, pts if m else None, m, c, tp)
             ok, exp = ref.ecmult_multi(sc, pts, g, scratch_bytes=1 << 22)
             assert ok == 1 and out.raw == exp, (m, c, tp, g is None)
+    # window sharding: the partial results of the shards add up to the MSM, whatever the number of shards (more shards than windows included)
+    emu.emu_msm_window_shards.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32]
+    for (m, c) in ((60, 0), (40, 4), (33, 16), (21, 11)):
+        sc, pts = _msm_case(rnd, ref, m)
+        g = b32(rnd.getrandbits(256) % N)
+        ok, exp = ref.ecmult_multi(sc, pts, g, scratch_bytes=1 << 22)
+        for shards in (1, 2, 3, 8, 70):
+            out = ctypes.create_string_buffer(64)
+            emu.emu_msm_window_shards(out, g, sc, pts, m, c, shards)
+            assert ok == 1 and out.raw == exp, (m, c, shards)
     # the dispatcher: window width grows with n, c = 8 below 2^11 terms, 16 at 2^20
     cs = [emu.emu_msm_choose_c(ctypes.c_size_t(n)) for n in (1, 88, 2048, 1 << 13, 1 << 15, 1 << 17, 1 << 20, 1 << 24)]
     assert cs == [8, 8, 8, 10, 11, 12, 16, 16], cs
