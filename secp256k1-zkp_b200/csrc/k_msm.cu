@@ -6,11 +6,13 @@
 //   k_msm_scan_a/_b   two-level exclusive scan of the histogram: entry offsets, piece offsets, part offsets, list of multi-piece buckets
 //   k_msm_scatter     thread per term: counting-sort scatter of (term index | sign) by (window,bucket)
 //   k_msm_units       thread per piece: piece -> (first entry, count, destination)
-//   k_msm_bucket_sum  persistent warps, one lane per piece, lanes pull the next piece when theirs is done (mixed additions)
+//   k_msm_bucket_sum  persistent warps take batches of pieces from a global queue; one lane per piece, lanes pull the next piece when theirs
+//                     is done (mixed additions)
 //   k_msm_combine     block per multi-piece (hot) bucket: strided partial sums + warp-shuffle tree
 //   k_msm_r1          running sums over chunks of 8 buckets (thread per chunk, or 4 lanes per chunk when chunks are few)
 //   k_msm_r2          block per (window, sum): plain sum of the chunk L's, bit sums of the chunk A's
-//   k_msm_tail        one block: per-window bit-Horner (4 lanes per window), two window-Horner chains (4 lanes each), join, to affine
+//   k_msm_tail        one block: per-window bit-Horner (a warp per window), two window-Horner chains (a warp per GLV half), join, to affine --
+//                     all in the lane form of ge_w10.cuh (one 26-bit limb of every coordinate per lane)
 #ifndef MSM_G4_OUTLINED
 #define B200_G4_INLINE 1          // the 4-lane group operations inlined into the (few) latency-bound loops of this file
 #endif

@@ -20,7 +20,8 @@
 //   running-sum reduction (:581-588), serial               chunks of 8 buckets (running sum, all chunks in parallel), then per window
 //                                                          sum_q L_q + 8*sum_q q*A_q with the second sum taken bit by bit (tree sums)
 //   Horner over the windows (:536-589), serial              two Horner chains (one per GLV half) side by side, every doubling / addition
-//                                                          spread over 4 lanes (ge_g4.cuh), then R = A + lambda(B)
+//                                                          spread over a whole warp (ge_w10.cuh: one 26-bit limb per lane), then R = A + lambda(B)
+//   one MSM = one machine                                   shards by terms (partial sums, msm.cuh is unchanged) or by bucket windows (msm_window_owned)
 // Only the final point has to match the reference; it does because the group element is unique.
 #pragma once
 #include "gtable.cuh"
