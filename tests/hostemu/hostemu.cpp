@@ -153,6 +153,13 @@ int emu_rangeproof_rewind(uint8_t* blind32, uint64_t* value, uint8_t* msg, size_
     memcpy(blind32, bl, 32); *value = v; *msg_len = ml;
     return 1;
 }
+// the ring challenge hash with its two word-assembled layouts (e of 32 / 33 bytes) and the generic byte path (any other length)
+int emu_borromean_challenge(uint8_t* out32, const uint8_t* e, uint32_t elen, const uint8_t* m32, uint32_t ring, uint32_t idx) {
+    sc s;
+    int ov = rp_borromean_challenge(s, e, elen, m32, ring, idx);
+    sc_get_b32(out32, s);
+    return ov;
+}
 int emu_pedersen_commit(uint8_t* out33, const uint8_t* blind32, uint64_t value, const uint8_t* gen64) {
     return pedersen_commit_item(out33, blind32, value, gen64, g_gt);
 }

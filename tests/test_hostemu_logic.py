@@ -271,6 +271,22 @@ def _msm_case(rnd, ref, m, same_scalar_from=None):
 LAMBDA = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
 
 
+def test_borromean_challenge_hash_layouts(emu):
+    """borromean_hash (src/modules/rangeproof/borromean_impl.h:23-37) = SHA256(e || m || be32(ring) || be32(idx)) reduced mod n: the kernels
+    assemble the two blocks as words for e of 32 bytes (e0) and 33 bytes (a serialized point); any other length takes the byte path"""
+    rnd = random.Random(31)
+    emu.emu_borromean_challenge.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32]
+    for _ in range(300):
+        for elen in (32, 33, 20, 64):
+            e = bytes(rnd.getrandbits(8) for _ in range(elen))
+            m = bytes(rnd.getrandbits(8) for _ in range(32))
+            ring, idx = rnd.choice([0, 1, 31, 0x01020304, 0xFFFFFFFF]), rnd.choice([0, 3, 0x80000000, 0xA1B2C3D4])
+            out = ctypes.create_string_buffer(32)
+            ov = emu.emu_borromean_challenge(out, e, elen, m, ring, idx)
+            d = int.from_bytes(hashlib.sha256(e + m + ring.to_bytes(4, "big") + idx.to_bytes(4, "big")).digest(), "big")
+            assert int.from_bytes(out.raw, "big") == d % N and ov == int(d >= N), (elen, ring, idx)
+
+
 def test_msm_pipeline_logic(emu, ref):
     """(also covers MSM_R2_PARTS > 1: c = 16 has 8192 chunk sums in the top window)
     the GPU MSM pipeline (k_msm.cu) executed sequentially on the host: every window width, forced small pieces (multi-piece buckets +
